@@ -1,0 +1,155 @@
+"""CPU suite: the oracle against the committed reference fixtures and the
+brute-force walk enumeration.  No GPU, no /root/reference."""
+import numpy as np
+import pytest
+
+from golden_util import CASES, load_case, oracle_kwargs
+from oracle.walk_bruteforce import random_temporal_graph, sum_walk_matrices
+from oracle.walk_projection import WalkProjectionOracle, decay_factors, edge_weights, projection_dim
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_oracle_bit_exact_against_reference_fixture(name):
+    z, cfg, batches = load_case(name)
+    kw = oracle_kwargs(cfg)
+    o = WalkProjectionOracle(p0=None if kw['use_matrix'] else z['p0'], **kw)
+    assert o.dim == int(z['dim'])
+    L = kw['num_layer']
+    for b, (s, d, t, w) in enumerate(batches):
+        o.update(s, d, t, weights=w)                 # the reference's own torch-exp weights
+        if b == 0:
+            for i in range(1, L + 1):
+                assert np.array_equal(o.P[i], z[f'after0_P{i}'])
+        if 'backup_now' in z.files and False:
+            pass
+    for i in range(1, L + 1):
+        assert np.array_equal(o.P[i], z[f'final_P{i}']), f'layer {i}'
+    assert o.now_time == z['final_now']
+    assert np.array_equal(o.P[0], z['p0']), 'P_0 must never be written by update'
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_oracle_own_weights_close_to_reference(name):
+    z, cfg, batches = load_case(name)
+    kw = oracle_kwargs(cfg)
+    o = WalkProjectionOracle(p0=None if kw['use_matrix'] else z['p0'], **kw)
+    for s, d, t, w in batches:
+        w_own = edge_weights(t, t[-1], kw['time_decay_weight'])
+        # torch's exp is 1-ulp: never more than one ulp away from the correctly rounded value
+        assert np.all(np.abs(w_own.astype(np.float64) - w) <= np.spacing(np.maximum(w_own, w)))
+        o.update(s, d, t)
+    for i in range(1, kw['num_layer'] + 1):
+        np.testing.assert_allclose(o.P[i], z[f'final_P{i}'], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_oracle_pairwise_and_gather(name):
+    z, cfg, batches = load_case(name)
+    kw = oracle_kwargs(cfg)
+    o = WalkProjectionOracle(p0=None if kw['use_matrix'] else z['p0'], **kw)
+    for s, d, t, w in batches:
+        o.update(s, d, t, weights=w)
+    a, b, ref = z['pair_a'], z['pair_b'], z['pair_feat']
+    got = o.pair_wise_gram(a, b)
+    assert got.shape == ref.shape == (len(a), (2 * kw['num_layer'] + 2) ** 2)
+    if kw['not_scale']:
+        scale = o.pair_norm_bound(a, b)
+        assert np.all(np.abs(got - ref) <= 1e-5 * np.abs(ref) + 2e-6 * scale)
+    else:
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6)
+        assert np.all(ref >= 0)                       # clamp + log(x+1) is non-negative
+    rows = o.get_random_projections(a)
+    assert len(rows) == kw['num_layer'] + 1 and rows[0].shape == (len(a), o.dim)
+
+
+@pytest.mark.parametrize('name', ['wiki_tiny', 'flights_tiny'])
+def test_oracle_backup_reload(name):
+    z, cfg, batches = load_case(name)
+    kw = oracle_kwargs(cfg)
+    L = kw['num_layer']
+    o = WalkProjectionOracle(p0=z['p0'], **kw)
+    nb = len(batches)
+    saved = None
+    for b, (s, d, t, w) in enumerate(batches):
+        o.update(s, d, t, weights=w)
+        if f'backup_P1' in z.files and saved is None:
+            # find the batch the fixture backed up at by matching the clock
+            if o.now_time == z['backup_now']:
+                ok = all(np.array_equal(o.P[i], z[f'backup_P{i}']) for i in range(1, L + 1))
+                if ok:
+                    saved = o.backup()
+    assert saved is not None
+    p0_before = o.P[0].copy()
+    o.reload(saved)
+    assert o.now_time == z['backup_now']
+    s, d, t, _ = batches[-1]
+    o.update(s, d, t, weights=z['after_reload_w'])
+    for i in range(1, L + 1):
+        assert np.array_equal(o.P[i], z[f'after_reload_P{i}'])
+    assert np.array_equal(o.P[0], p0_before)
+
+
+def test_layers_consume_pre_batch_state():
+    """Layer independence within a batch (reference processes layers top-down,
+    TPNet.py:90): after the first batch P_2.. are still all zero."""
+    z, cfg, batches = load_case('reddit_tiny')
+    assert np.any(z['after0_P1'] != 0)
+    assert not np.any(z['after0_P2']) and not np.any(z['after0_P3'])
+
+
+def test_clock_is_last_element_not_max():
+    kw = dict(node_num=6, edge_num=10, dim_factor=1, num_layer=1, time_decay_weight=0.1, use_matrix=False,
+              beginning_time=0.0, not_scale=True, enforce_dim=4)
+    o = WalkProjectionOracle(**kw)
+    o.update(np.array([1, 2]), np.array([3, 4]), np.array([9.0, 5.0]))
+    assert o.now_time == 5.0
+
+
+def test_empty_batch_raises_like_reference():
+    kw = dict(node_num=6, edge_num=10, dim_factor=1, num_layer=1, time_decay_weight=0.1, use_matrix=False,
+              beginning_time=0.0, not_scale=True, enforce_dim=4)
+    o = WalkProjectionOracle(**kw)
+    e = np.array([], dtype=np.int64)
+    with pytest.raises(IndexError):
+        o.update(e, e, np.array([], dtype=np.float64))
+    with pytest.raises(IndexError):
+        o.update(np.array([1]), np.array([6]), np.array([1.0]))
+
+
+def test_dim_rule():
+    assert projection_dim(9228, 157475, 10, -1, False) == 120      # Wikipedia shape
+    assert projection_dim(10985, 672448, 10, -1, False) == 140     # Reddit shape
+    assert projection_dim(13170, 1927146, 10, -1, False) == 150    # Flights shape
+    assert projection_dim(50, 157475, 10, -1, False) == 50         # capped by node_num
+    assert projection_dim(50, 10, 10, 64, False) == 64
+    assert projection_dim(50, 10, 10, 64, True) == 50
+
+
+def test_decay_factor_rounding():
+    c = decay_factors(1e-6, 3400.0, 0.0, 3)
+    base = np.exp(-1e-6 * 3400.0)
+    assert c.dtype == np.float32 and c[2] == np.float32(base ** 3)
+    assert np.all(decay_factors(1e-6, 7.0, 7.0, 3) == 1.0)
+
+
+def test_bruteforce_kat_fresh_graph():
+    """The notebook's known-answer test on a freshly drawn graph (cell 10)."""
+    rng = np.random.default_rng(7)
+    N, E, L, lam, B = 16, 60, 3, 1e-4, 5
+    s, d, _ = random_temporal_graph(N, E, rng)
+    t = np.repeat(np.arange(1, E // B + 1), B).astype(np.float64)
+    o = WalkProjectionOracle(node_num=N, edge_num=E, dim_factor=1, num_layer=L, time_decay_weight=lam,
+                             use_matrix=True, beginning_time=0.0, not_scale=True, enforce_dim=-1)
+    for i in range(0, E, B):
+        o.update(s[i:i + B], d[i:i + B], t[i:i + B])
+    brute = sum_walk_matrices(s, d, t, L, lam, N)
+    for j in range(L + 1):
+        shifted = o.P[j].astype(np.float64) * np.power(np.exp(-lam), j)
+        np.testing.assert_allclose(shifted, brute[j], rtol=1e-5, atol=1e-5)
+
+
+def test_bruteforce_fixture():
+    z = np.load(__import__('os').path.join(__import__('golden_util').GOLDEN_DIR, 'matrix_kat_brute.npz'))
+    brute = sum_walk_matrices(z['src'], z['dst'], z['t'], 3, 1e-4, 24)
+    for j in range(4):
+        np.testing.assert_allclose(brute[j], z[f'A{j}'], rtol=1e-12)
