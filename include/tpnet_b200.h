@@ -1,0 +1,154 @@
+/*
+ * tpnet_b200 — C ABI of the B200 (sm_100a) temporal-walk-matrix projection library.
+ *
+ * This is the drop-in boundary for ONE hot path of lxd99/TPNet: the state and
+ * operations of `RandomProjectionModule` (reference: models/TPNet.py:9-157).
+ * The reference has no FFI of its own (it is pure PyTorch); each entry point
+ * below names the reference lines it replaces.  The Python host side
+ * (tpnet_b200/random_projection.py) binds these symbols with ctypes and passes
+ * `tensor.data_ptr()` values and the current CUDA stream; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", POD arguments only; every pointer named `*_dev`/documented as
+ *     device memory is a CUDA device pointer on the current device, everything
+ *     else is host memory.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     never synchronises, never allocates; scratch memory is supplied by the
+ *     caller (size from tpn_update_workspace_bytes).
+ *   - return value: TPN_OK (0) or a negative TPN_ERR_* code; never throws.
+ *   - node ids are int64, 0 <= id < num_nodes (id 0 is the reference's padding
+ *     node: P_0[0] random, P_{>=1}[0] zero — it is an ordinary row here).
+ *
+ * State layout in HBM (node-major, one contiguous block per node):
+ *     value of layer l (0..L), column k (0..dim) of node u  =
+ *         data[u * node_stride + l * row_stride + k]
+ *   row_stride  >= dim,  multiple of 4 floats (16 B) so rows are float4-addressable;
+ *   node_stride >= (L+1) * row_stride, multiple of 4.
+ *   Columns [dim, row_stride) of every row MUST be zero (the kernels rely on it
+ *   and preserve it).
+ *   With this layout the reference's "P_i[u] += P_{i-1}[v] * w for i = L..1"
+ *   (TPNet.py:90-96) is ONE contiguous axpy of L*row_stride floats per message,
+ *   and the 2L+2 rows a pair-wise feature needs (TPNet.py:119-121) are two
+ *   contiguous blocks.
+ *
+ * Time decay (TPNet.py:83-85).  The reference multiplies every row of layers
+ * 1..L by the fp32 scalar c_l = f32(exp(-lambda*dt)^l) at EVERY update.  Two
+ * bit-identical realisations:
+ *   eager : stamps == NULL.  tpn_update sweeps the whole state once per call.
+ *   lazy  : stamps != NULL.  tpn_update appends (c_1..c_L) to `decay_log` as a
+ *           new epoch and touches only the rows of the batch.  A row stored at
+ *           epoch s is brought current by replaying, in order, the logged fp32
+ *           factors of epochs s+1..epoch — the same rounded multiply chain the
+ *           reference executed eagerly, so results are bit-identical, with no
+ *           N-proportional traffic.  Every reader (update / pairwise / gather)
+ *           replays on the fly; tpn_materialize writes all rows back current.
+ */
+#ifndef TPNET_B200_H_
+#define TPNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPN_ABI_VERSION 1
+
+#define TPN_MAX_LAYERS 4
+
+enum {
+    TPN_OK = 0,
+    TPN_ERR_INVALID_ARGUMENT = -1,   /* null pointer, bad shape, misaligned stride            */
+    TPN_ERR_WORKSPACE_TOO_SMALL = -2,
+    TPN_ERR_LOG_FULL = -3,           /* lazy mode: decay_log has no free epoch (materialise)   */
+    TPN_ERR_CUDA = -4,               /* a CUDA runtime call failed; see tpn_last_cuda_error()   */
+    TPN_ERR_UNSUPPORTED = -5         /* num_layer outside 1..TPN_MAX_LAYERS                     */
+};
+
+/* The L+1 projection matrices P_0..P_L of the reference's
+ * `self.random_projections` (TPNet.py:39-62) plus the lazy-decay bookkeeping. */
+typedef struct tpn_state {
+    float*   data;          /* device, [num_nodes][node_stride] fp32                           */
+    int64_t  num_nodes;     /* N, including the padding node 0                                 */
+    int32_t  num_layer;     /* L, 1..TPN_MAX_LAYERS                                            */
+    int32_t  dim;           /* d, logical row width (TPNet.py:30-33,45)                        */
+    int64_t  row_stride;    /* floats, multiple of 4, >= dim                                   */
+    int64_t  node_stride;   /* floats, multiple of 4, >= (L+1)*row_stride                      */
+    int32_t* stamps;        /* device, [num_nodes][L] epoch of last write of layer 1..L; NULL = eager */
+    float*   decay_log;     /* device, [log_capacity][L]; row e = factors applied entering epoch e */
+    int64_t  log_capacity;  /* rows in decay_log (row 0 unused)                                */
+    int64_t  epoch;         /* current epoch (0 = nothing logged); advanced by tpn_update      */
+} tpn_state_t;
+
+int tpn_version(void);
+const char* tpn_error_string(int code);
+/* text of the last CUDA error seen by this library on the calling thread ("" if none) */
+const char* tpn_last_cuda_error(void);
+/* SM count / compute capability of the current device (checks the library can run here). */
+int tpn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Scratch bytes tpn_update needs for a batch of `batch` edges (monotone in batch). */
+size_t tpn_update_workspace_bytes(int64_t batch);
+
+/*
+ * RandomProjectionModule.update — TPNet.py:67-99.
+ *   src_dev, dst_dev : int64[batch] device   (TPNet.py:74-75)
+ *   t_dev            : float64[batch] device (cast to fp32 inside, TPNet.py:77)
+ *   t_last           : node_interact_times[-1] (the LAST element, TPNet.py:76)
+ *   neg_lambda       : f32(-time_decay_weight)
+ *   decay            : HOST pointer to c_1..c_L = f32(pow(exp(-lambda*(t_last-now)), l))
+ *                      computed in f64 by the caller exactly as TPNet.py:84-85 does,
+ *                      or NULL when the clock did not move (all factors are 1.0).
+ *   err_flag_dev     : optional device int32; set to 1 if an id was out of range
+ *                      (such edges are dropped).  May be NULL.
+ * Semantics: weights w_j (TPNet.py:78); decay (eager sweep or new lazy epoch);
+ * for every layer i = L..1 and every target row, messages are added one at a
+ * time in the reference's order — first the row's occurrences as `src` in batch
+ * order, then its occurrences as `dst` (the two scatter_add_ of TPNet.py:93-96)
+ * — with the product rounded to fp32 before the add, no atomics, no FMA
+ * contraction.  Layer i reads the pre-batch (decayed) layer i-1.
+ * The caller's `now_time` bookkeeping (TPNet.py:99) stays on the host.
+ */
+int tpn_update(tpn_state_t* st,
+               const int64_t* src_dev, const int64_t* dst_dev, const double* t_dev, int64_t batch,
+               double t_last, float neg_lambda, const float* decay,
+               void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, void* stream);
+
+/*
+ * Input of `self.mlp` in RandomProjectionModule.get_pair_wise_feature —
+ * TPNet.py:112-129 without the trainable head (which stays in PyTorch).
+ *   a_ids_dev, b_ids_dev : int64[n] device
+ *   out_dev              : float32[n][(2L+2)^2] device, row-major (r, c) over the
+ *                          rows [a:P_0..P_L, b:P_0..P_L]                (TPNet.py:119-123)
+ *   apply_log_scale      : 1 -> clamp at 0 then log(x + 1.0)   (TPNet.py:127-128)
+ *                          0 -> raw inner products             (`not_scale`, :124-125)
+ */
+int tpn_pairwise(const tpn_state_t* st, const int64_t* a_ids_dev, const int64_t* b_ids_dev, int64_t n,
+                 int apply_log_scale, float* out_dev, void* stream);
+
+/*
+ * RandomProjectionModule.get_random_projections — TPNet.py:101-110.
+ *   out_dev : float32[L+1][n][dim] device (layer-major, so out_dev + l*n*dim is the
+ *             l-th [n, dim] tensor of the returned list)
+ */
+int tpn_gather(const tpn_state_t* st, const int64_t* ids_dev, int64_t n, float* out_dev, void* stream);
+
+/*
+ * Lazy mode only: replay the pending decay of EVERY row, write it back and set
+ * all stamps to the current epoch (used before backup / state_dict / when the
+ * log is full; afterwards the caller may reset epoch to 0 with tpn_reset_epoch).
+ * No-op in eager mode.
+ */
+int tpn_materialize(tpn_state_t* st, void* stream);
+/* Lazy mode: after tpn_materialize, restart the log (stamps <- 0, epoch <- 0). */
+int tpn_reset_epoch(tpn_state_t* st, void* stream);
+
+/* Zero layers 1..L of every node and all stamps; epoch <- 0 (reset_random_projections,
+ * TPNet.py:135-136; P_0 is re-drawn by the caller with torch's RNG, TPNet.py:139). */
+int tpn_clear_walk_layers(tpn_state_t* st, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPNET_B200_H_ */

@@ -70,6 +70,8 @@ def decay_factors(lam: float, t_last: float, now: float, num_layer: int) -> np.n
 class WalkProjectionOracle:
     """State + operations of the reference module, numpy/fp32, CPU only."""
 
+    LOOP_MAX = 512      # batches up to this size use the explicit Python loop
+
     def __init__(self, node_num: int, edge_num: int, dim_factor: int, num_layer: int,
                  time_decay_weight: float, use_matrix: bool, beginning_time: float,
                  not_scale: bool, enforce_dim: int, p0: Optional[np.ndarray] = None,
@@ -141,10 +143,17 @@ class WalkProjectionOracle:
             msg_to_src = below[dst] * w[:, None]                 # gathered BEFORE either scatter
             msg_to_dst = below[src] * w[:, None]
             tgt = self.P[i]
-            for j in range(src.shape[0]):                        # batch order per target row
-                tgt[src[j]] += msg_to_src[j]
-            for j in range(dst.shape[0]):
-                tgt[dst[j]] += msg_to_dst[j]
+            if src.shape[0] <= self.LOOP_MAX:
+                for j in range(src.shape[0]):                    # batch order per target row
+                    tgt[src[j]] += msg_to_src[j]
+                for j in range(dst.shape[0]):
+                    tgt[dst[j]] += msg_to_dst[j]
+            else:
+                # ufunc.at is unbuffered and applies the operands one index at a time in
+                # index order — the same sequential fp32 adds as the loop above
+                # (tests/test_oracle.py::test_add_at_equals_loop), just not in Python
+                np.add.at(tgt, src, msg_to_src)
+                np.add.at(tgt, dst, msg_to_dst)
         self.now_time = t_last
 
     # ---------------------------------------------------------------- reads

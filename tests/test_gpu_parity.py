@@ -1,0 +1,376 @@
+"""GPU suite (-m gpu): the CUDA path, called through the drop-in module and the raw
+C ABI, against the oracle (oracle/) and the committed reference fixtures.
+
+Tolerances (north_star: fp32 rtol 1e-5):
+  * projections after `update`: rtol 1e-5, atol 1e-6.  Bit-exact whenever the edge
+    weights are exactly representable (equal timestamps in a batch -> w == 1), because
+    everything else follows the reference's rounding points and summation order.
+  * pair-wise features: |err| <= 1e-5*|ref| + 2e-6*||x_r||*||x_c|| / (1 + max(G,0)) —
+    rtol 1e-5 plus the Cauchy-Schwarz floor any fp32 dot product of those rows has
+    (the reference's own batched GEMM is only reproducible to that floor).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASES, load_case, oracle_kwargs
+from oracle.walk_projection import WalkProjectionOracle
+from tpnet_b200 import RandomProjectionModule, _lib
+import tpnet_b200.random_projection as rpmod
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+MODES = ['eager', 'lazy']
+
+
+def module_from_cfg(kw, p0, mode):
+    m = RandomProjectionModule(device=DEV, beginning_time=np.float64(kw['beginning_time']), decay_mode=mode,
+                               **{k: v for k, v in kw.items() if k != 'beginning_time'})
+    if not kw['use_matrix']:
+        m.random_projections[0].data.copy_(torch.from_numpy(p0))
+    return m.to(DEV)
+
+
+def layers(m):
+    m.materialize()
+    return [p.data.cpu().numpy() for p in m.random_projections]
+
+
+def pair_tol(oracle, a, b, ref_raw):
+    scale = oracle.pair_norm_bound(a, b)
+    return scale / (1.0 + np.maximum(ref_raw, 0))
+
+
+# --------------------------------------------------------------------------- fixtures of the reference
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('name', CASES)
+def test_update_matches_reference_fixture(name, mode):
+    z, cfg, batches = load_case(name)
+    kw = oracle_kwargs(cfg)
+    m = module_from_cfg(kw, z['p0'], mode)
+    L = kw['num_layer']
+    exact = all(np.all(w == 1.0) for _, _, _, w in batches)
+    for b, (s, d, t, w) in enumerate(batches):
+        m.update(s, d, t)
+        if b == 0:
+            got = layers(m)
+            for i in range(1, L + 1):
+                np.testing.assert_allclose(got[i], z[f'after0_P{i}'], rtol=1e-5, atol=1e-6)
+            for i in range(2, L + 1):
+                assert not got[i].any(), 'layer i must consume the PRE-batch layer i-1 (TPNet.py:90)'
+    got = layers(m)
+    assert np.array_equal(got[0], z['p0']), 'P_0 is never written by update'
+    for i in range(1, L + 1):
+        if exact:
+            assert np.array_equal(got[i], z[f'final_P{i}']), f'layer {i} not bit-exact'
+        else:
+            np.testing.assert_allclose(got[i], z[f'final_P{i}'], rtol=1e-5, atol=1e-6)
+    assert float(m.now_time.item()) == float(z['final_now'])
+    m.check_errors()
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('name', CASES)
+def test_pairwise_and_gather_match_reference_fixture(name, mode):
+    z, cfg, batches = load_case(name)
+    kw = oracle_kwargs(cfg)
+    m = module_from_cfg(kw, z['p0'], mode)
+    o = WalkProjectionOracle(p0=None if kw['use_matrix'] else z['p0'], **kw)
+    for s, d, t, w in batches:
+        m.update(s, d, t)
+        o.update(s, d, t, weights=w)
+    a, b, ref = z['pair_a'], z['pair_b'], z['pair_feat']
+    got = m.pair_wise_gram(a, b).cpu().numpy()
+    assert got.shape == ref.shape
+    o.not_scale = True
+    raw = o.pair_wise_gram(a, b, exact=True)
+    tol = 1e-5 * np.abs(ref) + 2e-6 * (o.pair_norm_bound(a, b) if kw['not_scale'] else pair_tol(o, a, b, raw)) + 1e-7
+    assert np.all(np.abs(got - ref) <= tol), float(np.max(np.abs(got - ref) - tol))
+    rows = m.get_random_projections(a)
+    assert len(rows) == kw['num_layer'] + 1
+    mine = layers(m)
+    for i, r in enumerate(rows):
+        assert r.shape == (len(a), m.dim)
+        assert np.array_equal(r.cpu().numpy(), mine[i][a]), 'gather must return the current rows bit-exactly'
+    with torch.no_grad():
+        full = m.get_pair_wise_feature(a, b)
+    assert full.shape == (len(a), m.pair_wise_feature_dim)
+    assert torch.allclose(full, m.mlp(torch.from_numpy(got).to(DEV)))
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('name', ['wiki_tiny', 'flights_tiny'])
+def test_backup_reload_match_reference_fixture(name, mode):
+    z, cfg, batches = load_case(name)
+    kw = oracle_kwargs(cfg)
+    L = kw['num_layer']
+    m = module_from_cfg(kw, z['p0'], mode)
+    saved = None
+    for s, d, t, w in batches:
+        m.update(s, d, t)
+        if saved is None and float(m.now_time.item()) == float(z['backup_now']):
+            cand = m.backup_random_projections()
+            if all(np.allclose(cand[1][i].cpu().numpy(), z[f'backup_P{i + 1}'], rtol=1e-5, atol=1e-6)
+                   for i in range(L)):
+                saved = cand
+    assert saved is not None and len(saved[1]) == L and saved[1][0].shape == (kw['node_num'], m.dim)
+    assert saved[0].dtype == torch.float64
+    m.reload_random_projections(saved)
+    assert float(m.now_time.item()) == float(z['backup_now'])
+    s, d, t, _ = batches[-1]
+    m.update(s, d, t)
+    got = layers(m)
+    for i in range(1, L + 1):
+        np.testing.assert_allclose(got[i], z[f'after_reload_P{i}'], rtol=1e-5, atol=1e-6)
+
+
+# --------------------------------------------------------------------------- oracle, seeded streams
+def stream(rng, N, B, nb, skew, t0=0.0, span=500.0, equal_times=False):
+    t = t0
+    for _ in range(nb):
+        s = 1 + (rng.zipf(skew, B) - 1) % (N - 1)
+        d = 1 + (rng.zipf(skew, B) - 1) % (N - 1)
+        if equal_times:
+            t = t + float(rng.integers(0, 3)) * 86400.0
+            ts = np.full(B, t)
+        else:
+            ts = np.sort(t + rng.random(B) * span)
+            t = ts[-1]
+        yield s.astype(np.int64), d.astype(np.int64), ts.astype(np.float64)
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('B,N,dim,L', [(200, 300, 20, 2), (3000, 500, 24, 3), (2500, 4000, 150, 3), (777, 90, 7, 4),
+                                       (1, 10, 4, 1)])
+def test_update_bit_exact_with_equal_timestamps(B, N, dim, L, mode):
+    """With one timestamp per batch every w_j is exactly 1, so the CUDA path must equal the
+    oracle bit for bit: decay chain, stable sort-by-target (bitonic for 2B<=4096, radix
+    above), batch-order sequential sums, top-down layers."""
+    rng = np.random.default_rng(B + N)
+    kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=2e-6, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=dim)
+    o = WalkProjectionOracle(**kw)
+    m = module_from_cfg(kw, o.P[0], mode)
+    for s, d, t in stream(rng, N, B, 7, 1.3, equal_times=True):
+        o.update(s, d, t)
+        m.update(s, d, t)
+    got = layers(m)
+    for i in range(L + 1):
+        assert np.array_equal(got[i], o.P[i]), f'layer {i}'
+    m.check_errors()
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('B,N,dim,L,lam', [(200, 1000, 120, 2, 1e-6), (5000, 3000, 140, 3, 1e-5),
+                                           (200, 64, 210, 3, 1e-4)])
+def test_update_and_pairwise_vs_oracle(B, N, dim, L, lam, mode):
+    rng = np.random.default_rng(11)
+    kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=lam, use_matrix=False,
+              beginning_time=100.0, not_scale=False, enforce_dim=dim)
+    o = WalkProjectionOracle(**kw)
+    m = module_from_cfg(kw, o.P[0], mode)
+    for s, d, t in stream(rng, N, B, 6, 1.25, t0=100.0):
+        o.update(s, d, t)
+        m.update(s, d, t)
+    got = layers(m)
+    for i in range(1, L + 1):
+        scale = np.abs(o.P[i]).max()
+        np.testing.assert_allclose(got[i], o.P[i], rtol=1e-5, atol=1e-6 * max(scale, 1.0))
+    n = 4099                                              # ragged: not a multiple of the 16-pair CTA tile
+    a = rng.integers(0, N, n).astype(np.int64)
+    b = rng.integers(0, N, n).astype(np.int64)
+    b[:50] = a[:50]                                       # self pairs
+    feat = m.pair_wise_gram(a, b).cpu().numpy()
+    ref = o.pair_wise_gram(a, b)
+    o.not_scale = True
+    raw = o.pair_wise_gram(a, b, exact=True)
+    tol = 1e-5 * np.abs(ref) + 2e-6 * pair_tol(o, a, b, raw) + 1e-7
+    assert np.all(np.abs(feat - ref) <= tol), float(np.max(np.abs(feat - ref) - tol))
+    # raw (not_scale) features and row-major (r, c) ordering / symmetry
+    m.not_scale = True
+    g = m.pair_wise_gram(a, b).cpu().numpy().reshape(n, 2 * L + 2, 2 * L + 2)
+    assert np.array_equal(g, g.transpose(0, 2, 1))
+    tolr = 1e-5 * np.abs(raw) + 2e-6 * o.pair_norm_bound(a, b) + 1e-7
+    assert np.all(np.abs(g.reshape(n, -1) - raw) <= tolr)
+    # swapping the endpoints permutes the blocks exactly
+    gs = m.pair_wise_gram(b, a).cpu().numpy().reshape(n, 2 * L + 2, 2 * L + 2)
+    H = L + 1
+    assert np.array_equal(gs[:, :H, :H], g[:, H:, H:]) and np.array_equal(gs[:, :H, H:], g[:, H:, :H])
+
+
+def test_lazy_equals_eager_bitwise_and_log_restart(monkeypatch):
+    """Lazy replay is the same multiply chain as the eager sweep; a tiny log forces
+    materialise + restart several times."""
+    monkeypatch.setattr(rpmod, '_DEFAULT_LOG_EPOCHS', 5)
+    rng = np.random.default_rng(5)
+    N, L, dim = 800, 3, 36
+    kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=3e-4, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=dim)
+    torch.manual_seed(0)
+    e = RandomProjectionModule(device=DEV, decay_mode='eager', **kw).to(DEV)
+    z = RandomProjectionModule(device=DEV, decay_mode='lazy', **kw).to(DEV)
+    z.random_projections[0].data.copy_(e.random_projections[0].data)
+    ids = rng.integers(0, N, 512).astype(np.int64)
+    ids2 = rng.integers(0, N, 512).astype(np.int64)
+    for k, (s, d, t) in enumerate(stream(rng, N, 150, 23, 1.2)):
+        e.update(s, d, t)
+        z.update(s, d, t)
+        if k % 5 == 4:     # on-the-fly replay inside the readers, no materialise
+            assert torch.equal(e.pair_wise_gram(ids, ids2), z.pair_wise_gram(ids, ids2))
+            for x, y in zip(e.get_random_projections(ids), z.get_random_projections(ids)):
+                assert torch.equal(x, y)
+    for x, y in zip(layers(e), layers(z)):
+        assert np.array_equal(x, y)
+    sd = z.state_dict()        # materialises
+    assert torch.equal(sd['random_projections.2'], e.random_projections[2].data)
+
+
+def test_reset_and_rng_parity():
+    kw = dict(node_num=50, edge_num=500, dim_factor=2, num_layer=2, time_decay_weight=1e-3, use_matrix=False,
+              beginning_time=np.float64(3.0), not_scale=False, enforce_dim=-1)
+    for mode in MODES:
+        m = RandomProjectionModule(device=DEV, decay_mode=mode, **kw).to(DEV)
+        ids = np.arange(1, 40, dtype=np.int64)
+        m.update(ids, ids[::-1].copy(), np.linspace(4.0, 9.0, len(ids)))
+        assert layers(m)[1].any()
+        torch.manual_seed(123)
+        m.reset_random_projections()
+        got = layers(m)
+        assert not got[1].any() and not got[2].any()
+        assert float(m.now_time.item()) == 3.0 and m._now_host == 3.0
+        # same draw as nn.init.normal_ on a contiguous [N, d] CUDA parameter (TPNet.py:139)
+        torch.manual_seed(123)
+        expect = torch.empty(50, m.dim, device=DEV).normal_(0, 1 / np.sqrt(m.dim))
+        assert torch.equal(m.random_projections[0].data, expect)
+        assert not m._state[:, :, m.dim:].any()
+
+
+def test_edge_cases_and_errors():
+    kw = dict(node_num=20, edge_num=100, dim_factor=1, num_layer=2, time_decay_weight=1e-3, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=6)
+    m = RandomProjectionModule(device=DEV, **kw).to(DEV)
+    e = np.array([], dtype=np.int64)
+    assert m.get_pair_wise_feature(e, e).shape == (0, 36)
+    assert [r.shape for r in m.get_random_projections(e)] == [(0, 6)] * 3
+    with pytest.raises(IndexError):
+        m.update(e, e, np.array([], dtype=np.float64))
+    with pytest.raises(IndexError):
+        m.update(np.array([1]), np.array([20]), np.array([1.0]))
+    with pytest.raises(IndexError):
+        m.update(np.array([-1]), np.array([2]), np.array([1.0]))
+    with pytest.raises(IndexError):
+        m.get_pair_wise_feature(np.array([25]), np.array([1]))
+    # device-resident ids: out-of-range edges are dropped and flagged
+    s = torch.tensor([1, 99], device=DEV); d = torch.tensor([2, 3], device=DEV)
+    t = torch.tensor([1.0, 2.0], device=DEV, dtype=torch.float64)
+    m.update(s, d, t, next_time=2.0)
+    with pytest.raises(IndexError):
+        m.check_errors()
+    got = layers(m)
+    assert got[1][1].any() and got[1][2].any() and not got[1][3].any()
+    # int32 ids and python lists behave like int64 arrays
+    f1 = m.pair_wise_gram(np.array([1, 2], dtype=np.int32), [2, 1])
+    f2 = m.pair_wise_gram(np.array([1, 2]), np.array([2, 1]))
+    assert torch.equal(f1, f2)
+
+
+def test_use_matrix_wide_rows_multi_column_tiles():
+    """use_matrix=True with N > 1024 exercises the column-tiled walk kernel (row wider
+    than one 32-lane x 8-float4 tile) in both decay modes."""
+    rng = np.random.default_rng(2)
+    N, L = 1100, 2
+    kw = dict(node_num=N, edge_num=4000, dim_factor=1, num_layer=L, time_decay_weight=1e-5, use_matrix=True,
+              beginning_time=0.0, not_scale=True, enforce_dim=-1)
+    o = WalkProjectionOracle(**kw)
+    ms = [module_from_cfg(kw, None, mode) for mode in MODES]
+    for s, d, t in stream(rng, N, 64, 4, 1.5, equal_times=True):
+        o.update(s, d, t)
+        for m in ms:
+            m.update(s, d, t)
+    for m in ms:
+        got = layers(m)
+        for i in range(L + 1):
+            assert np.array_equal(got[i], o.P[i])
+
+
+def test_c_abi_direct_with_padded_node_stride():
+    """Raw C-ABI call (no module): node_stride larger than (L+1)*row_stride, error codes."""
+    lib = _lib.load()
+    N, L, d, rs, ns = 33, 2, 10, 12, 48
+    rng = np.random.default_rng(0)
+    host = np.zeros((N, ns), dtype=np.float32)
+    for l in range(L + 1):
+        host[:, l * rs:l * rs + d] = rng.standard_normal((N, d)).astype(np.float32)
+    state = torch.from_numpy(host).to(DEV)
+    st = _lib.TpnState(data=state.data_ptr(), num_nodes=N, num_layer=L, dim=d, row_stride=rs, node_stride=ns,
+                       stamps=None, decay_log=None, log_capacity=0, epoch=0)
+    a = torch.from_numpy(rng.integers(0, N, 21)).to(DEV)
+    b = torch.from_numpy(rng.integers(0, N, 21)).to(DEV)
+    out = torch.empty(21, 36, device=DEV)
+    stream_ptr = torch.cuda.current_stream().cuda_stream
+    assert lib.tpn_pairwise(ctypes.byref(st), a.data_ptr(), b.data_ptr(), 21, 0, out.data_ptr(), stream_ptr) == 0
+    x = np.concatenate([host[a.cpu().numpy()].reshape(21, 4, rs)[:, :3, :d],
+                        host[b.cpu().numpy()].reshape(21, 4, rs)[:, :3, :d]], axis=1).astype(np.float64)
+    ref = np.einsum('nrd,ncd->nrc', x, x).reshape(21, 36)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    g = torch.empty(3, 21, d, device=DEV)
+    assert lib.tpn_gather(ctypes.byref(st), a.data_ptr(), 21, g.data_ptr(), stream_ptr) == 0
+    assert np.array_equal(g[1].cpu().numpy(), host[a.cpu().numpy(), rs:rs + d])
+    st.row_stride = 10                                   # not a multiple of 4 floats
+    assert lib.tpn_pairwise(ctypes.byref(st), a.data_ptr(), b.data_ptr(), 21, 0, out.data_ptr(), stream_ptr) == -1
+    st.row_stride = rs
+    ws = torch.empty(64, dtype=torch.uint8, device=DEV)
+    t = torch.zeros(21, dtype=torch.float64, device=DEV)
+    rc = lib.tpn_update(ctypes.byref(st), a.data_ptr(), b.data_ptr(), t.data_ptr(), 21, 0.0, -1e-3, None,
+                        ws.data_ptr(), 64, None, stream_ptr)
+    assert rc == -2                                      # workspace too small
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.tpn_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)) == 0
+    assert sm.value > 0 and major.value >= 10, 'this library is built for sm_100a only'
+
+
+# --------------------------------------------------------------------------- BASELINE sizes: properties
+@pytest.mark.parametrize('mode', MODES)
+def test_full_size_reddit_shape_properties(mode):
+    """Reddit-shaped state (N=10,985, d=140, L=3), B=200, and one 100k-edge batch through the
+    radix path: size-independent properties instead of the (too slow) oracle."""
+    rng = np.random.default_rng(9)
+    N, L, dim = 10985, 3, 140
+    kw = dict(node_num=N, edge_num=672448, dim_factor=10, num_layer=L, time_decay_weight=1e-6, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=-1)
+    torch.manual_seed(0)
+    m = RandomProjectionModule(device=DEV, decay_mode=mode, **kw).to(DEV)
+    assert m.dim == dim
+    before = [x.astype(np.float64) for x in layers(m)]
+    # (1) conservation: with w == 1 and no clock movement, sum_u P_1[u] grows by sum_j (P_0[src_j] + P_0[dst_j])
+    s = (1 + (rng.zipf(1.2, 100000) - 1) % (N - 1)).astype(np.int64)
+    d = (1 + (rng.zipf(1.2, 100000) - 1) % (N - 1)).astype(np.int64)
+    t = np.zeros(100000)
+    m.update(s, d, t)
+    after = [x.astype(np.float64) for x in layers(m)]
+    grow = after[1].sum(0) - before[1].sum(0)
+    expect = before[0][s].sum(0) + before[0][d].sum(0)
+    np.testing.assert_allclose(grow, expect, rtol=1e-4, atol=1e-2)
+    assert not after[2].any() and np.array_equal(after[0], before[0])
+    # (2) against a plain PyTorch fp32 reference of the same op on the GPU (index_add_, any order)
+    P0 = torch.from_numpy(before[0]).float().to(DEV)
+    ref1 = torch.zeros_like(P0)
+    sd_, dd_ = torch.from_numpy(s).to(DEV), torch.from_numpy(d).to(DEV)
+    ref1.index_add_(0, sd_, P0[dd_])
+    ref1.index_add_(0, dd_, P0[sd_])
+    scale = float(ref1.abs().max())
+    np.testing.assert_allclose(after[1], ref1.cpu().numpy(), rtol=1e-4, atol=2e-5 * scale)
+    # (3) decoder + encoder shaped pair batches stay finite, non-negative, symmetric
+    for s, d, t in stream(rng, N, 200, 5, 1.2, t0=1.0, span=4000.0):
+        m.update(s, d, t)
+    K = 20
+    nbr = rng.integers(0, N, (400, K))
+    a = np.tile(nbr.reshape(-1), 2).astype(np.int64)
+    b = np.concatenate([np.repeat(np.tile(s, 2), K), np.repeat(np.tile(d, 2), K)]).astype(np.int64)
+    f = m.pair_wise_gram(a, b)
+    assert f.shape == (16000, 64) and bool(torch.isfinite(f).all()) and bool((f >= 0).all())
+    g = f.reshape(-1, 8, 8)
+    assert torch.equal(g, g.transpose(1, 2))
+    m.check_errors()

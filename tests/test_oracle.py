@@ -153,3 +153,24 @@ def test_bruteforce_fixture():
     brute = sum_walk_matrices(z['src'], z['dst'], z['t'], 3, 1e-4, 24)
     for j in range(4):
         np.testing.assert_allclose(brute[j], z[f'A{j}'], rtol=1e-12)
+
+
+def test_add_at_equals_loop():
+    """The large-batch path of the oracle (np.add.at) is the same sequential sum."""
+    rng = np.random.default_rng(3)
+    kw = dict(node_num=50, edge_num=4000, dim_factor=2, num_layer=3, time_decay_weight=1e-3, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=-1)
+    a = WalkProjectionOracle(**kw)
+    b = WalkProjectionOracle(p0=a.P[0], **kw)
+    b.LOOP_MAX = 0
+    t = 0.0
+    for _ in range(4):
+        B = 300
+        s = 1 + (rng.zipf(1.4, B) - 1) % 49
+        d = 1 + (rng.zipf(1.4, B) - 1) % 49
+        ts = np.sort(t + rng.random(B) * 100)
+        t = ts[-1]
+        a.update(s, d, ts)
+        b.update(s, d, ts)
+    for i in range(4):
+        assert np.array_equal(a.P[i], b.P[i])

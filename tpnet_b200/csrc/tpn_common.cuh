@@ -1,0 +1,87 @@
+// Shared device helpers for the tpnet_b200 kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tpnet_b200.h"
+
+namespace tpn {
+
+// Device-side copy of tpn_state_t (passed by value as a kernel argument).
+struct StateView {
+    float* data;
+    long long num_nodes;
+    int num_layer;
+    int dim;
+    long long row_stride;    // floats
+    long long node_stride;   // floats
+    int* stamps;             // nullptr => eager
+    const float* decay_log;  // [cap][L]
+    long long epoch;         // epoch readers replay up to
+};
+
+inline StateView make_view(const tpn_state_t* st) {
+    StateView v;
+    v.data = st->data;
+    v.num_nodes = st->num_nodes;
+    v.num_layer = st->num_layer;
+    v.dim = st->dim;
+    v.row_stride = st->row_stride;
+    v.node_stride = st->node_stride;
+    v.stamps = st->stamps;
+    v.decay_log = st->decay_log;
+    v.epoch = st->epoch;
+    return v;
+}
+
+inline int validate_state(const tpn_state_t* st) {
+    if (st == nullptr || st->data == nullptr) return TPN_ERR_INVALID_ARGUMENT;
+    if (st->num_layer < 1 || st->num_layer > TPN_MAX_LAYERS) return TPN_ERR_UNSUPPORTED;
+    if (st->num_nodes < 1 || st->dim < 1) return TPN_ERR_INVALID_ARGUMENT;
+    if (st->row_stride < st->dim || (st->row_stride & 3)) return TPN_ERR_INVALID_ARGUMENT;
+    if (st->node_stride < (long long)(st->num_layer + 1) * st->row_stride || (st->node_stride & 3))
+        return TPN_ERR_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(st->data) & 15) != 0) return TPN_ERR_INVALID_ARGUMENT;
+    if (st->stamps != nullptr && (st->decay_log == nullptr || st->log_capacity < 2 || st->epoch < 0 ||
+                                  st->epoch >= st->log_capacity))
+        return TPN_ERR_INVALID_ARGUMENT;
+    return TPN_OK;
+}
+
+void set_cuda_error(cudaError_t e);
+int check_launch();
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ void scale4(float4& v, float f) {
+    v.x = __fmul_rn(v.x, f);
+    v.y = __fmul_rn(v.y, f);
+    v.z = __fmul_rn(v.z, f);
+    v.w = __fmul_rn(v.w, f);
+}
+
+// acc += fl32(x * w): product rounded BEFORE the add (no FMA contraction), as the
+// reference materialises `P[idx] * time_weight` before scatter_add_ (TPNet.py:91-96).
+__device__ __forceinline__ void axpy4_rn(float4& acc, const float4& x, float w) {
+    acc.x = __fadd_rn(acc.x, __fmul_rn(x.x, w));
+    acc.y = __fadd_rn(acc.y, __fmul_rn(x.y, w));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(x.z, w));
+    acc.w = __fadd_rn(acc.w, __fmul_rn(x.w, w));
+}
+
+// Lazy decay: replay the logged fp32 factors of epochs (from, to] of layer index
+// `li` (= layer-1) on V float4 registers — the same rounded multiply chain the
+// reference applies eagerly once per update (TPNet.py:83-85).
+template <int V>
+__device__ __forceinline__ void replay(float4 (&x)[V], const float* __restrict__ log, int L, int li,
+                                       long long from, long long to) {
+    for (long long e = from + 1; e <= to; ++e) {
+        const float f = __ldg(log + e * L + li);
+#pragma unroll
+        for (int k = 0; k < V; ++k) scale4(x[k], f);
+    }
+}
+
+}  // namespace tpn

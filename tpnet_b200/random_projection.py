@@ -1,0 +1,390 @@
+"""Drop-in replacement for the reference's ``RandomProjectionModule``
+(``/root/reference/models/TPNet.py:9-157``) backed by the sm_100a CUDA library.
+
+Same constructor arguments, attributes, ``state_dict`` keys and method names as
+the reference, so ``train_link_prediction.py`` / ``evaluate_link_prediction.py``
+run on it unmodified (see INTEGRATION.md for the two-line patch).  All arithmetic
+of the hot path runs in the hand-written kernels reached through the C ABI
+(``include/tpnet_b200.h``); PyTorch only owns memory, streams and the trainable
+``self.mlp`` head.  There is no CPU path: calling a compute method while the
+state is not on a CUDA device raises.
+
+Differences a caller can observe (documented, none on the reference's own call
+sites):
+  * the L+1 projection matrices live in ONE packed node-major buffer
+    ``[N, L+1, row_stride]``; ``self.random_projections[i]`` are strided ``[N, d]``
+    views of it (values, shapes, dtypes and state_dict keys are the reference's);
+  * ``decay_mode='lazy'`` defers the per-update whole-matrix rescale
+    (TPNet.py:83-85) to the rows that are touched; reads through this class's
+    methods are always current, raw reads of ``random_projections[i]`` need
+    ``materialize()`` first (``state_dict()`` and ``backup_…`` do it themselves);
+  * ids may also be passed as int64 CUDA tensors (device-resident pipelines).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import TpnState
+
+IdArray = Union[np.ndarray, torch.Tensor]
+
+#: state size above which 'auto' picks lazy decay (the eager sweep of a state
+#: this small stays in L2 and costs a few microseconds)
+AUTO_LAZY_BYTES = 256 << 20
+_DEFAULT_LOG_EPOCHS = 4096
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class _Staging:
+    """Ring of pinned host buffers + device buffers for the per-call id/timestamp
+    upload: one async H2D copy per call, no pageable-memory sync."""
+
+    def __init__(self, slots: int = 4):
+        self.slots = slots
+        self.host: List[Optional[torch.Tensor]] = [None] * slots
+        self.dev: List[Optional[torch.Tensor]] = [None] * slots
+        self.done: List[Optional[torch.cuda.Event]] = [None] * slots
+        self.cursor = 0
+
+    def upload(self, arrays: Sequence[np.ndarray], device: torch.device) -> List[int]:
+        """Copies the given 8-byte-element host arrays back to back; returns device addresses."""
+        k = self.cursor
+        self.cursor = (k + 1) % self.slots
+        total = sum(a.nbytes for a in arrays)
+        if self.host[k] is None or self.host[k].numel() < total or self.dev[k].device != device:
+            cap = max(4096, 1 << (total - 1).bit_length())
+            self.host[k] = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            self.dev[k] = torch.empty(cap, dtype=torch.uint8, device=device)
+            self.done[k] = torch.cuda.Event()
+        else:
+            self.done[k].synchronize()           # the previous copy out of this pinned slot has finished
+        hview = self.host[k].numpy()
+        offs, o = [], 0
+        for a in arrays:
+            hview[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+            offs.append(o)
+            o += a.nbytes
+        self.dev[k][:total].copy_(self.host[k][:total], non_blocking=True)
+        self.done[k].record()
+        base = self.dev[k].data_ptr()
+        return [base + x for x in offs]
+
+
+class RandomProjectionModule(nn.Module):
+    def __init__(self, node_num: int, edge_num: int, dim_factor: int, num_layer: int, time_decay_weight: float,
+                 device: str, use_matrix: bool, beginning_time: np.float64, not_scale: bool, enforce_dim: int,
+                 decay_mode: str = 'auto'):
+        """Arguments as the reference constructor (TPNet.py:10-26).  ``decay_mode`` in
+        {'auto', 'eager', 'lazy'} selects how the time decay of TPNet.py:83-85 is
+        realised; all modes produce the same values."""
+        super().__init__()
+        if not 1 <= num_layer <= _lib.TPN_MAX_LAYERS:
+            raise ValueError(f'num_layer must be in 1..{_lib.TPN_MAX_LAYERS}')
+        if decay_mode not in ('auto', 'eager', 'lazy'):
+            raise ValueError("decay_mode must be 'auto', 'eager' or 'lazy'")
+        self.node_num = node_num
+        self.edge_num = edge_num
+        if enforce_dim != -1:                                             # TPNet.py:30-33
+            self.dim = enforce_dim
+        else:
+            self.dim = min(int(math.log(self.edge_num * 2)) * dim_factor, node_num)
+        self.num_layer = num_layer
+        self.time_decay_weight = time_decay_weight
+        self.begging_time = nn.Parameter(torch.tensor(beginning_time), requires_grad=False)   # (sic) TPNet.py:36
+        self.now_time = nn.Parameter(torch.tensor(beginning_time), requires_grad=False)
+        self.device = device
+        self.use_matrix = use_matrix
+        self.node_feature_dim = 128
+        self.not_scale = not_scale
+        if self.use_matrix:                                               # TPNet.py:44-45
+            self.dim = self.node_num
+        self.row_stride = _round_up(self.dim, 8)          # 32-byte sectors; pad columns stay zero
+        self.node_stride = (self.num_layer + 1) * self.row_stride
+        self.decay_mode = decay_mode
+
+        # packed node-major state; P_l[u] = _state[u, l, :dim]
+        self._state = torch.zeros(self.node_num, self.num_layer + 1, self.row_stride, dtype=torch.float32)
+        if self.use_matrix:
+            first = torch.eye(self.node_num)                              # TPNet.py:48-49
+        else:
+            # same RNG call as TPNet.py:58 so a seeded run draws the same P_0
+            first = torch.normal(0, 1 / math.sqrt(self.dim), (self.node_num, self.dim))
+        self._state[:, 0, :self.dim] = first
+        self.random_projections = nn.ParameterList(
+            [nn.Parameter(self._state[:, i, :self.dim], requires_grad=False) for i in range(self.num_layer + 1)])
+        self.pair_wise_feature_dim = (2 * self.num_layer + 2) ** 2        # TPNet.py:63
+        self.mlp = nn.Sequential(nn.Linear(self.pair_wise_feature_dim, self.pair_wise_feature_dim * 4), nn.ReLU(),
+                                 nn.Linear(self.pair_wise_feature_dim * 4, self.pair_wise_feature_dim))
+
+        # host mirrors / device scratch (not part of state_dict)
+        self._now_host = float(beginning_time)
+        self._begin_host = float(beginning_time)
+        self._epoch = 0
+        self._stamps: Optional[torch.Tensor] = None
+        self._decay_log: Optional[torch.Tensor] = None
+        self._ws: Optional[torch.Tensor] = None
+        self._err: Optional[torch.Tensor] = None
+        self._staging = _Staging()
+        self.validate_ids = True
+        self.launches = 0                     # kernels-launching C-ABI calls issued (bench accounting)
+        self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module.materialize())
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._after_external_write())
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def lazy(self) -> bool:
+        if self.decay_mode == 'auto':
+            return self._state.numel() * 4 > AUTO_LAZY_BYTES
+        return self.decay_mode == 'lazy'
+
+    def _apply(self, fn, recurse=True):
+        # nn.Module.to()/cuda()/cpu(): parameters are converted one by one (the views
+        # become independent tensors); gather them back into one packed buffer.
+        super()._apply(fn, recurse)
+        self._repack()
+        return self
+
+    def _is_packed(self) -> bool:
+        st = self._state
+        for i, p in enumerate(self.random_projections):
+            if (p.device != st.device or p.dtype != torch.float32 or p.shape != (self.node_num, self.dim)
+                    or p.stride() != (self.node_stride, 1)
+                    or p.data_ptr() != st.data_ptr() + 4 * i * self.row_stride):
+                return False
+        return True
+
+    def _repack(self) -> None:
+        if self._is_packed():
+            return
+        dev = self.random_projections[0].device
+        for p in self.random_projections:
+            if p.dtype != torch.float32:
+                raise TypeError('RandomProjectionModule state must stay float32')
+        new_state = torch.zeros(self.node_num, self.num_layer + 1, self.row_stride, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for i, p in enumerate(self.random_projections):
+                new_state[:, i, :self.dim].copy_(p.data)
+                p.data = new_state[:, i, :self.dim]
+        self._state = new_state
+        self._stamps = None
+        self._decay_log = None
+        self._ws = None
+        self._err = None
+        self._epoch = 0
+
+    def _after_external_write(self) -> None:
+        """load_state_dict / reload wrote fully materialised values: refresh mirrors."""
+        self._repack()
+        self._now_host = float(self.now_time.item())
+        self._begin_host = float(self.begging_time.item())
+        if self._stamps is not None:
+            self._stamps.zero_()
+        self._epoch = 0
+
+    def _require_cuda(self) -> torch.device:
+        dev = self._state.device
+        if dev.type != 'cuda':
+            raise RuntimeError('tpnet_b200.RandomProjectionModule computes on CUDA only (no CPU fallback): '
+                               'move the module with .to("cuda") first')
+        return dev
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self._state.device).cuda_stream
+
+    def _c_state(self) -> TpnState:
+        st = TpnState()
+        st.data = self._state.data_ptr()
+        st.num_nodes = self.node_num
+        st.num_layer = self.num_layer
+        st.dim = self.dim
+        st.row_stride = self.row_stride
+        st.node_stride = self.node_stride
+        if self.lazy:
+            if self._stamps is None:
+                # -1 = row known to be all zero (never written); rows holding data start at epoch 0
+                has_data = bool((self._state[:, 1:, :] != 0).any().item()) if self._state.numel() else False
+                self._stamps = torch.full((self.node_num, self.num_layer), 0 if has_data else -1, dtype=torch.int32,
+                                          device=self._state.device)
+                self._decay_log = torch.ones(_DEFAULT_LOG_EPOCHS, self.num_layer, dtype=torch.float32,
+                                             device=self._state.device)
+                self._epoch = 0
+            st.stamps = self._stamps.data_ptr()
+            st.decay_log = self._decay_log.data_ptr()
+            st.log_capacity = self._decay_log.shape[0]
+            st.epoch = self._epoch
+        else:
+            st.stamps = None
+            st.decay_log = None
+            st.log_capacity = 0
+            st.epoch = 0
+        return st
+
+    def _ids_to_device(self, arrays: Sequence[IdArray], kinds: Sequence[str], wrap_negative: bool = True) -> List[int]:
+        """Returns device addresses for id (int64) / time (float64) arrays given as
+        numpy arrays (staged through pinned memory) or CUDA tensors (used in place)."""
+        dev = self._state.device
+        if all(isinstance(a, torch.Tensor) for a in arrays):
+            out = []
+            for a, kind in zip(arrays, kinds):
+                want = torch.int64 if kind == 'id' else torch.float64
+                if a.device != dev or a.dtype != want or not a.is_contiguous():
+                    raise TypeError(f'device-resident {kind} arrays must be contiguous {want} tensors on {dev}')
+                out.append(a.data_ptr())
+            self._keepalive = list(arrays)
+            return out
+        host = []
+        for a, kind in zip(arrays, kinds):
+            if isinstance(a, torch.Tensor):
+                a = a.detach().cpu().numpy()
+            a = np.ascontiguousarray(a, dtype=np.int64 if kind == 'id' else np.float64)
+            if kind == 'id' and self.validate_ids and a.size:
+                lo = -self.node_num if wrap_negative else 0     # scatter_add_ rejects negatives, indexing wraps
+                if a.min() < lo or a.max() >= self.node_num:
+                    raise IndexError(f'index out of range for node_num {self.node_num}')
+                if a.min() < 0:
+                    a = np.where(a < 0, a + self.node_num, a)
+            host.append(a)
+        return self._staging.upload(host, dev)
+
+    # ------------------------------------------------------------------ reference API
+    def update(self, src_node_ids: IdArray, dst_node_ids: IdArray, node_interact_times: IdArray,
+               next_time: Optional[float] = None):
+        """TPNet.py:67-99.  ``next_time`` is only needed when the arrays are CUDA tensors
+        (it is ``node_interact_times[-1]``, which the host needs for the f64 decay factors)."""
+        dev = self._require_cuda()
+        lib = _lib.load()
+        n = int(len(src_node_ids))
+        if n == 0:
+            raise IndexError('index -1 is out of bounds for axis 0 with size 0')      # what TPNet.py:76 raises
+        if len(dst_node_ids) != n or len(node_interact_times) != n:
+            raise ValueError('src, dst and time arrays must have the same length')
+        if next_time is None:
+            last = node_interact_times[-1]
+            next_time = float(last.item()) if isinstance(last, torch.Tensor) else float(last)
+        lam = self.time_decay_weight
+        # c_l = f32(pow(exp(-lambda*(t_last - now)), l)) computed in f64 on the host, TPNet.py:84-85
+        base = np.exp(-lam * (np.float64(next_time) - np.float64(self._now_host)))
+        factors = (ctypes.c_float * self.num_layer)(*[float(np.float32(np.power(base, i)))
+                                                      for i in range(1, self.num_layer + 1)])
+        ptrs = self._ids_to_device([src_node_ids, dst_node_ids, node_interact_times], ['id', 'id', 'time'],
+                                   wrap_negative=False)
+        need = lib.tpn_update_workspace_bytes(n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+        if self._err is None:
+            self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = self._c_state()
+        args = (ptrs[0], ptrs[1], ptrs[2], n, float(next_time), float(np.float32(-lam)), factors,
+                self._ws.data_ptr(), self._ws.numel(), self._err.data_ptr(), self._stream())
+        rc = lib.tpn_update(ctypes.byref(st), *args)
+        if rc == _lib.TPN_ERR_LOG_FULL:
+            self._restart_log()
+            st = self._c_state()
+            rc = lib.tpn_update(ctypes.byref(st), *args)
+        _lib.check(rc, 'tpn_update')
+        self._epoch = int(st.epoch)
+        self.launches += 1
+        self._now_host = float(next_time)
+        self.now_time.data.fill_(self._now_host)                                       # TPNet.py:99
+
+    def get_random_projections(self, node_ids: IdArray) -> List[torch.Tensor]:
+        """TPNet.py:101-110: list of L+1 tensors [n, dim]."""
+        dev = self._require_cuda()
+        lib = _lib.load()
+        n = int(len(node_ids))
+        out = torch.empty(self.num_layer + 1, n, self.dim, dtype=torch.float32, device=dev)
+        if n:
+            ptrs = self._ids_to_device([node_ids], ['id'])
+            st = self._c_state()
+            _lib.check(lib.tpn_gather(ctypes.byref(st), ptrs[0], n, out.data_ptr(), self._stream()), 'tpn_gather')
+            self.launches += 1
+        return [out[i] for i in range(self.num_layer + 1)]
+
+    def pair_wise_gram(self, src_node_ids: IdArray, dst_node_ids: IdArray) -> torch.Tensor:
+        """The input of ``self.mlp``: TPNet.py:119-128 (everything before the head)."""
+        dev = self._require_cuda()
+        lib = _lib.load()
+        n = int(len(src_node_ids))
+        if len(dst_node_ids) != n:
+            raise ValueError('src and dst id arrays must have the same length')
+        out = torch.empty(n, self.pair_wise_feature_dim, dtype=torch.float32, device=dev)
+        if n:
+            ptrs = self._ids_to_device([src_node_ids, dst_node_ids], ['id', 'id'])
+            st = self._c_state()
+            _lib.check(lib.tpn_pairwise(ctypes.byref(st), ptrs[0], ptrs[1], n, 0 if self.not_scale else 1,
+                                        out.data_ptr(), self._stream()), 'tpn_pairwise')
+            self.launches += 1
+        return out
+
+    def get_pair_wise_feature(self, src_node_ids: IdArray, dst_node_ids: IdArray) -> torch.Tensor:
+        """TPNet.py:112-129.  Gradients flow to ``self.mlp`` only, as in the reference
+        (the projections are ``requires_grad=False``)."""
+        return self.mlp(self.pair_wise_gram(src_node_ids, dst_node_ids))
+
+    def reset_random_projections(self):
+        """TPNet.py:131-139."""
+        self._require_cuda()
+        lib = _lib.load()
+        st = self._c_state()
+        _lib.check(lib.tpn_clear_walk_layers(ctypes.byref(st), self._stream()), 'tpn_clear_walk_layers')
+        self._epoch = 0
+        self._now_host = self._begin_host
+        self.now_time.data = self.begging_time.clone()
+        if not self.use_matrix:
+            std = 1 / math.sqrt(self.dim)
+            p0 = self.random_projections[0]
+            with torch.no_grad():
+                if self.node_num * self.dim * 4 <= (2 << 30):
+                    # draw into a contiguous [N, d] tensor exactly like nn.init.normal_ on the
+                    # reference's contiguous parameter (same generator stream), then place it
+                    p0.copy_(torch.empty(self.node_num, self.dim, dtype=torch.float32, device=p0.device)
+                             .normal_(mean=0, std=std))
+                else:
+                    p0.normal_(mean=0, std=std)
+
+    def backup_random_projections(self) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        """TPNet.py:141-147: (now_time, [P_1..P_L]) — P_0 is not part of the backup."""
+        self.materialize()
+        return self.now_time.clone(), [self.random_projections[i].clone() for i in range(1, self.num_layer + 1)]
+
+    def reload_random_projections(self, random_projections):
+        """TPNet.py:149-157."""
+        now_time, layers = random_projections
+        with torch.no_grad():
+            self.now_time.data = now_time.clone().to(self.now_time.device)
+            for i in range(1, self.num_layer + 1):
+                self.random_projections[i].copy_(layers[i - 1])
+        self._after_external_write()
+
+    # ------------------------------------------------------------------ lazy-decay maintenance
+    def materialize(self) -> None:
+        """Bring every row current (no-op in eager mode or off-GPU)."""
+        if self._state.device.type != 'cuda' or not self.lazy or self._stamps is None or self._epoch == 0:
+            return
+        lib = _lib.load()
+        st = self._c_state()
+        _lib.check(lib.tpn_materialize(ctypes.byref(st), self._stream()), 'tpn_materialize')
+        self.launches += 1
+
+    def _restart_log(self) -> None:
+        lib = _lib.load()
+        self.materialize()
+        st = self._c_state()
+        _lib.check(lib.tpn_reset_epoch(ctypes.byref(st), self._stream()), 'tpn_reset_epoch')
+        self._epoch = 0
+
+    def check_errors(self) -> None:
+        """Synchronises and raises IndexError if a device-resident id was out of range."""
+        if self._err is not None and int(self._err.item()) != 0:
+            self._err.zero_()
+            raise IndexError(f'node id out of range for node_num {self.node_num} in a device-resident batch')

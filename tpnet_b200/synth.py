@@ -1,0 +1,120 @@
+"""Synthetic temporal graphs of the shapes BASELINE.json names (the real datasets are
+not available offline).  Host-side numpy only; used by bench.py and the tests.
+
+Shapes follow SURVEY.md §8(d) / the reference's processed-data conventions
+(``utils/DataLoader.py:96-135``): node ids are 1-based (0 is the padding node),
+bipartite graphs put destinations after sources, timestamps are non-decreasing
+float64 seconds.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Iterator, Tuple
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class GraphShape:
+    name: str
+    num_src: int           # bipartite: sources 1..num_src ; non-bipartite: all nodes
+    num_dst: int           # bipartite: destinations num_src+1..num_src+num_dst ; 0 = non-bipartite
+    num_edges: int
+    num_layer: int
+    time_decay_weight: float
+    time_span: float       # seconds covered by the full edge list
+    day_quantised: bool    # Flights: integer day stamps -> many equal timestamps per batch
+    skew: float            # zipf exponent of endpoint popularity
+    dim_factor: int = 10
+
+    @property
+    def num_nodes(self) -> int:          # without the padding node
+        return self.num_src + self.num_dst
+
+    @property
+    def node_num(self) -> int:           # constructor argument of the module (incl. pad id 0)
+        return self.num_nodes + 1
+
+    @property
+    def edge_num(self) -> int:           # constructor argument (edge feature rows incl. pad row)
+        return self.num_edges + 1
+
+    @property
+    def dim(self) -> int:                # TPNet.py:30-33
+        return min(int(math.log(self.edge_num * 2)) * self.dim_factor, self.node_num)
+
+
+SHAPES: Dict[str, GraphShape] = {
+    # configs[0]: Wikipedia-shaped, 2 projection layers
+    'wikipedia': GraphShape('wikipedia', 8227, 1000, 157474, 2, 1e-6, 2.68e6, False, 1.3),
+    # configs[1]: Reddit-shaped (the headline 1-GPU workload), default 3 layers
+    'reddit': GraphShape('reddit', 10000, 984, 672447, 3, 1e-6, 2.68e6, False, 1.3),
+    # configs[2]: Flights-shaped, non-bipartite, day-quantised timestamps
+    'flights': GraphShape('flights', 13169, 0, 1927145, 3, 1e-6, 122 * 86400.0, True, 1.3),
+    # configs[3]: power-law 10M nodes / 1B edges (state sharded over GPUs when N > 1)
+    'powerlaw': GraphShape('powerlaw', 10_000_000, 0, 1_000_000_000, 3, 1e-7, 3.0e7, False, 1.2),
+}
+
+
+def _popularity(rng: np.random.Generator, n: int, count: int, skew: float) -> np.ndarray:
+    """`count` draws in [0, n) with a zipf(skew) popularity profile, hubs scattered by a
+    fixed multiplicative permutation so that hot rows are not address-adjacent."""
+    raw = (rng.zipf(skew, count) - 1) % n
+    stride = 2654435761 % n
+    while math.gcd(stride, n) != 1:
+        stride += 1
+    return (raw * stride) % n
+
+
+def edge_stream(shape: GraphShape, batch: int, num_batches: int, seed: int = 0, start_edge: int = 0
+                ) -> Iterator[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
+    """Yields (src, dst, t) batches in chronological order.  The per-edge time step is the
+    full graph's (time_span / num_edges), so decay per batch is what the real stream has."""
+    rng = np.random.default_rng(seed)
+    dt = shape.time_span / shape.num_edges
+    e = start_edge
+    for _ in range(num_batches):
+        src = 1 + _popularity(rng, shape.num_src, batch, shape.skew)
+        if shape.num_dst:
+            dst = 1 + shape.num_src + _popularity(rng, shape.num_dst, batch, shape.skew)
+        else:
+            dst = 1 + _popularity(rng, shape.num_src, batch, shape.skew)
+        t = (e + np.arange(batch, dtype=np.float64) + rng.random(batch)) * dt
+        t.sort()
+        if shape.day_quantised:
+            t = np.floor(t / 86400.0) * 86400.0
+        e += batch
+        yield src.astype(np.int64), dst.astype(np.int64), t
+
+
+class RecentNeighbors:
+    """Host-side stand-in for the reference's `recent` NeighborSampler
+    (``utils/utils.py:160-224``): the last K neighbours of a node, zero-padded at the
+    FRONT (``utils/utils.py:211-219``)."""
+
+    def __init__(self, node_num: int, k: int):
+        self.k = k
+        self.table = np.zeros((node_num, k), dtype=np.int64)
+
+    def lookup(self, nodes: np.ndarray) -> np.ndarray:
+        return self.table[nodes]
+
+    def insert(self, src: np.ndarray, dst: np.ndarray) -> None:
+        tab = self.table
+        for u, v in zip(src.tolist(), dst.tolist()):
+            tab[u, :-1] = tab[u, 1:]
+            tab[u, -1] = v
+            tab[v, :-1] = tab[v, 1:]
+            tab[v, -1] = u
+
+
+def tpnet_pair_lists(nbr: RecentNeighbors, src: np.ndarray, dst: np.ndarray):
+    """The (a_ids, b_ids) of the encoder call for one (src, dst) batch — the index
+    construction of ``models/TPNet.py:206-219`` + ``:313-316``: 4*B*K pairs."""
+    node_ids = np.concatenate([src, dst])
+    s2, d2 = np.tile(src, 2), np.tile(dst, 2)
+    neighbours = nbr.lookup(node_ids)                                   # [2B, K]
+    a = np.tile(neighbours.reshape(-1), 2)
+    b = np.concatenate([np.repeat(s2, nbr.k), np.repeat(d2, nbr.k)])
+    return a.astype(np.int64), b.astype(np.int64)
