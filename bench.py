@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument('--decay-mode', default='auto', choices=['auto', 'eager', 'lazy'])
     ap.add_argument('--no-flush', action='store_true', help='keep L2 warm between steps (reported, not the headline)')
     ap.add_argument('--cpu-sample-steps', type=int, default=30)
+    ap.add_argument('--warm-batches', type=int, default=WARM_BATCHES, help='untimed batches that fill the state')
     return ap.parse_args()
 
 
@@ -213,7 +214,7 @@ def main():
         if rank != 0:
             return
         threads = os.cpu_count() or 1
-        warm_batches, steps = make_steps(shape, K + W, seed=rank)
+        warm_batches, steps = make_steps(shape, K + W, seed=rank, warm=args.warm_batches)
         sec = cpu_port_run(shape, warm_batches, steps, W, K, threads)
         val = BATCH / sec
         line = {'impl': 'reference', 'metric': 'temporal edges/sec (update+pairwise encode)', 'value': val,
@@ -239,7 +240,7 @@ def main():
     _lib.load()
 
     n_steps = 2 * (K + W)
-    warm_batches, steps = make_steps(shape, n_steps, seed=rank)      # replicas: each rank its own stream
+    warm_batches, steps = make_steps(shape, n_steps, seed=rank, warm=args.warm_batches)   # replicas: own stream per rank
     m = build_module(shape, device, args.decay_mode, warm_batches[0][2][0])
     for s, d, t in warm_batches:
         m.update(s, d, t)
@@ -281,18 +282,26 @@ def main():
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     m.check_errors()
 
-    # -- dominant kernel (the 4BK-pair encoder launch): live CUDA-event timing, L2 flushed
-    pair_ms = []
-    for k in range(min(K, 50)):
-        ds = dsteps[W + k]
+    # -- dominant kernel (the 4BK-pair encoder launch): live CUDA-event timing, L2 flushed.
+    #    Each launch is captured alone in a CUDA graph so that no host launch latency sits
+    #    between the two events (the flush before it gives the host time to enqueue).
+    n_pair = min(K, 100)
+    pair_graphs = []
+    with torch.cuda.stream(side):
+        for k in range(n_pair):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, stream=side):
+                m.pair_wise_gram(*dsteps[W + k]['enc_pos'])
+            pair_graphs.append(g)
+    torch.cuda.synchronize()
+    pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_pair)]
+    for k in range(n_pair):
         flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = m.pair_wise_gram(*ds['enc_pos'])
-        b.record()
-        b.synchronize()
-        pair_ms.append(a.elapsed_time(b))
-    pair_ms_avg = float(np.mean(pair_ms))
+        pev[k][0].record()
+        pair_graphs[k].replay()
+        pev[k][1].record()
+    torch.cuda.synchronize()
+    pair_ms_avg = float(np.mean([a.elapsed_time(b) for a, b in pev]))
     pairs_per_launch = len(dsteps[0]['enc_pos'][0])
 
     # -- end to end through the public numpy API (pinned H2D + head + scalar D2H per step)

@@ -88,8 +88,9 @@ const char* tpn_last_cuda_error(void);
 /* SM count / compute capability of the current device (checks the library can run here). */
 int tpn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
-/* Scratch bytes tpn_update needs for a batch of `batch` edges (monotone in batch). */
-size_t tpn_update_workspace_bytes(int64_t batch);
+/* Scratch bytes tpn_update needs for a batch of `batch` edges on state `st` (uses num_layer
+ * and row_stride only; monotone in batch up to the snapshot threshold). */
+size_t tpn_update_workspace_bytes(const tpn_state_t* st, int64_t batch);
 
 /*
  * RandomProjectionModule.update — TPNet.py:67-99.

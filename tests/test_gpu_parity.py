@@ -143,11 +143,13 @@ def stream(rng, N, B, nb, skew, t0=0.0, span=500.0, equal_times=False):
 
 @pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('B,N,dim,L', [(200, 300, 20, 2), (3000, 500, 24, 3), (2500, 4000, 150, 3), (777, 90, 7, 4),
-                                       (1, 10, 4, 1)])
+                                       (1, 10, 4, 1), (512, 64, 12, 3), (40000, 5000, 24, 3), (33000, 700, 40, 1)])
 def test_update_bit_exact_with_equal_timestamps(B, N, dim, L, mode):
     """With one timestamp per batch every w_j is exactly 1, so the CUDA path must equal the
     oracle bit for bit: decay chain, stable sort-by-target (bitonic for 2B<=4096, radix
-    above), batch-order sequential sums, top-down layers."""
+    above), batch-order sequential sums, top-down layers.  Sizes cover every code path:
+    rank sort (2B<=1024), bitonic (<=4096), radix; snapshot + all-layer walk (2B<=65536) and
+    the per-layer walk above that."""
     rng = np.random.default_rng(B + N)
     kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=2e-6, use_matrix=False,
               beginning_time=0.0, not_scale=False, enforce_dim=dim)

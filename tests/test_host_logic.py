@@ -35,8 +35,9 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
         assert hasattr(raw, sym), sym
     assert lib.tpn_version() == _lib.ABI_VERSION
     assert lib.tpn_error_string(0) == b'ok'
-    assert lib.tpn_update_workspace_bytes(200) > 0
-    assert lib.tpn_update_workspace_bytes(100000) > lib.tpn_update_workspace_bytes(200)
+    st = _lib.TpnState(num_layer=3, row_stride=144)
+    assert lib.tpn_update_workspace_bytes(ctypes.byref(st), 200) > 0
+    assert lib.tpn_update_workspace_bytes(ctypes.byref(st), 100000) > lib.tpn_update_workspace_bytes(ctypes.byref(st), 200)
 
 
 def test_struct_layout_matches_header():

@@ -62,7 +62,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.tpn_device_info.restype = c_int
     lib.tpn_device_info.argtypes = [POINTER(c_int), POINTER(c_int), POINTER(c_int)]
     lib.tpn_update_workspace_bytes.restype = c_size_t
-    lib.tpn_update_workspace_bytes.argtypes = [c_int64]
+    lib.tpn_update_workspace_bytes.argtypes = [POINTER(TpnState), c_int64]
     lib.tpn_update.restype = c_int
     lib.tpn_update.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_double, c_float,
                                POINTER(c_float), c_void_p, c_size_t, c_void_p, c_void_p]

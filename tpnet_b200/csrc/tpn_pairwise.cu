@@ -7,12 +7,16 @@
 // d ~ 100-200: ~3 flop/byte, far below the fp32 ridge, so this is a gather-bound kernel
 // and tensor cores are deliberately not used.
 //
-// Mapping: G = 8 lanes per pair, 4 pairs per warp.  Lane j of a group reads float4
-// columns j, j+8, ... of all R rows (the group reads 128 contiguous bytes per row per
-// step; a node's L+1 rows are one contiguous block in the node-major state), keeps the
-// R(R+1)/2 unique dot products in registers, reduces them over the 8 lanes with shuffles,
-// applies the epilogue once per unique entry and mirrors it through shared memory so the
-// warp writes its 4 * R*R outputs as coalesced 128-bit streaming stores.
+// Mapping: G lanes per pair (G = 8: 4 pairs per warp, throughput shape; G = 32: one pair
+// per warp, latency shape for the small decoder calls).  Lane j of a group reads float4
+// columns j, j+G, ... of all R rows (the group reads G*16 contiguous bytes per row per
+// step; a node's L+1 rows are one contiguous block in the node-major state) and keeps the
+// R(R+1)/2 unique dot products in registers as packed (even, odd) float2 partial sums fed
+// by the sm_100 packed FFMA2.  The sums are reduced over the group with a transposing
+// butterfly (each shuffle step halves the number of live values), so every lane ends up
+// owning NP/G finished entries, applies the epilogue to just those and mirrors them
+// through shared memory; the warp then writes its pairs' R*R outputs as coalesced
+// 128-bit streaming stores.
 // Lazy-decay mode: rows of layers >= 1 are brought current in registers (replay of the
 // logged fp32 factors) before they enter the products; nothing is written back.
 #include "tpn_common.cuh"
@@ -21,27 +25,43 @@ namespace tpn {
 namespace {
 
 constexpr int kPairThreads = 128;
-constexpr int kGroup = 8;
-constexpr int kPairsPerWarp = 32 / kGroup;
-constexpr int kPairsPerBlock = kPairThreads / kGroup;
 
-template <int LAYERS, bool LAZY>
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
+// One butterfly step over N live values: lanes whose `mask` bit is set keep the upper half.
+template <int N>
+__device__ __forceinline__ void halve(float (&v)[N], int n, int mask, bool upper) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        if (i < n / 2) {
+            const float send = upper ? v[i] : v[i + n / 2];
+            const float keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+    }
+}
+
+template <int LAYERS, int G, bool LAZY>
 __global__ void __launch_bounds__(kPairThreads)
 pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long long* __restrict__ b_ids,
                 long long n, int apply_log_scale, float* __restrict__ out, int ds4) {
     constexpr int H = LAYERS + 1;          // rows per endpoint
     constexpr int R = 2 * H;               // rows per pair
     constexpr int F = R * R;               // outputs per pair
-    __shared__ __align__(16) float tile[kPairThreads / 32][kPairsPerWarp * F];
+    constexpr int NU = R * (R + 1) / 2;    // unique Gram entries
+    constexpr int NP = (NU + G - 1) / G * G;   // padded so the butterfly divides evenly
+    constexpr int PPW = 32 / G;            // pairs per warp
+    __shared__ __align__(16) float tile[kPairThreads / 32][PPW * F];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int sub = lane / kGroup;         // pair slot inside the warp
-    const int gl = lane % kGroup;          // lane inside the group
-    const long long pair0 = ((long long)blockIdx.x * (kPairThreads / 32) + warp) * kPairsPerWarp;
+    const int sub = lane / G;              // pair slot inside the warp
+    const int gl = lane % G;               // lane inside the group
+    const long long pair0 = ((long long)blockIdx.x * (kPairThreads / 32) + warp) * PPW;
     if (pair0 >= n) return;                // whole warp out of range
     const long long pair = pair0 + sub;
-    const long long pc = pair < n ? pair : n - 1;          // clamp: inactive groups redo the last pair, never store
+    const long long pc = pair < n ? pair : n - 1;          // inactive groups redo the last pair, never store
 
     long long ida = a_ids[pc], idb = b_ids[pc];
     // ids are validated on the host for numpy inputs; clamp so a bad device id can never fault
@@ -59,11 +79,11 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
         }
     }
 
-    float acc[R * (R + 1) / 2];
+    float2 acc[NU];
 #pragma unroll
-    for (int i = 0; i < R * (R + 1) / 2; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NU; ++i) acc[i] = make_float2(0.f, 0.f);
 
-    for (int c = gl; c < ds4; c += kGroup) {
+    for (int c = gl; c < ds4; c += G) {
         float4 x[R];
 #pragma unroll
         for (int l = 0; l < H; ++l) {
@@ -89,54 +109,54 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
         int e = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
+            const float2 rl = lo2(x[r]), rh = hi2(x[r]);
 #pragma unroll
             for (int q = r; q < R; ++q) {
-                float s = acc[e];
-                s = fmaf(x[r].x, x[q].x, s);
-                s = fmaf(x[r].y, x[q].y, s);
-                s = fmaf(x[r].z, x[q].z, s);
-                s = fmaf(x[r].w, x[q].w, s);
-                acc[e] = s;
+                acc[e] = __ffma2_rn(rl, lo2(x[q]), acc[e]);
+                acc[e] = __ffma2_rn(rh, hi2(x[q]), acc[e]);
                 ++e;
             }
         }
     }
 
-    // reduce over the 8 lanes of the group
+    // transposing butterfly over the G lanes of the group: NP values -> NP/G per lane
+    float s[NP];
 #pragma unroll
-    for (int i = 0; i < R * (R + 1) / 2; ++i) {
-        float s = acc[i];
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        acc[i] = s;
+    for (int i = 0; i < NP; ++i) s[i] = i < NU ? acc[i].x + acc[i].y : 0.f;
+    int first = 0;                         // index of the entry held in s[0] after the reduction
+    {
+        int nlive = NP;
+#pragma unroll
+        for (int mask = G / 2; mask >= 1; mask >>= 1) {
+            const bool upper = (gl & mask) != 0;
+            halve<NP>(s, nlive, mask, upper);
+            nlive >>= 1;
+            if (upper) first += nlive;
+        }
     }
 
-    // epilogue: unique entry e is finished by lane (e mod 8) of the group and mirrored
+    // epilogue on the NP/G entries this lane owns; mirror through shared memory
     float* mine = &tile[warp][sub * F];
-    {
-        int e = 0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-#pragma unroll
-            for (int q = r; q < R; ++q) {
-                if ((e % kGroup) == gl) {
-                    float g = acc[e];
-                    if (apply_log_scale) {
-                        g = g < 0.f ? 0.f : g;                 // random_feature[random_feature < 0] = 0
-                        g = logf(__fadd_rn(g, 1.0f));          // torch.log(x + 1.0), not log1p
-                    }
-                    mine[r * R + q] = g;
-                    mine[q * R + r] = g;
-                }
-                ++e;
+    for (int k = 0; k < NP / G; ++k) {
+        const int e = first + k;
+        if (e < NU) {
+            int r = 0, rem = e;
+            while (rem >= R - r) { rem -= R - r; ++r; }     // unique entry e -> (r, q), q >= r
+            const int q = r + rem;
+            float g = s[k];
+            if (apply_log_scale) {
+                g = g < 0.f ? 0.f : g;                      // random_feature[random_feature < 0] = 0
+                g = logf(__fadd_rn(g, 1.0f));               // torch.log(x + 1.0), not log1p
             }
+            mine[r * R + q] = g;
+            mine[q * R + r] = g;
         }
     }
     __syncwarp();
-    // coalesced write-out of the warp's (up to) 4 pairs: 4*F floats, contiguous in `out`
+    // coalesced write-out of the warp's pairs: PPW*F floats, contiguous in `out`
     const long long left = n - pair0;
-    const int valid = (int)(left < kPairsPerWarp ? left : kPairsPerWarp) * F;     // multiple of 4 (F = 4 H^2)
+    const int valid = (int)(left < PPW ? left : PPW) * F;     // multiple of 4 (F = 4 H^2)
     float* dst = out + pair0 * F;
     const float* srcs = &tile[warp][0];
     for (int i = lane * 4; i < valid; i += 32 * 4) {
@@ -145,15 +165,25 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
     }
 }
 
+template <int LAYERS, int G>
+void launch_g(const StateView& v, const long long* a, const long long* b, long long n, int scale, float* out,
+              cudaStream_t s) {
+    constexpr int pairs_per_block = kPairThreads / G;
+    const unsigned grid = (unsigned)((n + pairs_per_block - 1) / pairs_per_block);
+    const int ds4 = (int)(v.row_stride / 4);
+    if (v.stamps != nullptr)
+        pairwise_kernel<LAYERS, G, true><<<grid, kPairThreads, 0, s>>>(v, a, b, n, scale, out, ds4);
+    else
+        pairwise_kernel<LAYERS, G, false><<<grid, kPairThreads, 0, s>>>(v, a, b, n, scale, out, ds4);
+}
+
 template <int LAYERS>
 void launch(const StateView& v, const long long* a, const long long* b, long long n, int scale, float* out,
             cudaStream_t s) {
-    const unsigned grid = (unsigned)((n + kPairsPerBlock - 1) / kPairsPerBlock);
-    const int ds4 = (int)(v.row_stride / 4);
-    if (v.stamps != nullptr)
-        pairwise_kernel<LAYERS, true><<<grid, kPairThreads, 0, s>>>(v, a, b, n, scale, out, ds4);
-    else
-        pairwise_kernel<LAYERS, false><<<grid, kPairThreads, 0, s>>>(v, a, b, n, scale, out, ds4);
+    // few pairs (decoder calls): one warp per pair fills more SMs and needs fewer
+    // dependent round trips per pair; many pairs: 8 lanes per pair wastes no lanes on d ~ 140
+    if (n <= 4096) launch_g<LAYERS, 32>(v, a, b, n, scale, out, s);
+    else launch_g<LAYERS, 8>(v, a, b, n, scale, out, s);
 }
 
 }  // namespace

@@ -5,19 +5,26 @@
 //                  2B messages  m <  B : target src[m], source dst[m]            (first scatter_add_, :93)
 //                               m >= B : target dst[m-B], source src[m-B]        (second scatter_add_, :95)
 //                  lazy mode: append c_1..c_L to the decay log as a new epoch.
-//   2. sort      : stable sort of the message indices by target id, so that each
-//                  target's messages are contiguous and in the reference's
-//                  accumulation order (batch order within the src role, then the
-//                  dst role).  B <= 2048: one CTA, bitonic network in shared memory
-//                  on (target << 32 | m).  Larger: LSD radix sort, 8-bit digits,
-//                  warp-match ranking (integer atomics only on histogram counts).
-//   3. sweep     : eager mode only — P_l *= c_l over the whole state          (TPNet.py:83-85)
-//   4. walk      : one launch per layer i = L..1 (top-down, TPNet.py:90, so layer i
-//                  reads the pre-batch layer i-1).  A group of G lanes owns one target
-//                  row: reads it once, replays pending decay (lazy), adds its messages
-//                  sequentially as fadd_rn(acc, fmul_rn(P_{i-1}[v], w)), writes it once.
-//                  128-bit loads/stores; consecutive lanes read consecutive float4.
-//                  No float atomics anywhere: one owner per target row.
+//   2. sort      : stable sort of the messages by target id, so that each target's
+//                  messages are contiguous and in the reference's accumulation order
+//                  (batch order within the src role, then the dst role).
+//                    2B <= 1024 : one CTA, rank sort in shared memory (one barrier)
+//                    2B <= 4096 : one CTA, bitonic network on (target << 32 | m)
+//                    larger     : LSD radix sort, 8-bit digits, warp-match ranking
+//                                 (integer atomics only on histogram counts).
+//   3. sweep     : eager mode only — P_l *= c_l over the whole state          (TPNet.py:83-85).
+//                  For 2B <= 4096 it runs in the SAME launch as prep (block 0 sorts while
+//                  the other blocks sweep).
+//   4. walk      : each target row is owned by one group of lanes: read once, pending decay
+//                  replayed (lazy), messages added one at a time in order as
+//                  fadd_rn(acc, fmul_rn(source, w)), written once.  128-bit accesses, several
+//                  source rows in flight per group.  No float atomics anywhere.
+//                  Layer i must read the PRE-batch layer i-1 (TPNet.py:90 goes top-down):
+//                    2B <= kSnapMaxMsgs : the pre-batch rows 1..L-1 of the batch's nodes are
+//                        copied to a snapshot (every source node is also a target), then ONE
+//                        launch updates all layers, reading layer 0 from the state and
+//                        layers >= 1 from the snapshot;
+//                    larger : one launch per layer, top-down (no extra traffic).
 #include "tpn_common.cuh"
 
 namespace tpn {
@@ -25,6 +32,9 @@ namespace tpn {
 namespace {
 
 constexpr int kSmallMaxMsgs = 4096;      // 2B <= 4096 -> single-CTA sort
+constexpr int kRankMaxMsgs = 1024;       // 2B <= 1024 -> rank sort (one barrier) instead of the bitonic network
+constexpr int kSnapMaxMsgs = 65536;      // 2B <= 65536 -> snapshot + single all-layer walk launch
+constexpr int kPrepThreads = 1024;
 constexpr int kRadixThreads = 256;
 constexpr int kRadixItems = 8;
 constexpr int kRadixTile = kRadixThreads * kRadixItems;   // 2048 keys per block
@@ -45,12 +55,14 @@ struct Workspace {
     uint32_t* ssrc;    // [E] source node of the p-th sorted message
     float* sw;         // [E] weight of the p-th sorted message
     uint32_t* hist;    // [256 * nblk]
+    uint32_t* sslot;   // [E] sorted position of the segment head of the p-th message's SOURCE node
+    float* snap;       // [E][(L-1)*row_stride] pre-batch rows 1..L-1 of each target (snapshot path only)
     size_t bytes;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-Workspace carve(void* base, int64_t batch) {
+Workspace carve(void* base, int64_t batch, int num_layer, int64_t row_stride) {
     const size_t E = 2 * (size_t)batch;
     const size_t nblk = (E + kRadixTile - 1) / kRadixTile;
     char* p = reinterpret_cast<char*>(base);
@@ -65,6 +77,9 @@ Workspace carve(void* base, int64_t batch) {
     ws.ssrc = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.sw = reinterpret_cast<float*>(take(4 * E));
     ws.hist = reinterpret_cast<uint32_t*>(take(4 * kRadixBins * (nblk + 1)));
+    ws.sslot = reinterpret_cast<uint32_t*>(take(4 * E));
+    const size_t snap_rows = E <= (size_t)kSnapMaxMsgs ? E : 0;
+    ws.snap = reinterpret_cast<float*>(take(sizeof(float) * snap_rows * (size_t)(num_layer - 1) * row_stride + 16));
     ws.bytes = off;
     return ws;
 }
@@ -79,21 +94,49 @@ __device__ __forceinline__ float edge_weight(double t, float t_last_f, float neg
 }
 
 // ---------------------------------------------------------------- small path
-__global__ void __launch_bounds__(1024)
+// Block 0: weights + stable sort + sorted payload (+ decay-log append).  Blocks >= 1 (eager
+// mode with a clock move only): the whole-state decay sweep, overlapped with the sort.
+struct SweepArgs {
+    long long total4;      // float4 to scale (0 = no sweep)
+    int ds4;
+};
+
+__device__ __forceinline__ void sweep_body(const StateView& st, const DecayArgs& decay, long long total4, int ds4,
+                                           long long first, long long stride) {
+    // layers 1..L of a node are contiguous right after its layer-0 row
+    const long long per_node4 = (long long)st.num_layer * ds4;
+    for (long long i = first; i < total4; i += stride) {
+        const long long node = i / per_node4;
+        const int r = (int)(i - node * per_node4);
+        const int li = r / ds4;
+        float* p = st.data + node * st.node_stride + st.row_stride + (long long)r * 4;
+        float4 x = ld4(p);
+        scale4(x, decay.c[li]);
+        st4(p, x);
+    }
+}
+
+__global__ void __launch_bounds__(kPrepThreads)
 prep_small_kernel(const long long* __restrict__ src, const long long* __restrict__ dst,
                   const double* __restrict__ t, int B, float t_last_f, float neg_lambda, long long num_nodes,
                   uint32_t* __restrict__ skey, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
-                  int* __restrict__ err_flag, float* decay_log, int L, long long new_epoch, DecayArgs decay) {
-    __shared__ unsigned long long comp[kSmallMaxMsgs];
+                  uint32_t* __restrict__ sslot, int* __restrict__ err_flag, float* decay_log, int L,
+                  long long new_epoch, DecayArgs decay, StateView st, SweepArgs sweep) {
+    if (blockIdx.x > 0) {
+        sweep_body(st, decay, sweep.total4, sweep.ds4, (long long)(blockIdx.x - 1) * kPrepThreads + threadIdx.x,
+                   (long long)(gridDim.x - 1) * kPrepThreads);
+        return;
+    }
+    __shared__ unsigned long long comp[kSmallMaxMsgs];       // (target << 32 | message index)
     __shared__ float wsm[kSmallMaxMsgs / 2];
     const int E = 2 * B;
-    int P = 1;
-    while (P < E) P <<= 1;
     if (threadIdx.x == 0 && decay_log != nullptr && decay.has_decay) {
         for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay.c[l];
     }
-    for (int m = threadIdx.x; m < P; m += blockDim.x) {
-        unsigned long long c = ~0ull;                       // padding sorts last
+    int P = E;
+    if (E > kRankMaxMsgs) { P = 1; while (P < E) P <<= 1; }
+    for (int m = threadIdx.x; m < P; m += kPrepThreads) {
+        unsigned long long c = ~0ull;                         // padding sorts last
         if (m < E) {
             const int j = m < B ? m : m - B;
             const long long tgt = m < B ? src[j] : dst[j];
@@ -107,10 +150,32 @@ prep_small_kernel(const long long* __restrict__ src, const long long* __restrict
         comp[m] = c;
     }
     __syncthreads();
+    if (E <= kRankMaxMsgs) {
+        // rank sort: position = number of composites smaller than mine (composites are unique,
+        // so this is the stable order); the same scan counts the keys below the SOURCE id,
+        // which is where the source node's own segment starts (every source is also a target)
+        for (int m = threadIdx.x; m < E; m += kPrepThreads) {
+            const unsigned long long mine = comp[m];
+            const int j = m < B ? m : m - B;
+            const uint32_t other = (uint32_t)(m < B ? dst[j] : src[j]);
+            const unsigned long long other_lo = (unsigned long long)other << 32;
+            int rank = 0, slot = 0;
+            for (int i = 0; i < E; ++i) {
+                const unsigned long long c = comp[i];        // same address across the warp: broadcast
+                rank += c < mine;
+                slot += c < other_lo;
+            }
+            skey[rank] = (uint32_t)(mine >> 32);
+            ssrc[rank] = other;
+            sw[rank] = wsm[j];
+            sslot[rank] = (uint32_t)slot;
+        }
+        return;
+    }
     // bitonic network on the composite (target, message index): total order == stable order
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            for (int i = threadIdx.x; i < P; i += kPrepThreads) {
                 const int ixj = i ^ j;
                 if (ixj > i) {
                     const unsigned long long a = comp[i], b = comp[ixj];
@@ -121,13 +186,22 @@ prep_small_kernel(const long long* __restrict__ src, const long long* __restrict
             __syncthreads();
         }
     }
-    for (int p = threadIdx.x; p < E; p += blockDim.x) {
+    for (int p = threadIdx.x; p < E; p += kPrepThreads) {
         const unsigned long long c = comp[p];
         const uint32_t m = (uint32_t)c;
         const int j = m < (uint32_t)B ? m : m - B;
+        const uint32_t other = (uint32_t)(m < (uint32_t)B ? dst[j] : src[j]);
         skey[p] = (uint32_t)(c >> 32);
-        ssrc[p] = (uint32_t)(m < (uint32_t)B ? dst[j] : src[j]);
+        ssrc[p] = other;
         sw[p] = wsm[j];
+        // lower bound of the source id among the sorted targets
+        const unsigned long long other_lo = (unsigned long long)other << 32;
+        int lo = 0, hi = E;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (comp[mid] < other_lo) lo = mid + 1; else hi = mid;
+        }
+        sslot[p] = (uint32_t)lo;
     }
 }
 
@@ -258,109 +332,168 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
 }
 
 __global__ void __launch_bounds__(256)
-payload_kernel(const uint32_t* __restrict__ order, const long long* __restrict__ src,
-               const long long* __restrict__ dst, const float* __restrict__ w, long long B, int E,
-               uint32_t* __restrict__ ssrc, float* __restrict__ sw) {
+payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ skey,
+               const long long* __restrict__ src, const long long* __restrict__ dst, const float* __restrict__ w,
+               long long B, int E, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
+               uint32_t* __restrict__ sslot) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= E) return;
     const uint32_t m = order[p];
     const long long j = m < B ? m : m - B;
-    ssrc[p] = (uint32_t)(m < B ? dst[j] : src[j]);
+    const uint32_t other = (uint32_t)(m < B ? dst[j] : src[j]);
+    ssrc[p] = other;
     sw[p] = w[j];
-}
-
-// ---------------------------------------------------------------- eager decay sweep
-__global__ void __launch_bounds__(256)
-sweep_decay_kernel(StateView st, DecayArgs decay, long long total4, int ds4) {
-    // layers 1..L of a node are contiguous right after its layer-0 row
-    const long long per_node4 = (long long)st.num_layer * ds4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long node = i / per_node4;
-        const int r = (int)(i - node * per_node4);
-        const int li = r / ds4;
-        float* p = st.data + node * st.node_stride + st.row_stride + (long long)r * 4;
-        float4 x = ld4(p);
-        scale4(x, decay.c[li]);
-        st4(p, x);
+    if (sslot != nullptr) {          // snapshot path: where the source node's own segment starts
+        int lo = 0, hi = E;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (skey[mid] < other) lo = mid + 1; else hi = mid;
+        }
+        sslot[p] = (uint32_t)lo;
     }
 }
 
-// ---------------------------------------------------------------- the walk update, one layer
-template <int G, int VPL, bool LAZY>
+// ---------------------------------------------------------------- eager decay sweep (large path)
+__global__ void __launch_bounds__(256)
+sweep_decay_kernel(StateView st, DecayArgs decay, long long total4, int ds4) {
+    sweep_body(st, decay, total4, ds4, (long long)blockIdx.x * blockDim.x + threadIdx.x,
+               (long long)gridDim.x * blockDim.x);
+}
+
+// ---------------------------------------------------------------- the walk update
+// Work item = (target segment, column tile).  A group of 8 lanes owns 8*V consecutive float4
+// of the target span, reads them once, replays pending decay (lazy), then walks the
+// segment's messages in order — D rows in flight at a time — adding
+// fadd_rn(acc, fmul_rn(source, w)), and writes the span back once.
+//   ALL = false : span = row `layer` of the target; sources = row layer-1 of the state
+//                 (launched per layer, top-down; lazy sources are replayed in registers).
+//   ALL = true  : span = rows 1..L of the target (contiguous in the node-major state);
+//                 source row 0 comes from the state (P_0 is never written), source rows
+//                 1..L-1 from the pre-batch snapshot taken by snapshot_kernel — one launch
+//                 covers all layers and still reads only pre-batch values (TPNet.py:90).
+template <int V, int D, bool LAZY, bool ALL>
 __global__ void __launch_bounds__(kWalkThreads)
-walk_update_layer_kernel(StateView st, int layer, const uint32_t* __restrict__ skey,
-                         const uint32_t* __restrict__ ssrc, const float* __restrict__ sw, int E, int ds4,
-                         int write_stamp) {
+walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ssrc,
+            const float* __restrict__ sw, const uint32_t* __restrict__ sslot, const float* __restrict__ snap,
+            int E, int ds4, int write_stamp) {
+    constexpr int G = 8;
     const int gid = (blockIdx.x * kWalkThreads + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
     if (gid >= E) return;
     const uint32_t key = skey[gid];
     if ((long long)key >= st.num_nodes) return;          // dropped edge (id out of range)
     if (gid > 0 && skey[gid - 1] == key) return;         // not the head of its segment
-    const int col0 = blockIdx.y * (G * VPL) + lane;      // float4 column of register 0
     const int L = st.num_layer;
+    const int span4 = ALL ? L * ds4 : ds4;               // float4 in the target span
+    const int snap4 = (L - 1) * ds4;                     // float4 per snapshot slot
+    const int col0 = blockIdx.y * (G * V) + lane;
 
-    float* trow = st.data + (long long)key * st.node_stride + (long long)layer * st.row_stride;
-    float4 acc[VPL];
-    long long tstamp = 0;
-    if (LAZY) tstamp = st.stamps[(long long)key * L + (layer - 1)];
+    float* tbase = st.data + (long long)key * st.node_stride + (long long)(ALL ? 1 : layer) * st.row_stride;
+    float4 acc[V];
+    int tli[V];                                          // decay-log column (target layer - 1) per register
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
+    for (int k = 0; k < V; ++k) {
         const int c = col0 + k * G;
-        acc[k] = (c < ds4 && (!LAZY || tstamp >= 0)) ? ld4(trow + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (LAZY && tstamp >= 0) replay<VPL>(acc, st.decay_log, L, layer - 1, tstamp, st.epoch);
-
-    const bool src_decays = LAZY && layer >= 2;          // P_0 never decays
-    int p = gid;
-    uint32_t v = ssrc[p];
-    float w = sw[p];
-    float4 x[VPL];
-    long long vstamp = 0;
-    {
-        const float* srow = st.data + (long long)v * st.node_stride + (long long)(layer - 1) * st.row_stride;
-        if (src_decays) vstamp = st.stamps[(long long)v * L + (layer - 2)];
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-            const int c = col0 + k * G;
-            x[k] = (c < ds4 && vstamp >= 0) ? ld4(srow + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        tli[k] = ALL ? (c < span4 ? c / ds4 : 0) : layer - 1;
+        long long tstamp = 0;
+        if (LAZY && c < span4) tstamp = st.stamps[(long long)key * L + tli[k]];
+        acc[k] = (c < span4 && tstamp >= 0) ? ld4(tbase + 4 * (long long)c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (LAZY && c < span4 && tstamp >= 0) {
+            float4 one[1] = {acc[k]};
+            replay<1>(one, st.decay_log, L, tli[k], tstamp, st.epoch);
+            acc[k] = one[0];
         }
     }
-    while (true) {
-        const int pn = p + 1;
-        const bool more = pn < E && skey[pn] == key;
-        float4 xn[VPL];
-        uint32_t vn = 0;
-        float wn = 0.f;
-        long long vnstamp = 0;
-        if (more) {                                       // issue the next row's loads before consuming this one
-            vn = ssrc[pn];
-            wn = sw[pn];
-            const float* srow = st.data + (long long)vn * st.node_stride + (long long)(layer - 1) * st.row_stride;
-            if (src_decays) vnstamp = st.stamps[(long long)vn * L + (layer - 2)];
+
+    int p = gid;
+    bool more = true;
+    while (more) {
+        // gather the next D messages of the segment: all row loads are issued before any add
+        float4 x[D][V];
+        float w[D];
+        int cnt = 0;
 #pragma unroll
-            for (int k = 0; k < VPL; ++k) {
-                const int c = col0 + k * G;
-                xn[k] = (c < ds4 && vnstamp >= 0) ? ld4(srow + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < D; ++j) {
+            const int pj = p + j;
+            const bool ok = more && pj < E && (j == 0 || skey[pj] == key);
+            if (!ok) more = false;
+            w[j] = 0.f;
+            if (ok) {
+                ++cnt;
+                const uint32_t v = ssrc[pj];
+                w[j] = sw[pj];
+                const float* sstate = st.data + (long long)v * st.node_stride +
+                                      (long long)(ALL ? 0 : layer - 1) * st.row_stride;
+                const float* ssnap = ALL ? snap + (long long)sslot[pj] * snap4 * 4 : nullptr;
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const int c = col0 + k * G;
+                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < span4) {
+                        if (ALL) {
+                            val = c < ds4 ? ld4(sstate + 4 * (long long)c) : ld4(ssnap + 4 * (long long)(c - ds4));
+                        } else {
+                            long long vstamp = 0;
+                            if (LAZY && layer >= 2) vstamp = st.stamps[(long long)v * L + (layer - 2)];
+                            if (vstamp >= 0) {
+                                val = ld4(sstate + 4 * (long long)c);
+                                if (LAZY && layer >= 2) {       // P_0 never decays
+                                    float4 one[1] = {val};
+                                    replay<1>(one, st.decay_log, L, layer - 2, vstamp, st.epoch);
+                                    val = one[0];
+                                }
+                            }
+                        }
+                    }
+                    x[j][k] = val;
+                }
             }
         }
-        if (src_decays && vstamp >= 0) replay<VPL>(x, st.decay_log, L, layer - 2, vstamp, st.epoch);
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) axpy4_rn(acc[k], x[k], w);
-        if (!more) break;
+        for (int j = 0; j < D; ++j) {
+            if (j < cnt) {
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) x[k] = xn[k];
-        v = vn; w = wn; vstamp = vnstamp; p = pn;
+                for (int k = 0; k < V; ++k) axpy4_rn(acc[k], x[j][k], w[j]);
+            }
+        }
+        p += cnt;
+        if (more) more = p < E && skey[p] == key;
     }
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
+    for (int k = 0; k < V; ++k) {
         const int c = col0 + k * G;
-        if (c < ds4) st4(trow + 4 * c, acc[k]);
+        if (c < span4) st4(tbase + 4 * (long long)c, acc[k]);
     }
     if (LAZY && write_stamp && lane == 0) st.stamps[(long long)key * L + (layer - 1)] = (int)st.epoch;
 }
 
+// Pre-batch copy of rows 1..L-1 of every target of the batch (brought current in lazy mode),
+// one warp per segment head; slot = sorted position of the head.
+template <bool LAZY>
+__global__ void __launch_bounds__(256)
+snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, int E, int ds4, float* __restrict__ snap) {
+    const int p = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= E) return;
+    const uint32_t key = skey[p];
+    if ((long long)key >= st.num_nodes) return;
+    if (p > 0 && skey[p - 1] == key) return;
+    const int L = st.num_layer;
+    const int snap4 = (L - 1) * ds4;
+    const float* rows = st.data + (long long)key * st.node_stride + st.row_stride;    // row 1
+    float* slot = snap + (long long)p * snap4 * 4;
+    for (int c = lane; c < snap4; c += 32) {
+        const int li = c / ds4;                         // layer - 1
+        long long stamp = 0;
+        if (LAZY) stamp = st.stamps[(long long)key * L + li];
+        float4 one[1];
+        one[0] = stamp >= 0 ? ld4(rows + 4 * (long long)c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (LAZY && stamp >= 0) replay<1>(one, st.decay_log, L, li, stamp, st.epoch);
+        st4(slot + 4 * (long long)c, one[0]);
+    }
+}
+
+// stamps of all layers (layer == 0) or one layer of every target <- current epoch
 __global__ void __launch_bounds__(256)
 stamp_targets_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, int E) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,35 +501,38 @@ stamp_targets_kernel(StateView st, int layer, const uint32_t* __restrict__ skey,
     const uint32_t key = skey[p];
     if ((long long)key >= st.num_nodes) return;
     if (p > 0 && skey[p - 1] == key) return;
-    st.stamps[(long long)key * st.num_layer + (layer - 1)] = (int)st.epoch;
+    if (layer >= 1) {
+        st.stamps[(long long)key * st.num_layer + (layer - 1)] = (int)st.epoch;
+    } else {
+        for (int l = 0; l < st.num_layer; ++l) st.stamps[(long long)key * st.num_layer + l] = (int)st.epoch;
+    }
 }
 
-template <int G, int VPL>
-void launch_walk(const StateView& v, int layer, const Workspace& ws, int E, int ds4, int col_tiles, bool lazy,
+template <int V, int D, bool ALL>
+void launch_walk(const StateView& v, int layer, const Workspace& ws, int E, int ds4, int tiles, bool lazy,
                  cudaStream_t stream) {
-    const long long groups = E;
-    dim3 grid((unsigned)((groups * G + kWalkThreads - 1) / kWalkThreads), (unsigned)col_tiles);
-    const int write_stamp = col_tiles == 1;
+    dim3 grid((unsigned)(((long long)E * 8 + kWalkThreads - 1) / kWalkThreads), (unsigned)tiles);
+    const int write_stamp = (!ALL && tiles == 1) ? 1 : 0;
     if (lazy)
-        walk_update_layer_kernel<G, VPL, true><<<grid, kWalkThreads, 0, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw,
-                                                                                  E, ds4, write_stamp);
+        walk_kernel<V, D, true, ALL><<<grid, kWalkThreads, 0, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
+                                                                        ws.snap, E, ds4, write_stamp);
     else
-        walk_update_layer_kernel<G, VPL, false><<<grid, kWalkThreads, 0, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw,
-                                                                                   E, ds4, write_stamp);
+        walk_kernel<V, D, false, ALL><<<grid, kWalkThreads, 0, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
+                                                                         ws.snap, E, ds4, write_stamp);
 }
 
-template <int G>
-void dispatch_walk(int vpl, const StateView& v, int layer, const Workspace& ws, int E, int ds4, int col_tiles,
-                   bool lazy, cudaStream_t s) {
+// per-layer walk: V float4 per lane so that one tile covers rows up to 256 floats
+void dispatch_layer_walk(int vpl, const StateView& v, int layer, const Workspace& ws, int E, int ds4, int tiles,
+                         bool lazy, cudaStream_t s) {
     switch (vpl) {
-        case 1: launch_walk<G, 1>(v, layer, ws, E, ds4, col_tiles, lazy, s); break;
-        case 2: launch_walk<G, 2>(v, layer, ws, E, ds4, col_tiles, lazy, s); break;
-        case 3: launch_walk<G, 3>(v, layer, ws, E, ds4, col_tiles, lazy, s); break;
-        case 4: launch_walk<G, 4>(v, layer, ws, E, ds4, col_tiles, lazy, s); break;
-        case 5: launch_walk<G, 5>(v, layer, ws, E, ds4, col_tiles, lazy, s); break;
-        case 6: launch_walk<G, 6>(v, layer, ws, E, ds4, col_tiles, lazy, s); break;
-        case 7: launch_walk<G, 7>(v, layer, ws, E, ds4, col_tiles, lazy, s); break;
-        default: launch_walk<G, 8>(v, layer, ws, E, ds4, col_tiles, lazy, s); break;
+        case 1: launch_walk<1, 8, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
+        case 2: launch_walk<2, 8, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
+        case 3: launch_walk<3, 4, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
+        case 4: launch_walk<4, 4, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
+        case 5: launch_walk<5, 4, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
+        case 6: launch_walk<6, 3, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
+        case 7: launch_walk<7, 2, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
+        default: launch_walk<8, 2, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
     }
 }
 
@@ -404,9 +540,10 @@ void dispatch_walk(int vpl, const StateView& v, int layer, const Workspace& ws, 
 
 }  // namespace tpn
 
-extern "C" size_t tpn_update_workspace_bytes(int64_t batch) {
+extern "C" size_t tpn_update_workspace_bytes(const tpn_state_t* st, int64_t batch) {
     if (batch < 1) batch = 1;
-    return tpn::carve(nullptr, batch).bytes;
+    if (st == nullptr) return 0;
+    return tpn::carve(nullptr, batch, st->num_layer, st->row_stride).bytes;
 }
 
 extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t* dst_dev, const double* t_dev,
@@ -415,10 +552,10 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
     using namespace tpn;
     int rc = validate_state(st);
     if (rc != TPN_OK) return rc;
-    if (batch < 1 || batch > (int64_t)0x3fffffff || src_dev == nullptr || dst_dev == nullptr || t_dev == nullptr ||
+    if (batch < 1 || batch > ((int64_t)1 << 26) || src_dev == nullptr || dst_dev == nullptr || t_dev == nullptr ||
         ws_dev == nullptr || st->num_nodes >= (int64_t)0xffffffffll)
         return TPN_ERR_INVALID_ARGUMENT;
-    Workspace ws = carve(ws_dev, batch);
+    Workspace ws = carve(ws_dev, batch, st->num_layer, st->row_stride);
     if (ws.bytes > ws_bytes) return TPN_ERR_WORKSPACE_TOO_SMALL;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     const bool lazy = st->stamps != nullptr;
@@ -442,14 +579,30 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
     }
 
     const int E = (int)(2 * batch);
+    const int ds4 = (int)(st->row_stride / 4);
     const float t_last_f = (float)t_last;
     const long long* src = reinterpret_cast<const long long*>(src_dev);
     const long long* dst = reinterpret_cast<const long long*>(dst_dev);
     float* log_w = lazy ? st->decay_log : nullptr;
+    const bool snapshot_path = E <= kSnapMaxMsgs && L >= 1;
+    const bool eager_sweep = !lazy && dargs.has_decay;
+    const long long sweep_total4 = st->num_nodes * (long long)L * ds4;
+
+    st->epoch = new_epoch;
+    const StateView view = make_view(st);
 
     if (E <= kSmallMaxMsgs) {
-        prep_small_kernel<<<1, 1024, 0, stream>>>(src, dst, t_dev, (int)batch, t_last_f, neg_lambda, st->num_nodes,
-                                                  ws.key_a, ws.ssrc, ws.sw, err_flag_dev, log_w, L, new_epoch, dargs);
+        SweepArgs sw_args;
+        sw_args.total4 = eager_sweep ? sweep_total4 : 0;
+        sw_args.ds4 = ds4;
+        unsigned grid = 1;
+        if (eager_sweep) {
+            const long long want = (sweep_total4 + kPrepThreads - 1) / kPrepThreads;
+            grid += (unsigned)(want < 148 * 4 ? (want < 1 ? 1 : want) : 148 * 4);
+        }
+        prep_small_kernel<<<grid, kPrepThreads, 0, stream>>>(src, dst, t_dev, (int)batch, t_last_f, neg_lambda,
+                                                             st->num_nodes, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
+                                                             err_flag_dev, log_w, L, new_epoch, dargs, view, sw_args);
     } else {
         prep_large_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, stream>>>(
             src, dst, t_dev, batch, t_last_f, neg_lambda, st->num_nodes, ws.w, ws.key_a, ws.val_a, err_flag_dev, log_w,
@@ -469,32 +622,38 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
         if (kin != ws.key_a) {       // odd number of passes: sorted keys live in key_b
             cudaMemcpyAsync(ws.key_a, kin, sizeof(uint32_t) * E, cudaMemcpyDeviceToDevice, stream);
         }
-        payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(vin, src, dst, ws.w, batch, E, ws.ssrc, ws.sw);
-    }
-    st->epoch = new_epoch;
-    StateView view = make_view(st);
-
-    const int ds4 = (int)(st->row_stride / 4);
-    if (!lazy && dargs.has_decay) {
-        const long long total4 = st->num_nodes * (long long)L * ds4;
-        const long long want = (total4 + 255) / 256;
-        const unsigned grid = (unsigned)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
-        sweep_decay_kernel<<<grid, 256, 0, stream>>>(view, dargs, total4, ds4);
+        payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(vin, ws.key_a, src, dst, ws.w, batch, E, ws.ssrc, ws.sw,
+                                                            snapshot_path ? ws.sslot : nullptr);
+        if (eager_sweep) {
+            const long long want = (sweep_total4 + 255) / 256;
+            const unsigned grid = (unsigned)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
+            sweep_decay_kernel<<<grid, 256, 0, stream>>>(view, dargs, sweep_total4, ds4);
+        }
     }
 
-    // lanes per target row: 8 for rows up to 256 floats, else a full warp; <= 8 float4 per lane per column tile
-    const int G = ds4 <= 64 ? 8 : 32;
-    int vpl = (ds4 + G - 1) / G;
-    int col_tiles = 1;
-    if (vpl > 8) {
-        col_tiles = (vpl + 7) / 8;
-        vpl = 8;
-    }
-    for (int layer = L; layer >= 1; --layer) {
-        if (G == 8) dispatch_walk<8>(vpl, view, layer, ws, E, ds4, col_tiles, lazy, stream);
-        else dispatch_walk<32>(vpl, view, layer, ws, E, ds4, col_tiles, lazy, stream);
-        if (lazy && col_tiles > 1)
-            stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, layer, ws.key_a, E);
+    if (snapshot_path) {
+        if (L >= 2) {
+            const unsigned grid = (unsigned)(((long long)E * 32 + 255) / 256);
+            if (lazy) snapshot_kernel<true><<<grid, 256, 0, stream>>>(view, ws.key_a, E, ds4, ws.snap);
+            else snapshot_kernel<false><<<grid, 256, 0, stream>>>(view, ws.key_a, E, ds4, ws.snap);
+        }
+        // one float4 per lane for latency-bound batches, two once there is enough work to fill the GPU
+        const int span4 = L * ds4;
+        if (E <= 8192) launch_walk<1, 8, true>(view, 0, ws, E, ds4, (span4 + 7) / 8, lazy, stream);
+        else launch_walk<2, 8, true>(view, 0, ws, E, ds4, (span4 + 15) / 16, lazy, stream);
+        if (lazy) stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, 0, ws.key_a, E);
+    } else {
+        int vpl = (ds4 + 7) / 8;
+        int tiles = 1;
+        if (vpl > 8) {
+            tiles = (vpl + 7) / 8;
+            vpl = 8;
+        }
+        for (int layer = L; layer >= 1; --layer) {
+            dispatch_layer_walk(vpl, view, layer, ws, E, ds4, tiles, lazy, stream);
+            if (lazy && tiles > 1)
+                stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, layer, ws.key_a, E);
+        }
     }
     return check_launch();
 }

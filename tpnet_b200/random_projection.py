@@ -278,12 +278,12 @@ class RandomProjectionModule(nn.Module):
                                                       for i in range(1, self.num_layer + 1)])
         ptrs = self._ids_to_device([src_node_ids, dst_node_ids, node_interact_times], ['id', 'id', 'time'],
                                    wrap_negative=False)
-        need = lib.tpn_update_workspace_bytes(n)
+        st = self._c_state()
+        need = lib.tpn_update_workspace_bytes(ctypes.byref(st), n)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
         if self._err is None:
             self._err = torch.zeros(1, dtype=torch.int32, device=dev)
-        st = self._c_state()
         args = (ptrs[0], ptrs[1], ptrs[2], n, float(next_time), float(np.float32(-lam)), factors,
                 self._ws.data_ptr(), self._ws.numel(), self._err.data_ptr(), self._stream())
         rc = lib.tpn_update(ctypes.byref(st), *args)
