@@ -83,13 +83,21 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
 #pragma unroll
     for (int i = 0; i < NU; ++i) acc[i] = make_float2(0.f, 0.f);
 
-    for (int c = gl; c < ds4; c += G) {
-        float4 x[R];
+    // software pipeline: the rows of column step i+1 are requested before step i is consumed
+    auto load_rows = [&](float4 (&x)[R], int c) {
 #pragma unroll
         for (int l = 0; l < H; ++l) {
             x[l] = ld4(pa + (long long)l * st.row_stride + 4 * c);
             x[H + l] = ld4(pb + (long long)l * st.row_stride + 4 * c);
         }
+    };
+    float4 nxt[R];
+    if (gl < ds4) load_rows(nxt, gl);
+    for (int c = gl; c < ds4; c += G) {
+        float4 x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = nxt[r];
+        if (c + G < ds4) load_rows(nxt, c + G);
         if (LAZY) {
 #pragma unroll
             for (int l = 1; l < H; ++l) {
@@ -165,6 +173,219 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
     }
 }
 
+// ---------------------------------------------------------------- TMA (bulk-copy) variant
+// Same math, different data movement: the L+1 rows of a node are ONE contiguous block of
+// (L+1)*row_stride*4 bytes in the node-major state, so a warp fetches everything its 4 pairs
+// need with at most 8 `cp.async.bulk` copies (global -> shared, completion counted on a
+// per-warp mbarrier) issued by one lane.  The whole working set of the warp is in flight at
+// once (no per-lane load instructions, no register staging, no dependent round trips per
+// column step), and b-endpoints repeated by consecutive pairs — the encoder's pair lists
+// repeat each b K times (TPNet.py:313-316) — are fetched once per warp.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int LAYERS, bool LAZY>
+__global__ void __launch_bounds__(kPairThreads)
+pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const long long* __restrict__ b_ids,
+                    long long n, int apply_log_scale, float* __restrict__ out, int ds4) {
+    constexpr int G = 8;
+    constexpr int H = LAYERS + 1;
+    constexpr int R = 2 * H;
+    constexpr int F = R * R;
+    constexpr int NU = R * (R + 1) / 2;
+    constexpr int NP = (NU + G - 1) / G * G;
+    constexpr int PPW = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar[kPairThreads / 32];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G;
+    const int gl = lane % G;
+    const long long pair0 = ((long long)blockIdx.x * (kPairThreads / 32) + warp) * PPW;
+    if (pair0 >= n) return;
+    const long long pair = pair0 + sub;
+    const long long pc = pair < n ? pair : n - 1;
+
+    long long ida = a_ids[pc], idb = b_ids[pc];
+    ida = ida < 0 ? 0 : (ida >= st.num_nodes ? st.num_nodes - 1 : ida);
+    idb = idb < 0 ? 0 : (idb >= st.num_nodes ? st.num_nodes - 1 : idb);
+
+    const uint32_t block_bytes = (uint32_t)(H * st.row_stride * 4);       // rows P_0..P_L of one node
+    unsigned char* wbase = smem_raw + (size_t)warp * (2 * PPW) * block_bytes;
+    uint64_t* bar = &mbar[warp];
+
+    // b endpoints of the warp's 4 pairs; a run of equal ids shares one slot
+    long long bid[PPW];
+#pragma unroll
+    for (int s = 0; s < PPW; ++s) bid[s] = __shfl_sync(0xffffffffu, idb, s * G);
+    int sb = sub;
+#pragma unroll
+    for (int s = PPW - 1; s >= 1; --s)
+        if (sb == s && bid[s] == bid[s - 1]) sb = s - 1;
+
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t copies = PPW;
+#pragma unroll
+        for (int s = 0; s < PPW; ++s) copies += (s == 0 || bid[s] != bid[s - 1]) ? 1u : 0u;
+        mbar_expect_tx(bar, copies * block_bytes);
+    }
+    __syncwarp();                                   // expect_tx is registered before any copy can complete
+    // lanes 0, 8, 16, 24 own one pair each: fetch its a block, and its b block unless shared
+    if (gl == 0) {
+        bulk_g2s(wbase + (size_t)sub * block_bytes, st.data + ida * st.node_stride, block_bytes, bar);
+        if (sb == sub)
+            bulk_g2s(wbase + (size_t)(PPW + sub) * block_bytes, st.data + idb * st.node_stride, block_bytes, bar);
+    }
+
+    long long stamp[R];
+    if (LAZY) {
+#pragma unroll
+        for (int l = 1; l < H; ++l) {
+            stamp[l] = st.stamps[ida * LAYERS + (l - 1)];
+            stamp[H + l] = st.stamps[idb * LAYERS + (l - 1)];
+        }
+    }
+    float2 acc[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) acc[i] = make_float2(0.f, 0.f);
+
+    const float* pa = reinterpret_cast<const float*>(wbase + (size_t)sub * block_bytes);
+    const float* pb = reinterpret_cast<const float*>(wbase + (size_t)(PPW + sb) * block_bytes);
+    mbar_wait(bar, 0);
+
+    for (int c = gl; c < ds4; c += G) {
+        float4 x[R];
+#pragma unroll
+        for (int l = 0; l < H; ++l) {
+            x[l] = ld4(pa + (long long)l * st.row_stride + 4 * c);
+            x[H + l] = ld4(pb + (long long)l * st.row_stride + 4 * c);
+        }
+        if (LAZY) {
+#pragma unroll
+            for (int l = 1; l < H; ++l) {
+                float4 one[1];
+                if (stamp[l] >= 0) {
+                    one[0] = x[l];
+                    replay<1>(one, st.decay_log, LAYERS, l - 1, stamp[l], st.epoch);
+                    x[l] = one[0];
+                }
+                if (stamp[H + l] >= 0) {
+                    one[0] = x[H + l];
+                    replay<1>(one, st.decay_log, LAYERS, l - 1, stamp[H + l], st.epoch);
+                    x[H + l] = one[0];
+                }
+            }
+        }
+        int e = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float2 rl = lo2(x[r]), rh = hi2(x[r]);
+#pragma unroll
+            for (int q = r; q < R; ++q) {
+                acc[e] = __ffma2_rn(rl, lo2(x[q]), acc[e]);
+                acc[e] = __ffma2_rn(rh, hi2(x[q]), acc[e]);
+                ++e;
+            }
+        }
+    }
+
+    float s[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) s[i] = i < NU ? acc[i].x + acc[i].y : 0.f;
+    int first = 0;
+    {
+        int nlive = NP;
+#pragma unroll
+        for (int mask = G / 2; mask >= 1; mask >>= 1) {
+            const bool upper = (gl & mask) != 0;
+            halve<NP>(s, nlive, mask, upper);
+            nlive >>= 1;
+            if (upper) first += nlive;
+        }
+    }
+    __syncwarp();                                   // every lane is done reading the row buffers
+    float* tile = reinterpret_cast<float*>(wbase);  // reuse them as the output staging tile
+    float* mine = tile + sub * F;
+#pragma unroll
+    for (int k = 0; k < NP / G; ++k) {
+        const int e = first + k;
+        if (e < NU) {
+            int r = 0, rem = e;
+            while (rem >= R - r) { rem -= R - r; ++r; }
+            const int q = r + rem;
+            float g = s[k];
+            if (apply_log_scale) {
+                g = g < 0.f ? 0.f : g;
+                g = logf(__fadd_rn(g, 1.0f));
+            }
+            mine[r * R + q] = g;
+            mine[q * R + r] = g;
+        }
+    }
+    __syncwarp();
+    const long long left = n - pair0;
+    const int valid = (int)(left < PPW ? left : PPW) * F;
+    float* dst = out + pair0 * F;
+    for (int i = lane * 4; i < valid; i += 32 * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + i);
+        __stcs(reinterpret_cast<float4*>(dst + i), v);
+    }
+}
+
+template <int LAYERS>
+bool launch_tma(const StateView& v, const long long* a, const long long* b, long long n, int scale, float* out,
+                cudaStream_t s) {
+    constexpr int R = 2 * (LAYERS + 1);
+    const size_t block_bytes = (size_t)(LAYERS + 1) * v.row_stride * 4;
+    const size_t smem = (size_t)(kPairThreads / 32) * 8 * block_bytes;
+    // the staging tile (4 pairs * R*R floats) aliases the row buffers; keep >= 2 CTAs per SM
+    if (smem > 110 * 1024 || 4 * R * R * sizeof(float) > 8 * block_bytes || (block_bytes & 15) != 0 ||
+        (v.node_stride & 3) != 0)
+        return false;
+    static bool configured[2] = {false, false};
+    const bool lazy = v.stamps != nullptr;
+    auto kernel = lazy ? pairwise_tma_kernel<LAYERS, true> : pairwise_tma_kernel<LAYERS, false>;
+    if (!configured[lazy ? 1 : 0]) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return false;
+        }
+        configured[lazy ? 1 : 0] = true;
+    }
+    const unsigned grid = (unsigned)((n + 15) / 16);
+    kernel<<<grid, kPairThreads, smem, s>>>(v, a, b, n, scale, out, (int)(v.row_stride / 4));
+    return true;
+}
+
 template <int LAYERS, int G>
 void launch_g(const StateView& v, const long long* a, const long long* b, long long n, int scale, float* out,
               cudaStream_t s) {
@@ -182,8 +403,11 @@ void launch(const StateView& v, const long long* a, const long long* b, long lon
             cudaStream_t s) {
     // few pairs (decoder calls): one warp per pair fills more SMs and needs fewer
     // dependent round trips per pair; many pairs: 8 lanes per pair wastes no lanes on d ~ 140
-    if (n <= 4096) launch_g<LAYERS, 32>(v, a, b, n, scale, out, s);
-    else launch_g<LAYERS, 8>(v, a, b, n, scale, out, s);
+    if (n <= 4096) {
+        launch_g<LAYERS, 32>(v, a, b, n, scale, out, s);
+    } else if (!launch_tma<LAYERS>(v, a, b, n, scale, out, s)) {
+        launch_g<LAYERS, 8>(v, a, b, n, scale, out, s);          // rows too wide for the shared-memory staging
+    }
 }
 
 }  // namespace

@@ -56,6 +56,7 @@ struct Workspace {
     float* sw;         // [E] weight of the p-th sorted message
     uint32_t* hist;    // [256 * nblk]
     uint32_t* sslot;   // [E] sorted position of the segment head of the p-th message's SOURCE node
+    uint32_t* slen;    // [E] number of messages with the same target as the p-th sorted message
     float* snap;       // [E][(L-1)*row_stride] pre-batch rows 1..L-1 of each target (snapshot path only)
     size_t bytes;
 };
@@ -78,6 +79,7 @@ Workspace carve(void* base, int64_t batch, int num_layer, int64_t row_stride) {
     ws.sw = reinterpret_cast<float*>(take(4 * E));
     ws.hist = reinterpret_cast<uint32_t*>(take(4 * kRadixBins * (nblk + 1)));
     ws.sslot = reinterpret_cast<uint32_t*>(take(4 * E));
+    ws.slen = reinterpret_cast<uint32_t*>(take(4 * E));
     const size_t snap_rows = E <= (size_t)kSnapMaxMsgs ? E : 0;
     ws.snap = reinterpret_cast<float*>(take(sizeof(float) * snap_rows * (size_t)(num_layer - 1) * row_stride + 16));
     ws.bytes = off;
@@ -120,21 +122,83 @@ __global__ void __launch_bounds__(kPrepThreads)
 prep_small_kernel(const long long* __restrict__ src, const long long* __restrict__ dst,
                   const double* __restrict__ t, int B, float t_last_f, float neg_lambda, long long num_nodes,
                   uint32_t* __restrict__ skey, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
-                  uint32_t* __restrict__ sslot, int* __restrict__ err_flag, float* decay_log, int L,
-                  long long new_epoch, DecayArgs decay, StateView st, SweepArgs sweep) {
+                  uint32_t* __restrict__ sslot, uint32_t* __restrict__ slen, int* __restrict__ err_flag,
+                  float* decay_log, int L, long long new_epoch, DecayArgs decay, StateView st, SweepArgs sweep) {
     if (blockIdx.x > 0) {
         sweep_body(st, decay, sweep.total4, sweep.ds4, (long long)(blockIdx.x - 1) * kPrepThreads + threadIdx.x,
                    (long long)(gridDim.x - 1) * kPrepThreads);
         return;
     }
-    __shared__ unsigned long long comp[kSmallMaxMsgs];       // (target << 32 | message index)
+    __shared__ __align__(16) unsigned long long comp[kSmallMaxMsgs];   // (target << 32 | message index)
     __shared__ float wsm[kSmallMaxMsgs / 2];
     const int E = 2 * B;
     if (threadIdx.x == 0 && decay_log != nullptr && decay.has_decay) {
         for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay.c[l];
     }
-    int P = E;
-    if (E > kRankMaxMsgs) { P = 1; while (P < E) P <<= 1; }
+    if (E <= kRankMaxMsgs) {
+        // ---- rank sort.  Keys are packed as (target << 10 | m) in 32 bits when the node ids
+        // allow it (num_nodes < 2^22), else as 64-bit composites.  Composites are unique, so
+        // "number of composites smaller than mine" IS the stable sorted position.  The same
+        // scan gives, for the message's SOURCE node, where that node's own segment starts
+        // (every source is also a target) and, for the target, the segment length.
+        uint32_t* c32 = reinterpret_cast<uint32_t*>(comp);
+        const bool narrow = num_nodes < (1ll << 22);
+        const int Epad = (E + 3) & ~3;
+        for (int m = threadIdx.x; m < Epad; m += kPrepThreads) {
+            uint32_t key = 0xffffffffu >> 10;                 // padding: above every real key
+            if (m < E) {
+                const int j = m < B ? m : m - B;
+                const long long tgt = m < B ? src[j] : dst[j];
+                const long long oth = m < B ? dst[j] : src[j];
+                const bool ok = tgt >= 0 && tgt < num_nodes && oth >= 0 && oth < num_nodes;
+                if (!ok && err_flag != nullptr) *err_flag = 1;
+                key = ok ? (uint32_t)tgt : (uint32_t)num_nodes;   // sentinel: dropped by walk
+                if (m < B) wsm[m] = edge_weight(t[m], t_last_f, neg_lambda);
+            }
+            if (narrow) c32[m] = (key << 10) | (uint32_t)m;
+            else comp[m] = ((unsigned long long)(m < E ? key : 0xffffffffu) << 32) | (uint32_t)m;
+        }
+        __syncthreads();
+        for (int m = threadIdx.x; m < E; m += kPrepThreads) {
+            const int j = m < B ? m : m - B;
+            const uint32_t other = (uint32_t)(m < B ? dst[j] : src[j]);
+            int rank = 0, slot = 0, upper = 0;
+            uint32_t mykey;
+            if (narrow) {
+                const uint32_t mine = c32[m];
+                mykey = mine >> 10;
+                const uint32_t other_lo = other << 10, next_lo = (mykey + 1) << 10;
+                const uint4* c4 = reinterpret_cast<const uint4*>(c32);
+                for (int i = 0; i < Epad / 4; ++i) {
+                    const uint4 c = c4[i];                    // same address across the warp: broadcast
+                    rank += (c.x < mine) + (c.y < mine) + (c.z < mine) + (c.w < mine);
+                    slot += (c.x < other_lo) + (c.y < other_lo) + (c.z < other_lo) + (c.w < other_lo);
+                    upper += (c.x < next_lo) + (c.y < next_lo) + (c.z < next_lo) + (c.w < next_lo);
+                }
+            } else {
+                const unsigned long long mine = comp[m];
+                mykey = (uint32_t)(mine >> 32);
+                const unsigned long long other_lo = (unsigned long long)other << 32;
+                const unsigned long long next_lo = (unsigned long long)(mykey + 1) << 32;
+                for (int i = 0; i < E; ++i) {
+                    const unsigned long long c = comp[i];
+                    rank += c < mine;
+                    slot += c < other_lo;
+                    upper += c < next_lo;
+                }
+            }
+            const int lower = rank - 0;      // rank counts everything below (key, m); the head is the lower bound
+            skey[rank] = mykey;
+            ssrc[rank] = other;
+            sw[rank] = wsm[j];
+            sslot[rank] = (uint32_t)slot;
+            slen[rank] = (uint32_t)(upper - lower);          // at the head (lower == rank) this is the segment length
+        }
+        return;
+    }
+    // ---- bitonic network on the composite (target, message index): total order == stable order
+    int P = 1;
+    while (P < E) P <<= 1;
     for (int m = threadIdx.x; m < P; m += kPrepThreads) {
         unsigned long long c = ~0ull;                         // padding sorts last
         if (m < E) {
@@ -143,36 +207,13 @@ prep_small_kernel(const long long* __restrict__ src, const long long* __restrict
             const long long oth = m < B ? dst[j] : src[j];
             const bool ok = tgt >= 0 && tgt < num_nodes && oth >= 0 && oth < num_nodes;
             if (!ok && err_flag != nullptr) *err_flag = 1;
-            const uint32_t key = ok ? (uint32_t)tgt : (uint32_t)num_nodes;    // sentinel: dropped by walk
+            const uint32_t key = ok ? (uint32_t)tgt : (uint32_t)num_nodes;
             c = ((unsigned long long)key << 32) | (uint32_t)m;
             if (m < B) wsm[m] = edge_weight(t[m], t_last_f, neg_lambda);
         }
         comp[m] = c;
     }
     __syncthreads();
-    if (E <= kRankMaxMsgs) {
-        // rank sort: position = number of composites smaller than mine (composites are unique,
-        // so this is the stable order); the same scan counts the keys below the SOURCE id,
-        // which is where the source node's own segment starts (every source is also a target)
-        for (int m = threadIdx.x; m < E; m += kPrepThreads) {
-            const unsigned long long mine = comp[m];
-            const int j = m < B ? m : m - B;
-            const uint32_t other = (uint32_t)(m < B ? dst[j] : src[j]);
-            const unsigned long long other_lo = (unsigned long long)other << 32;
-            int rank = 0, slot = 0;
-            for (int i = 0; i < E; ++i) {
-                const unsigned long long c = comp[i];        // same address across the warp: broadcast
-                rank += c < mine;
-                slot += c < other_lo;
-            }
-            skey[rank] = (uint32_t)(mine >> 32);
-            ssrc[rank] = other;
-            sw[rank] = wsm[j];
-            sslot[rank] = (uint32_t)slot;
-        }
-        return;
-    }
-    // bitonic network on the composite (target, message index): total order == stable order
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = threadIdx.x; i < P; i += kPrepThreads) {
@@ -189,19 +230,27 @@ prep_small_kernel(const long long* __restrict__ src, const long long* __restrict
     for (int p = threadIdx.x; p < E; p += kPrepThreads) {
         const unsigned long long c = comp[p];
         const uint32_t m = (uint32_t)c;
+        const uint32_t mykey = (uint32_t)(c >> 32);
         const int j = m < (uint32_t)B ? m : m - B;
         const uint32_t other = (uint32_t)(m < (uint32_t)B ? dst[j] : src[j]);
-        skey[p] = (uint32_t)(c >> 32);
+        skey[p] = mykey;
         ssrc[p] = other;
         sw[p] = wsm[j];
-        // lower bound of the source id among the sorted targets
+        // lower bound of the source id among the sorted targets; end of my own segment
         const unsigned long long other_lo = (unsigned long long)other << 32;
+        const unsigned long long next_lo = (unsigned long long)(mykey + 1) << 32;
         int lo = 0, hi = E;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (comp[mid] < other_lo) lo = mid + 1; else hi = mid;
         }
         sslot[p] = (uint32_t)lo;
+        lo = p; hi = E;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (comp[mid] < next_lo) lo = mid + 1; else hi = mid;
+        }
+        slen[p] = (uint32_t)(lo - p);                         // messages from p to the end of the segment
     }
 }
 
@@ -335,12 +384,13 @@ __global__ void __launch_bounds__(256)
 payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ skey,
                const long long* __restrict__ src, const long long* __restrict__ dst, const float* __restrict__ w,
                long long B, int E, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
-               uint32_t* __restrict__ sslot) {
+               uint32_t* __restrict__ sslot, uint32_t* __restrict__ slen) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= E) return;
     const uint32_t m = order[p];
     const long long j = m < B ? m : m - B;
     const uint32_t other = (uint32_t)(m < B ? dst[j] : src[j]);
+    const uint32_t mykey = skey[p];
     ssrc[p] = other;
     sw[p] = w[j];
     if (sslot != nullptr) {          // snapshot path: where the source node's own segment starts
@@ -351,6 +401,16 @@ payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ 
         }
         sslot[p] = (uint32_t)lo;
     }
+    uint32_t len = 0;
+    if (p == 0 || skey[p - 1] != mykey) {     // heads only: end of the segment by binary search
+        int lo = p, hi = E;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (skey[mid] <= mykey) lo = mid + 1; else hi = mid;
+        }
+        len = (uint32_t)(lo - p);
+    }
+    slen[p] = len;
 }
 
 // ---------------------------------------------------------------- eager decay sweep (large path)
@@ -361,10 +421,12 @@ sweep_decay_kernel(StateView st, DecayArgs decay, long long total4, int ds4) {
 }
 
 // ---------------------------------------------------------------- the walk update
-// Work item = (target segment, column tile).  A group of 8 lanes owns 8*V consecutive float4
-// of the target span, reads them once, replays pending decay (lazy), then walks the
-// segment's messages in order — D rows in flight at a time — adding
-// fadd_rn(acc, fmul_rn(source, w)), and writes the span back once.
+// Work item = (target segment, column tile), one WARP each.  The warp owns 32*V consecutive
+// float4 of the target span (512*V contiguous bytes), reads them once, replays pending decay
+// (lazy), then walks the segment's messages in order: the 32 lanes fetch the metadata
+// (source id, weight, snapshot slot) of 32 messages with one coalesced load each and
+// broadcast it by shuffle; D source rows are in flight per lane before the first add;
+// every add is fadd_rn(acc, fmul_rn(source, w)); the span is written back once.
 //   ALL = false : span = row `layer` of the target; sources = row layer-1 of the state
 //                 (launched per layer, top-down; lazy sources are replayed in registers).
 //   ALL = true  : span = rows 1..L of the target (contiguous in the node-major state);
@@ -374,94 +436,89 @@ sweep_decay_kernel(StateView st, DecayArgs decay, long long total4, int ds4) {
 template <int V, int D, bool LAZY, bool ALL>
 __global__ void __launch_bounds__(kWalkThreads)
 walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ssrc,
-            const float* __restrict__ sw, const uint32_t* __restrict__ sslot, const float* __restrict__ snap,
-            int E, int ds4, int write_stamp) {
-    constexpr int G = 8;
-    const int gid = (blockIdx.x * kWalkThreads + threadIdx.x) / G;
-    const int lane = threadIdx.x % G;
-    if (gid >= E) return;
-    const uint32_t key = skey[gid];
-    if ((long long)key >= st.num_nodes) return;          // dropped edge (id out of range)
-    if (gid > 0 && skey[gid - 1] == key) return;         // not the head of its segment
+            const float* __restrict__ sw, const uint32_t* __restrict__ sslot, const uint32_t* __restrict__ slen,
+            const float* __restrict__ snap, int E, int ds4, int write_stamp) {
+    const int wid = (blockIdx.x * kWalkThreads + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= E) return;
+    const uint32_t key = skey[wid];
+    const uint32_t prev = wid > 0 ? skey[wid - 1] : 0xffffffffu;
+    const int len = (int)slen[wid];
+    if ((long long)key >= st.num_nodes || prev == key) return;   // dropped edge / not a segment head
     const int L = st.num_layer;
     const int span4 = ALL ? L * ds4 : ds4;               // float4 in the target span
     const int snap4 = (L - 1) * ds4;                     // float4 per snapshot slot
-    const int col0 = blockIdx.y * (G * V) + lane;
+    const int col0 = blockIdx.y * (32 * V) + lane;
 
     float* tbase = st.data + (long long)key * st.node_stride + (long long)(ALL ? 1 : layer) * st.row_stride;
     float4 acc[V];
-    int tli[V];                                          // decay-log column (target layer - 1) per register
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-        const int c = col0 + k * G;
-        tli[k] = ALL ? (c < span4 ? c / ds4 : 0) : layer - 1;
+        const int c = col0 + k * 32;
+        const int tli = ALL ? (c < span4 ? c / ds4 : 0) : layer - 1;     // decay-log column of this register
         long long tstamp = 0;
-        if (LAZY && c < span4) tstamp = st.stamps[(long long)key * L + tli[k]];
+        if (LAZY && c < span4) tstamp = st.stamps[(long long)key * L + tli];
         acc[k] = (c < span4 && tstamp >= 0) ? ld4(tbase + 4 * (long long)c) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (LAZY && c < span4 && tstamp >= 0) {
             float4 one[1] = {acc[k]};
-            replay<1>(one, st.decay_log, L, tli[k], tstamp, st.epoch);
+            replay<1>(one, st.decay_log, L, tli, tstamp, st.epoch);
             acc[k] = one[0];
         }
     }
 
-    int p = gid;
-    bool more = true;
-    while (more) {
-        // gather the next D messages of the segment: all row loads are issued before any add
-        float4 x[D][V];
-        float w[D];
-        int cnt = 0;
+    for (int base = 0; base < len; base += 32) {
+        const int nmsg = min(32, len - base);
+        // one coalesced metadata load per lane covers 32 messages
+        uint32_t my_v = 0, my_slot = 0;
+        float my_w = 0.f;
+        long long my_vstamp = 0;
+        if (lane < nmsg) {
+            const int p = wid + base + lane;
+            my_v = ssrc[p];
+            my_w = sw[p];
+            if (ALL) my_slot = sslot[p];
+            else if (LAZY && layer >= 2) my_vstamp = st.stamps[(long long)my_v * L + (layer - 2)];
+        }
+        for (int j0 = 0; j0 < nmsg; j0 += D) {
+            float4 x[D][V];
+            float w[D];
+            long long vstamp[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const int pj = p + j;
-            const bool ok = more && pj < E && (j == 0 || skey[pj] == key);
-            if (!ok) more = false;
-            w[j] = 0.f;
-            if (ok) {
-                ++cnt;
-                const uint32_t v = ssrc[pj];
-                w[j] = sw[pj];
+            for (int j = 0; j < D; ++j) {                 // issue every row load of the chunk first
+                const int jj = j0 + j;
+                const int sl = jj < nmsg ? jj : 0;
+                const uint32_t v = __shfl_sync(0xffffffffu, my_v, sl);
+                w[j] = __shfl_sync(0xffffffffu, my_w, sl);
+                const uint32_t slot = ALL ? __shfl_sync(0xffffffffu, my_slot, sl) : 0u;
+                vstamp[j] = (!ALL && LAZY) ? __shfl_sync(0xffffffffu, my_vstamp, sl) : 0;
                 const float* sstate = st.data + (long long)v * st.node_stride +
                                       (long long)(ALL ? 0 : layer - 1) * st.row_stride;
-                const float* ssnap = ALL ? snap + (long long)sslot[pj] * snap4 * 4 : nullptr;
+                const float* ssnap = ALL ? snap + (long long)slot * snap4 * 4 : nullptr;
 #pragma unroll
                 for (int k = 0; k < V; ++k) {
-                    const int c = col0 + k * G;
+                    const int c = col0 + k * 32;
                     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c < span4) {
-                        if (ALL) {
-                            val = c < ds4 ? ld4(sstate + 4 * (long long)c) : ld4(ssnap + 4 * (long long)(c - ds4));
-                        } else {
-                            long long vstamp = 0;
-                            if (LAZY && layer >= 2) vstamp = st.stamps[(long long)v * L + (layer - 2)];
-                            if (vstamp >= 0) {
-                                val = ld4(sstate + 4 * (long long)c);
-                                if (LAZY && layer >= 2) {       // P_0 never decays
-                                    float4 one[1] = {val};
-                                    replay<1>(one, st.decay_log, L, layer - 2, vstamp, st.epoch);
-                                    val = one[0];
-                                }
-                            }
-                        }
+                    if (jj < nmsg && c < span4) {
+                        if (ALL) val = c < ds4 ? ld4(sstate + 4 * (long long)c) : ld4(ssnap + 4 * (long long)(c - ds4));
+                        else if (vstamp[j] >= 0) val = ld4(sstate + 4 * (long long)c);
                     }
                     x[j][k] = val;
                 }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            if (j < cnt) {
+            for (int j = 0; j < D; ++j) {
+                if (j0 + j < nmsg) {
+                    if (!ALL && LAZY && layer >= 2 && vstamp[j] >= 0)      // P_0 never decays
+                        replay<V>(x[j], st.decay_log, L, layer - 2, vstamp[j], st.epoch);
 #pragma unroll
-                for (int k = 0; k < V; ++k) axpy4_rn(acc[k], x[j][k], w[j]);
+                    for (int k = 0; k < V; ++k) axpy4_rn(acc[k], x[j][k], w[j]);
+                }
             }
         }
-        p += cnt;
-        if (more) more = p < E && skey[p] == key;
     }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-        const int c = col0 + k * G;
+        const int c = col0 + k * 32;
         if (c < span4) st4(tbase + 4 * (long long)c, acc[k]);
     }
     if (LAZY && write_stamp && lane == 0) st.stamps[(long long)key * L + (layer - 1)] = (int)st.epoch;
@@ -511,29 +568,14 @@ stamp_targets_kernel(StateView st, int layer, const uint32_t* __restrict__ skey,
 template <int V, int D, bool ALL>
 void launch_walk(const StateView& v, int layer, const Workspace& ws, int E, int ds4, int tiles, bool lazy,
                  cudaStream_t stream) {
-    dim3 grid((unsigned)(((long long)E * 8 + kWalkThreads - 1) / kWalkThreads), (unsigned)tiles);
+    dim3 grid((unsigned)(((long long)E * 32 + kWalkThreads - 1) / kWalkThreads), (unsigned)tiles);
     const int write_stamp = (!ALL && tiles == 1) ? 1 : 0;
     if (lazy)
         walk_kernel<V, D, true, ALL><<<grid, kWalkThreads, 0, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
-                                                                        ws.snap, E, ds4, write_stamp);
+                                                                        ws.slen, ws.snap, E, ds4, write_stamp);
     else
         walk_kernel<V, D, false, ALL><<<grid, kWalkThreads, 0, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
-                                                                         ws.snap, E, ds4, write_stamp);
-}
-
-// per-layer walk: V float4 per lane so that one tile covers rows up to 256 floats
-void dispatch_layer_walk(int vpl, const StateView& v, int layer, const Workspace& ws, int E, int ds4, int tiles,
-                         bool lazy, cudaStream_t s) {
-    switch (vpl) {
-        case 1: launch_walk<1, 8, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
-        case 2: launch_walk<2, 8, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
-        case 3: launch_walk<3, 4, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
-        case 4: launch_walk<4, 4, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
-        case 5: launch_walk<5, 4, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
-        case 6: launch_walk<6, 3, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
-        case 7: launch_walk<7, 2, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
-        default: launch_walk<8, 2, false>(v, layer, ws, E, ds4, tiles, lazy, s); break;
-    }
+                                                                         ws.slen, ws.snap, E, ds4, write_stamp);
 }
 
 }  // namespace
@@ -602,7 +644,8 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
         }
         prep_small_kernel<<<grid, kPrepThreads, 0, stream>>>(src, dst, t_dev, (int)batch, t_last_f, neg_lambda,
                                                              st->num_nodes, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
-                                                             err_flag_dev, log_w, L, new_epoch, dargs, view, sw_args);
+                                                             ws.slen, err_flag_dev, log_w, L, new_epoch, dargs, view,
+                                                             sw_args);
     } else {
         prep_large_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, stream>>>(
             src, dst, t_dev, batch, t_last_f, neg_lambda, st->num_nodes, ws.w, ws.key_a, ws.val_a, err_flag_dev, log_w,
@@ -623,7 +666,7 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
             cudaMemcpyAsync(ws.key_a, kin, sizeof(uint32_t) * E, cudaMemcpyDeviceToDevice, stream);
         }
         payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(vin, ws.key_a, src, dst, ws.w, batch, E, ws.ssrc, ws.sw,
-                                                            snapshot_path ? ws.sslot : nullptr);
+                                                            snapshot_path ? ws.sslot : nullptr, ws.slen);
         if (eager_sweep) {
             const long long want = (sweep_total4 + 255) / 256;
             const unsigned grid = (unsigned)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
@@ -637,20 +680,25 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
             if (lazy) snapshot_kernel<true><<<grid, 256, 0, stream>>>(view, ws.key_a, E, ds4, ws.snap);
             else snapshot_kernel<false><<<grid, 256, 0, stream>>>(view, ws.key_a, E, ds4, ws.snap);
         }
-        // one float4 per lane for latency-bound batches, two once there is enough work to fill the GPU
+        // one float4 per lane: a warp covers 512 contiguous bytes of the L*row_stride span
         const int span4 = L * ds4;
-        if (E <= 8192) launch_walk<1, 8, true>(view, 0, ws, E, ds4, (span4 + 7) / 8, lazy, stream);
-        else launch_walk<2, 8, true>(view, 0, ws, E, ds4, (span4 + 15) / 16, lazy, stream);
+        launch_walk<1, 16, true>(view, 0, ws, E, ds4, (span4 + 31) / 32, lazy, stream);
         if (lazy) stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, 0, ws.key_a, E);
     } else {
-        int vpl = (ds4 + 7) / 8;
+        // per-layer walk: V float4 per lane so that one tile covers rows up to 512 floats
+        int vpl = (ds4 + 31) / 32;
         int tiles = 1;
-        if (vpl > 8) {
-            tiles = (vpl + 7) / 8;
-            vpl = 8;
+        if (vpl > 4) {
+            tiles = (vpl + 3) / 4;
+            vpl = 4;
         }
         for (int layer = L; layer >= 1; --layer) {
-            dispatch_layer_walk(vpl, view, layer, ws, E, ds4, tiles, lazy, stream);
+            switch (vpl) {
+                case 1: launch_walk<1, 16, false>(view, layer, ws, E, ds4, tiles, lazy, stream); break;
+                case 2: launch_walk<2, 8, false>(view, layer, ws, E, ds4, tiles, lazy, stream); break;
+                case 3: launch_walk<3, 4, false>(view, layer, ws, E, ds4, tiles, lazy, stream); break;
+                default: launch_walk<4, 4, false>(view, layer, ws, E, ds4, tiles, lazy, stream); break;
+            }
             if (lazy && tiles > 1)
                 stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, layer, ws.key_a, E);
         }
