@@ -141,10 +141,13 @@ def cpu_port_run(shape, warm_batches, steps, n_warm, n_timed, threads):
 
     def one(st):
         with torch.no_grad():
-            acc = ref.pair_wise(*st['enc_pos']).sum() + ref.pair_wise(*st['enc_neg']).sum()
-            acc = acc + ref.pair_wise(st['src'], st['dst']).sum() + ref.pair_wise(st['src'], st['neg']).sum()
+            ref.pair_wise(*st['enc_pos'])
+            ref.pair_wise(*st['enc_neg'])
+            pos = ref.pair_wise(st['src'], st['dst'])
+            neg = ref.pair_wise(st['src'], st['neg'])
             ref.update(st['src'], st['dst'], st['t'])
-        return float(acc)
+            res = pos.sum() - neg.sum()
+        return float(res)
 
     for st in steps[:n_warm]:
         one(st)
@@ -187,11 +190,13 @@ def resident_step(m, ds):
 def api_step(m, st):
     """One step through the public numpy API, head included, scalar result read back."""
     with torch.no_grad():
-        acc = m.get_pair_wise_feature(*st['enc_pos']).sum() + m.get_pair_wise_feature(*st['enc_neg']).sum()
-        acc = acc + m.get_pair_wise_feature(st['src'], st['dst']).sum() \
-            + m.get_pair_wise_feature(st['src'], st['neg']).sum()
+        m.get_pair_wise_feature(*st['enc_pos'])                # encoder features (feed the Mixer in TPNet)
+        m.get_pair_wise_feature(*st['enc_neg'])
+        pos = m.get_pair_wise_feature(st['src'], st['dst'])    # decoder features -> the step's scalar result
+        neg = m.get_pair_wise_feature(st['src'], st['neg'])
         m.update(st['src'], st['dst'], st['t'])
-    return float(acc.item())                                   # D2H read of the step's result
+        res = pos.sum() - neg.sum()
+    return float(res.item())                                   # D2H read of the step's result
 
 
 def main():

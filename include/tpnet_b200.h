@@ -63,7 +63,8 @@ enum {
     TPN_ERR_WORKSPACE_TOO_SMALL = -2,
     TPN_ERR_LOG_FULL = -3,           /* lazy mode: decay_log has no free epoch (materialise)   */
     TPN_ERR_CUDA = -4,               /* a CUDA runtime call failed; see tpn_last_cuda_error()   */
-    TPN_ERR_UNSUPPORTED = -5         /* num_layer outside 1..TPN_MAX_LAYERS                     */
+    TPN_ERR_UNSUPPORTED = -5,        /* num_layer outside 1..TPN_MAX_LAYERS                     */
+    TPN_ERR_INDEX = -6               /* tpn_stage: a node id is out of range                    */
 };
 
 /* The L+1 projection matrices P_0..P_L of the reference's
@@ -148,6 +149,29 @@ int tpn_reset_epoch(tpn_state_t* st, void* stream);
 /* Zero layers 1..L of every node and all stamps; epoch <- 0 (reset_random_projections,
  * TPNet.py:135-136; P_0 is re-drawn by the caller with torch's RNG, TPNet.py:139). */
 int tpn_clear_walk_layers(tpn_state_t* st, void* stream);
+
+/*
+ * Host -> device staging of the per-call id / timestamp arrays (the reference's
+ * `torch.from_numpy(ids).to(device)` at TPNet.py:74-77 and the implicit conversion at :109).
+ * A stager owns a ring of pinned host slots and device slots on the current device.
+ * tpn_stage copies `count` host arrays of 8-byte elements back to back into the next slot,
+ * issues ONE cudaMemcpyAsync on `stream` and returns the device address of each array in
+ * dev_out[i]; the addresses stay valid until the ring wraps (`slots` later calls).
+ *   kinds[i] = TPN_STAGE_RAW      : copied verbatim (float64 timestamps)
+ *            = TPN_STAGE_ID_WRAP  : int64 ids, -num_nodes <= id < num_nodes, negatives wrap
+ *                                   (what tensor indexing does, TPNet.py:109)
+ *            = TPN_STAGE_ID       : int64 ids, 0 <= id < num_nodes (what scatter_add_ accepts, :93-96)
+ * Returns TPN_ERR_INDEX if an id is out of range (nothing is launched).
+ * tpn_stager_create allocates (once); tpn_stage only re-allocates if a call exceeds slot_bytes.
+ */
+typedef struct tpn_stager tpn_stager_t;
+#define TPN_STAGE_RAW 0
+#define TPN_STAGE_ID_WRAP 1
+#define TPN_STAGE_ID 2
+int tpn_stager_create(tpn_stager_t** out, size_t slot_bytes, int slots);
+void tpn_stager_destroy(tpn_stager_t* sg);
+int tpn_stage(tpn_stager_t* sg, const void* const* host, const int64_t* elems, const int* kinds, int count,
+              int64_t num_nodes, void** dev_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_PKG, '_C', 'libtpnet_b200.so')
 
 TPN_OK = 0
 TPN_ERR_LOG_FULL = -3
+TPN_ERR_INDEX = -6
+STAGE_RAW, STAGE_ID_WRAP, STAGE_ID = 0, 1, 2
 TPN_MAX_LAYERS = 4
 ABI_VERSION = 1
 
@@ -24,6 +26,7 @@ EXPORTED_SYMBOLS = (
     'tpn_version', 'tpn_error_string', 'tpn_last_cuda_error', 'tpn_device_info',
     'tpn_update_workspace_bytes', 'tpn_update', 'tpn_pairwise', 'tpn_gather',
     'tpn_materialize', 'tpn_reset_epoch', 'tpn_clear_walk_layers',
+    'tpn_stager_create', 'tpn_stager_destroy', 'tpn_stage',
 )
 
 
@@ -74,6 +77,13 @@ def _declare(lib: ctypes.CDLL) -> None:
         fn = getattr(lib, name)
         fn.restype = c_int
         fn.argtypes = [POINTER(TpnState), c_void_p]
+    lib.tpn_stager_create.restype = c_int
+    lib.tpn_stager_create.argtypes = [POINTER(c_void_p), c_size_t, c_int]
+    lib.tpn_stager_destroy.restype = None
+    lib.tpn_stager_destroy.argtypes = [c_void_p]
+    lib.tpn_stage.restype = c_int
+    lib.tpn_stage.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int), c_int, c_int64,
+                              POINTER(c_void_p), c_void_p]
 
 
 def load() -> ctypes.CDLL:
@@ -99,6 +109,8 @@ def load() -> ctypes.CDLL:
 def check(code: int, where: str) -> None:
     if code == TPN_OK:
         return
+    if code == TPN_ERR_INDEX:
+        raise IndexError(f'{where}: node id out of range')
     lib = load()
     detail = lib.tpn_error_string(code).decode()
     cuda = lib.tpn_last_cuda_error().decode()

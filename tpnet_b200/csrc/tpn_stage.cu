@@ -1,0 +1,150 @@
+// Host->device staging of the per-call id / timestamp arrays.
+//
+// The reference converts its numpy id arrays with `torch.from_numpy(...).to(device)` on every
+// call (models/TPNet.py:74-77 and the implicit conversion at :109) — a pageable, synchronous
+// copy.  Here one C call copies the arrays into a ring of pinned host slots (validating the
+// ids on the way, which replaces the bounds check torch indexing performs), issues ONE
+// cudaMemcpyAsync per call on the caller's stream and records an event so that a slot is
+// never overwritten before its copy has left.  No Python-level stream/event objects.
+#include <stdlib.h>
+#include <string.h>
+
+#include "tpn_common.cuh"
+
+struct tpn_stager {
+    int slots;
+    size_t slot_bytes;
+    int cursor;
+    char** host;          // pinned
+    char** dev;
+    cudaEvent_t* done;
+    bool* used;
+};
+
+namespace {
+
+void release(tpn_stager* sg) {
+    if (sg == nullptr) return;
+    for (int i = 0; i < sg->slots; ++i) {
+        if (sg->host && sg->host[i]) cudaFreeHost(sg->host[i]);
+        if (sg->dev && sg->dev[i]) cudaFree(sg->dev[i]);
+        if (sg->done && sg->done[i]) cudaEventDestroy(sg->done[i]);
+    }
+    free(sg->host);
+    free(sg->dev);
+    free(sg->done);
+    free(sg->used);
+    sg->host = nullptr;
+    sg->dev = nullptr;
+    sg->done = nullptr;
+    sg->used = nullptr;
+}
+
+int allocate(tpn_stager* sg, size_t slot_bytes, int slots) {
+    sg->slots = slots;
+    sg->slot_bytes = slot_bytes;
+    sg->cursor = 0;
+    sg->host = (char**)calloc(slots, sizeof(char*));
+    sg->dev = (char**)calloc(slots, sizeof(char*));
+    sg->done = (cudaEvent_t*)calloc(slots, sizeof(cudaEvent_t));
+    sg->used = (bool*)calloc(slots, sizeof(bool));
+    if (!sg->host || !sg->dev || !sg->done || !sg->used) return TPN_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < slots; ++i) {
+        cudaError_t e = cudaHostAlloc((void**)&sg->host[i], slot_bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&sg->dev[i], slot_bytes);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sg->done[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            tpn::set_cuda_error(e);
+            return TPN_ERR_CUDA;
+        }
+    }
+    return TPN_OK;
+}
+
+}  // namespace
+
+extern "C" int tpn_stager_create(tpn_stager_t** out, size_t slot_bytes, int slots) {
+    if (out == nullptr || slots < 1 || slots > 64) return TPN_ERR_INVALID_ARGUMENT;
+    if (slot_bytes < 4096) slot_bytes = 4096;
+    tpn_stager* sg = (tpn_stager*)calloc(1, sizeof(tpn_stager));
+    if (sg == nullptr) return TPN_ERR_INVALID_ARGUMENT;
+    const int rc = allocate(sg, slot_bytes, slots);
+    if (rc != TPN_OK) {
+        release(sg);
+        free(sg);
+        return rc;
+    }
+    *out = sg;
+    return TPN_OK;
+}
+
+extern "C" void tpn_stager_destroy(tpn_stager_t* sg) {
+    if (sg == nullptr) return;
+    release(sg);
+    free(sg);
+}
+
+extern "C" int tpn_stage(tpn_stager_t* sg, const void* const* host, const int64_t* elems, const int* kinds,
+                         int count, int64_t num_nodes, void** dev_out, void* stream_v) {
+    if (sg == nullptr || host == nullptr || elems == nullptr || kinds == nullptr || dev_out == nullptr ||
+        count < 1 || count > 8)
+        return TPN_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    size_t total = 0;
+    for (int i = 0; i < count; ++i) {
+        if (elems[i] < 0 || host[i] == nullptr) return TPN_ERR_INVALID_ARGUMENT;
+        total += (size_t)elems[i] * 8;
+    }
+    if (total > sg->slot_bytes) {                     // grow: rare (first call with a bigger batch)
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+            tpn::set_cuda_error(e);
+            return TPN_ERR_CUDA;
+        }
+        const int slots = sg->slots;
+        size_t want = sg->slot_bytes;
+        while (want < total) want *= 2;
+        release(sg);
+        const int rc = allocate(sg, want, slots);
+        if (rc != TPN_OK) return rc;
+    }
+    const int k = sg->cursor;
+    sg->cursor = (k + 1) % sg->slots;
+    if (sg->used[k]) {
+        const cudaError_t e = cudaEventSynchronize(sg->done[k]);     // the copy out of this slot has left
+        if (e != cudaSuccess) {
+            tpn::set_cuda_error(e);
+            return TPN_ERR_CUDA;
+        }
+    }
+    char* dst = sg->host[k];
+    size_t off = 0;
+    for (int i = 0; i < count; ++i) {
+        const int64_t n = elems[i];
+        if (kinds[i] == TPN_STAGE_RAW) {
+            memcpy(dst + off, host[i], (size_t)n * 8);
+        } else {
+            const int64_t* src = reinterpret_cast<const int64_t*>(host[i]);
+            int64_t* out64 = reinterpret_cast<int64_t*>(dst + off);
+            const int64_t lo = kinds[i] == TPN_STAGE_ID_WRAP ? -num_nodes : 0;   // indexing wraps, scatter does not
+            int64_t mn = 0, mx = 0;
+            for (int64_t j = 0; j < n; ++j) {
+                const int64_t v = src[j];
+                mn = v < mn ? v : mn;
+                mx = v > mx ? v : mx;
+                out64[j] = v < 0 ? v + num_nodes : v;
+            }
+            if (mn < lo || mx >= num_nodes) return TPN_ERR_INDEX;
+        }
+        dev_out[i] = sg->dev[k] + off;
+        off += (size_t)n * 8;
+    }
+    cudaError_t e = cudaMemcpyAsync(sg->dev[k], sg->host[k], total, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaEventRecord(sg->done[k], stream);
+    if (e != cudaSuccess) {
+        tpn::set_cuda_error(e);
+        return TPN_ERR_CUDA;
+    }
+    sg->used[k] = true;
+    return TPN_OK;
+}

@@ -45,39 +45,56 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
-class _Staging:
-    """Ring of pinned host buffers + device buffers for the per-call id/timestamp
-    upload: one async H2D copy per call, no pageable-memory sync."""
+class _Stager:
+    """Thin owner of the C-side pinned staging ring (csrc/tpn_stage.cu): one ctypes call copies
+    the per-call id / timestamp arrays into pinned memory (validating ids on the way) and issues
+    one async H2D copy on the current stream."""
 
-    def __init__(self, slots: int = 4):
-        self.slots = slots
-        self.host: List[Optional[torch.Tensor]] = [None] * slots
-        self.dev: List[Optional[torch.Tensor]] = [None] * slots
-        self.done: List[Optional[torch.cuda.Event]] = [None] * slots
-        self.cursor = 0
+    def __init__(self, slot_bytes: int = 1 << 20, slots: int = 8):
+        self._lib = _lib.load()
+        self.handle = ctypes.c_void_p()
+        _lib.check(self._lib.tpn_stager_create(ctypes.byref(self.handle), slot_bytes, slots), 'tpn_stager_create')
+        self.host = (ctypes.c_void_p * 8)()
+        self.elems = (ctypes.c_int64 * 8)()
+        self.kinds = (ctypes.c_int * 8)()
+        self.out = (ctypes.c_void_p * 8)()
 
-    def upload(self, arrays: Sequence[np.ndarray], device: torch.device) -> List[int]:
-        """Copies the given 8-byte-element host arrays back to back; returns device addresses."""
-        k = self.cursor
-        self.cursor = (k + 1) % self.slots
-        total = sum(a.nbytes for a in arrays)
-        if self.host[k] is None or self.host[k].numel() < total or self.dev[k].device != device:
-            cap = max(4096, 1 << (total - 1).bit_length())
-            self.host[k] = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-            self.dev[k] = torch.empty(cap, dtype=torch.uint8, device=device)
-            self.done[k] = torch.cuda.Event()
-        else:
-            self.done[k].synchronize()           # the previous copy out of this pinned slot has finished
-        hview = self.host[k].numpy()
-        offs, o = [], 0
-        for a in arrays:
-            hview[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
-            offs.append(o)
-            o += a.nbytes
-        self.dev[k][:total].copy_(self.host[k][:total], non_blocking=True)
-        self.done[k].record()
-        base = self.dev[k].data_ptr()
-        return [base + x for x in offs]
+    def upload(self, arrays: Sequence[np.ndarray], kinds: Sequence[int], num_nodes: int, stream: int) -> List[int]:
+        for i, a in enumerate(arrays):
+            self.host[i] = a.__array_interface__['data'][0]
+            self.elems[i] = a.shape[0]
+            self.kinds[i] = kinds[i]
+        rc = self._lib.tpn_stage(self.handle, self.host, self.elems, self.kinds, len(arrays), num_nodes, self.out,
+                                 stream)
+        if rc:
+            if rc == _lib.TPN_ERR_INDEX:
+                raise IndexError(f'index out of range for node_num {num_nodes}')
+            _lib.check(rc, 'tpn_stage')
+        return [self.out[i] for i in range(len(arrays))]
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._lib.tpn_stager_destroy(self.handle)
+                self.handle = ctypes.c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class _Host:
+    """Mutable host-side bookkeeping kept off the nn.Module (its __setattr__ is slow)."""
+    __slots__ = ('now', 'begin', 'epoch', 'launches', 'stager', 'st', 'st_ref', 'dev_index', 'keepalive')
+
+    def __init__(self, t0: float):
+        self.now = t0
+        self.begin = t0
+        self.epoch = 0
+        self.launches = 0
+        self.stager: Optional[_Stager] = None
+        self.st: Optional[TpnState] = None
+        self.st_ref = None
+        self.dev_index = -1
+        self.keepalive = None
 
 
 class RandomProjectionModule(nn.Module):
@@ -127,20 +144,26 @@ class RandomProjectionModule(nn.Module):
                                  nn.Linear(self.pair_wise_feature_dim * 4, self.pair_wise_feature_dim))
 
         # host mirrors / device scratch (not part of state_dict)
-        self._now_host = float(beginning_time)
-        self._begin_host = float(beginning_time)
-        self._epoch = 0
+        self._h = _Host(float(beginning_time))
         self._stamps: Optional[torch.Tensor] = None
         self._decay_log: Optional[torch.Tensor] = None
         self._ws: Optional[torch.Tensor] = None
+        self._ws_batch = 0
         self._err: Optional[torch.Tensor] = None
-        self._staging = _Staging()
         self.validate_ids = True
-        self.launches = 0                     # kernels-launching C-ABI calls issued (bench accounting)
         self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module.materialize())
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._after_external_write())
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def _now_host(self) -> float:
+        return self._h.now
+
+    @property
+    def launches(self) -> int:
+        """C-ABI calls that launched kernels so far (bench accounting)."""
+        return self._h.launches
+
     @property
     def lazy(self) -> bool:
         if self.decay_mode == 'auto':
@@ -179,17 +202,22 @@ class RandomProjectionModule(nn.Module):
         self._stamps = None
         self._decay_log = None
         self._ws = None
+        self._ws_batch = 0
         self._err = None
-        self._epoch = 0
+        self._h.epoch = 0
+        self._h.st = None
+        self._h.stager = None
+        self._h.dev_index = dev.index if dev.type == 'cuda' and dev.index is not None else (
+            torch.cuda.current_device() if dev.type == 'cuda' else -1)
 
     def _after_external_write(self) -> None:
         """load_state_dict / reload wrote fully materialised values: refresh mirrors."""
         self._repack()
-        self._now_host = float(self.now_time.item())
-        self._begin_host = float(self.begging_time.item())
+        self._h.now = float(self.now_time.item())
+        self._h.begin = float(self.begging_time.item())
         if self._stamps is not None:
             self._stamps.zero_()
-        self._epoch = 0
+        self._h.epoch = 0
 
     def _require_cuda(self) -> torch.device:
         dev = self._state.device
@@ -199,62 +227,74 @@ class RandomProjectionModule(nn.Module):
         return dev
 
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self._state.device).cuda_stream
+        h = self._h
+        if h.dev_index < 0:
+            dev = self._state.device
+            h.dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        return torch._C._cuda_getCurrentRawStream(h.dev_index)
 
-    def _c_state(self) -> TpnState:
-        st = TpnState()
-        st.data = self._state.data_ptr()
-        st.num_nodes = self.node_num
-        st.num_layer = self.num_layer
-        st.dim = self.dim
-        st.row_stride = self.row_stride
-        st.node_stride = self.node_stride
-        if self.lazy:
-            if self._stamps is None:
-                # -1 = row known to be all zero (never written); rows holding data start at epoch 0
-                has_data = bool((self._state[:, 1:, :] != 0).any().item()) if self._state.numel() else False
-                self._stamps = torch.full((self.node_num, self.num_layer), 0 if has_data else -1, dtype=torch.int32,
-                                          device=self._state.device)
-                self._decay_log = torch.ones(_DEFAULT_LOG_EPOCHS, self.num_layer, dtype=torch.float32,
-                                             device=self._state.device)
-                self._epoch = 0
-            st.stamps = self._stamps.data_ptr()
-            st.decay_log = self._decay_log.data_ptr()
-            st.log_capacity = self._decay_log.shape[0]
-            st.epoch = self._epoch
-        else:
-            st.stamps = None
-            st.decay_log = None
-            st.log_capacity = 0
-            st.epoch = 0
-        return st
+    def _c_state(self):
+        """ctypes view of the state (cached; rebuilt when a buffer changes). Returns byref(struct)."""
+        h = self._h
+        st = h.st
+        if st is None:
+            st = TpnState()
+            st.data = self._state.data_ptr()
+            st.num_nodes = self.node_num
+            st.num_layer = self.num_layer
+            st.dim = self.dim
+            st.row_stride = self.row_stride
+            st.node_stride = self.node_stride
+            if self.lazy:
+                if self._stamps is None:
+                    # -1 = row known to be all zero (never written); rows holding data start at epoch 0
+                    has_data = bool((self._state[:, 1:, :] != 0).any().item()) if self._state.numel() else False
+                    self._stamps = torch.full((self.node_num, self.num_layer), 0 if has_data else -1,
+                                              dtype=torch.int32, device=self._state.device)
+                    self._decay_log = torch.ones(_DEFAULT_LOG_EPOCHS, self.num_layer, dtype=torch.float32,
+                                                 device=self._state.device)
+                    h.epoch = 0
+                st.stamps = self._stamps.data_ptr()
+                st.decay_log = self._decay_log.data_ptr()
+                st.log_capacity = self._decay_log.shape[0]
+            else:
+                st.stamps = None
+                st.decay_log = None
+                st.log_capacity = 0
+            h.st = st
+            h.st_ref = ctypes.byref(st)
+        st.epoch = h.epoch
+        return h.st_ref
 
     def _ids_to_device(self, arrays: Sequence[IdArray], kinds: Sequence[str], wrap_negative: bool = True) -> List[int]:
         """Returns device addresses for id (int64) / time (float64) arrays given as
         numpy arrays (staged through pinned memory) or CUDA tensors (used in place)."""
         dev = self._state.device
-        if all(isinstance(a, torch.Tensor) for a in arrays):
+        if isinstance(arrays[0], torch.Tensor) and all(isinstance(a, torch.Tensor) and a.is_cuda for a in arrays):
             out = []
             for a, kind in zip(arrays, kinds):
                 want = torch.int64 if kind == 'id' else torch.float64
                 if a.device != dev or a.dtype != want or not a.is_contiguous():
                     raise TypeError(f'device-resident {kind} arrays must be contiguous {want} tensors on {dev}')
                 out.append(a.data_ptr())
-            self._keepalive = list(arrays)
+            self._h.keepalive = arrays
             return out
-        host = []
+        host, ck = [], []
+        id_kind = _lib.STAGE_ID_WRAP if wrap_negative else _lib.STAGE_ID
+        if not self.validate_ids:
+            id_kind = _lib.STAGE_RAW
         for a, kind in zip(arrays, kinds):
             if isinstance(a, torch.Tensor):
                 a = a.detach().cpu().numpy()
-            a = np.ascontiguousarray(a, dtype=np.int64 if kind == 'id' else np.float64)
-            if kind == 'id' and self.validate_ids and a.size:
-                lo = -self.node_num if wrap_negative else 0     # scatter_add_ rejects negatives, indexing wraps
-                if a.min() < lo or a.max() >= self.node_num:
-                    raise IndexError(f'index out of range for node_num {self.node_num}')
-                if a.min() < 0:
-                    a = np.where(a < 0, a + self.node_num, a)
+            want = np.int64 if kind == 'id' else np.float64
+            if not (isinstance(a, np.ndarray) and a.dtype == want and a.ndim == 1 and a.flags.c_contiguous):
+                a = np.ascontiguousarray(a, dtype=want).reshape(-1)
             host.append(a)
-        return self._staging.upload(host, dev)
+            ck.append(id_kind if kind == 'id' else _lib.STAGE_RAW)
+        h = self._h
+        if h.stager is None:
+            h.stager = _Stager()
+        return h.stager.upload(host, ck, self.node_num, self._stream())
 
     # ------------------------------------------------------------------ reference API
     def update(self, src_node_ids: IdArray, dst_node_ids: IdArray, node_interact_times: IdArray,
@@ -273,29 +313,33 @@ class RandomProjectionModule(nn.Module):
             next_time = float(last.item()) if isinstance(last, torch.Tensor) else float(last)
         lam = self.time_decay_weight
         # c_l = f32(pow(exp(-lambda*(t_last - now)), l)) computed in f64 on the host, TPNet.py:84-85
-        base = np.exp(-lam * (np.float64(next_time) - np.float64(self._now_host)))
+        h = self._h
+        base = np.exp(-lam * (np.float64(next_time) - np.float64(h.now)))
         factors = (ctypes.c_float * self.num_layer)(*[float(np.float32(np.power(base, i)))
                                                       for i in range(1, self.num_layer + 1)])
         ptrs = self._ids_to_device([src_node_ids, dst_node_ids, node_interact_times], ['id', 'id', 'time'],
                                    wrap_negative=False)
         st = self._c_state()
-        need = lib.tpn_update_workspace_bytes(ctypes.byref(st), n)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+        if self._ws is None or self._ws_batch < n:
+            need = lib.tpn_update_workspace_bytes(st, n)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+            self._ws_batch = n
         if self._err is None:
             self._err = torch.zeros(1, dtype=torch.int32, device=dev)
         args = (ptrs[0], ptrs[1], ptrs[2], n, float(next_time), float(np.float32(-lam)), factors,
                 self._ws.data_ptr(), self._ws.numel(), self._err.data_ptr(), self._stream())
-        rc = lib.tpn_update(ctypes.byref(st), *args)
+        rc = lib.tpn_update(st, *args)
         if rc == _lib.TPN_ERR_LOG_FULL:
             self._restart_log()
             st = self._c_state()
-            rc = lib.tpn_update(ctypes.byref(st), *args)
-        _lib.check(rc, 'tpn_update')
-        self._epoch = int(st.epoch)
-        self.launches += 1
-        self._now_host = float(next_time)
-        self.now_time.data.fill_(self._now_host)                                       # TPNet.py:99
+            rc = lib.tpn_update(st, *args)
+        if rc:
+            _lib.check(rc, 'tpn_update')
+        h.epoch = int(h.st.epoch)
+        h.launches += 1
+        h.now = float(next_time)
+        self.now_time.data.fill_(h.now)                                                # TPNet.py:99
 
     def get_random_projections(self, node_ids: IdArray) -> List[torch.Tensor]:
         """TPNet.py:101-110: list of L+1 tensors [n, dim]."""
@@ -305,9 +349,10 @@ class RandomProjectionModule(nn.Module):
         out = torch.empty(self.num_layer + 1, n, self.dim, dtype=torch.float32, device=dev)
         if n:
             ptrs = self._ids_to_device([node_ids], ['id'])
-            st = self._c_state()
-            _lib.check(lib.tpn_gather(ctypes.byref(st), ptrs[0], n, out.data_ptr(), self._stream()), 'tpn_gather')
-            self.launches += 1
+            rc = lib.tpn_gather(self._c_state(), ptrs[0], n, out.data_ptr(), self._stream())
+            if rc:
+                _lib.check(rc, 'tpn_gather')
+            self._h.launches += 1
         return [out[i] for i in range(self.num_layer + 1)]
 
     def pair_wise_gram(self, src_node_ids: IdArray, dst_node_ids: IdArray) -> torch.Tensor:
@@ -320,10 +365,11 @@ class RandomProjectionModule(nn.Module):
         out = torch.empty(n, self.pair_wise_feature_dim, dtype=torch.float32, device=dev)
         if n:
             ptrs = self._ids_to_device([src_node_ids, dst_node_ids], ['id', 'id'])
-            st = self._c_state()
-            _lib.check(lib.tpn_pairwise(ctypes.byref(st), ptrs[0], ptrs[1], n, 0 if self.not_scale else 1,
-                                        out.data_ptr(), self._stream()), 'tpn_pairwise')
-            self.launches += 1
+            rc = lib.tpn_pairwise(self._c_state(), ptrs[0], ptrs[1], n, 0 if self.not_scale else 1,
+                                  out.data_ptr(), self._stream())
+            if rc:
+                _lib.check(rc, 'tpn_pairwise')
+            self._h.launches += 1
         return out
 
     def get_pair_wise_feature(self, src_node_ids: IdArray, dst_node_ids: IdArray) -> torch.Tensor:
@@ -335,10 +381,9 @@ class RandomProjectionModule(nn.Module):
         """TPNet.py:131-139."""
         self._require_cuda()
         lib = _lib.load()
-        st = self._c_state()
-        _lib.check(lib.tpn_clear_walk_layers(ctypes.byref(st), self._stream()), 'tpn_clear_walk_layers')
-        self._epoch = 0
-        self._now_host = self._begin_host
+        _lib.check(lib.tpn_clear_walk_layers(self._c_state(), self._stream()), 'tpn_clear_walk_layers')
+        self._h.epoch = 0
+        self._h.now = self._h.begin
         self.now_time.data = self.begging_time.clone()
         if not self.use_matrix:
             std = 1 / math.sqrt(self.dim)
@@ -369,19 +414,17 @@ class RandomProjectionModule(nn.Module):
     # ------------------------------------------------------------------ lazy-decay maintenance
     def materialize(self) -> None:
         """Bring every row current (no-op in eager mode or off-GPU)."""
-        if self._state.device.type != 'cuda' or not self.lazy or self._stamps is None or self._epoch == 0:
+        if self._state.device.type != 'cuda' or not self.lazy or self._stamps is None or self._h.epoch == 0:
             return
         lib = _lib.load()
-        st = self._c_state()
-        _lib.check(lib.tpn_materialize(ctypes.byref(st), self._stream()), 'tpn_materialize')
-        self.launches += 1
+        _lib.check(lib.tpn_materialize(self._c_state(), self._stream()), 'tpn_materialize')
+        self._h.launches += 1
 
     def _restart_log(self) -> None:
         lib = _lib.load()
         self.materialize()
-        st = self._c_state()
-        _lib.check(lib.tpn_reset_epoch(ctypes.byref(st), self._stream()), 'tpn_reset_epoch')
-        self._epoch = 0
+        _lib.check(lib.tpn_reset_epoch(self._c_state(), self._stream()), 'tpn_reset_epoch')
+        self._h.epoch = 0
 
     def check_errors(self) -> None:
         """Synchronises and raises IndexError if a device-resident id was out of range."""
