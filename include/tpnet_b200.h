@@ -118,6 +118,22 @@ int tpn_update(tpn_state_t* st,
                void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, void* stream);
 
 /*
+ * Message-level form of tpn_update for a node-sharded state (no reference
+ * counterpart — the reference is single-device).  Message m adds source row src_dev[m] into
+ * target row tgt_dev[m] with the weight of timestamp t_dev[m]; messages of one target are
+ * accumulated in the order given.  Ids index rows of `st` (local rows, followed by the rows
+ * received from other ranks); received rows must be current and are only ever read.
+ */
+int tpn_update_messages(tpn_state_t* st,
+                        const int64_t* tgt_dev, const int64_t* src_dev, const double* t_dev, int64_t num_messages,
+                        double t_last, float neg_lambda, const float* decay,
+                        void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, void* stream);
+
+/* Sharded exchange, sender side: out_dev[i] = whole node block (node_stride floats, rows 0..L,
+ * brought current in lazy mode) of ids_dev[i] — the payload of the all-to-all. */
+int tpn_gather_blocks(const tpn_state_t* st, const int64_t* ids_dev, int64_t n, float* out_dev, void* stream);
+
+/*
  * Input of `self.mlp` in RandomProjectionModule.get_pair_wise_feature —
  * TPNet.py:112-129 without the trainable head (which stays in PyTorch).
  *   a_ids_dev, b_ids_dev : int64[n] device

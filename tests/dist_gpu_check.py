@@ -1,0 +1,90 @@
+"""Multi-GPU check of the sharded path, launched by torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/dist_gpu_check.py
+
+Every rank runs ShardedRandomProjection on the same replicated stream; rank 0 also runs the
+single-GPU module.  The sharded state must equal the single-GPU state BIT FOR BIT (same
+kernels, same per-row accumulation order); pair-wise features within the fp32 dot-product
+tolerance (different launch shapes pick different reduction trees)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from tpnet_b200 import RandomProjectionModule  # noqa: E402
+from tpnet_b200.sharded import ShardedRandomProjection  # noqa: E402
+
+
+def stream(rng, N, B, nb, skew):
+    t = 0.0
+    for _ in range(nb):
+        s = 1 + (rng.zipf(skew, B) - 1) % (N - 1)
+        d = 1 + (rng.zipf(skew, B) - 1) % (N - 1)
+        ts = np.sort(t + rng.random(B) * 500.0)
+        t = ts[-1]
+        yield s.astype(np.int64), d.astype(np.int64), ts
+
+
+def main():
+    rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE']); local = int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    ok = True
+    for mode in ('eager', 'lazy'):
+        for (N, B, dim, L) in [(403, 200, 20, 3), (5003, 40000, 24, 2), (997, 3000, 140, 3)]:
+            kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=1e-4,
+                      device=str(dev), use_matrix=False, beginning_time=np.float64(0.0), not_scale=False,
+                      enforce_dim=dim)
+            torch.manual_seed(7)
+            sh = ShardedRandomProjection(decay_mode=mode, ext_rows=2 * B + 16, **kw).to(dev)
+            ref = None
+            if rank == 0:
+                torch.manual_seed(7)
+                ref = RandomProjectionModule(decay_mode=mode, **kw).to(dev)
+            rng = np.random.default_rng(N)
+            for s, d, t in stream(rng, N, B, 4, 1.3):
+                sh.update(s, d, t)
+                if ref is not None:
+                    ref.update(s, d, t)
+            full = sh.gather_global()
+            n = 3001
+            a = rng.integers(0, N, n).astype(np.int64)
+            b = rng.integers(0, N, n).astype(np.int64)
+            keep, feat = sh.pair_wise_gram(a, b)
+            if rank == 0:
+                ref.materialize()
+                for i in range(L + 1):
+                    same = torch.equal(full[i], ref.random_projections[i].data)
+                    ok &= same
+                    if not same:
+                        err = (full[i] - ref.random_projections[i].data).abs().max().item()
+                        print(f'MISMATCH mode={mode} N={N} B={B} layer {i}: max abs err {err}')
+                want = ref.pair_wise_gram(a, b)[torch.from_numpy(keep).to(dev)]
+                close = torch.allclose(feat, want, rtol=1e-5, atol=2e-5)
+                ok &= close
+                if not close:
+                    print(f'PAIRWISE MISMATCH mode={mode} N={N}: {(feat - want).abs().max().item()}')
+            sh.check_errors()
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.broadcast(flag, 0)
+            ok = bool(flag.item())
+            if rank == 0:
+                print(f'mode={mode} N={N} B={B} d={dim} L={L} world={world}: {"ok" if ok else "FAILED"} '
+                      f'(rows received on rank 0: {sh.exchanged_rows})')
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+    if rank == 0:
+        print('sharded == single GPU: PASS')
+
+
+if __name__ == '__main__':
+    main()

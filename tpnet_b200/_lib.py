@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     'tpn_update_workspace_bytes', 'tpn_update', 'tpn_pairwise', 'tpn_gather',
     'tpn_materialize', 'tpn_reset_epoch', 'tpn_clear_walk_layers',
     'tpn_stager_create', 'tpn_stager_destroy', 'tpn_stage',
+    'tpn_update_messages', 'tpn_gather_blocks',
 )
 
 
@@ -69,6 +70,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.tpn_update.restype = c_int
     lib.tpn_update.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_double, c_float,
                                POINTER(c_float), c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.tpn_update_messages.restype = c_int
+    lib.tpn_update_messages.argtypes = lib.tpn_update.argtypes
+    lib.tpn_gather_blocks.restype = c_int
+    lib.tpn_gather_blocks.argtypes = [POINTER(TpnState), c_void_p, c_int64, c_void_p, c_void_p]
     lib.tpn_pairwise.restype = c_int
     lib.tpn_pairwise.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]
     lib.tpn_gather.restype = c_int

@@ -57,6 +57,31 @@ gather_kernel(StateView st, const long long* __restrict__ ids, long long n, floa
     }
 }
 
+// Sharded exchange, sender side: out[i] = the whole node block (rows 0..L, node_stride floats)
+// of ids[i], brought current in lazy mode.  One warp per id.
+template <bool LAZY>
+__global__ void __launch_bounds__(256)
+gather_blocks_kernel(StateView st, const long long* __restrict__ ids, long long n, float* __restrict__ out, int ds4) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    long long id = ids[i];
+    id = id < 0 ? 0 : (id >= st.num_nodes ? st.num_nodes - 1 : id);
+    const float* base = st.data + id * st.node_stride;
+    float* o = out + i * st.node_stride;
+    const int block4 = (int)(st.node_stride >> 2);
+    for (int c = lane; c < block4; c += 32) {
+        const int l = c / ds4;                       // rows are row_stride apart; tail padding belongs to "row" > L
+        float4 x[1];
+        x[0] = ld4(base + 4 * (long long)c);
+        if (LAZY && l >= 1 && l <= st.num_layer) {
+            const long long stamp = st.stamps[id * st.num_layer + (l - 1)];
+            if (stamp >= 0) replay<1>(x, st.decay_log, st.num_layer, l - 1, stamp, st.epoch);
+        }
+        st4(o + 4 * (long long)c, x[0]);
+    }
+}
+
 // Lazy mode: bring every written row current and stamp it with the current epoch.
 __global__ void __launch_bounds__(256) materialize_kernel(StateView st, long long rows, int ds4) {
     // one warp per (node, layer>=1) row
@@ -155,6 +180,25 @@ extern "C" int tpn_gather(const tpn_state_t* st, const int64_t* ids_dev, int64_t
     const long long* ids = reinterpret_cast<const long long*>(ids_dev);
     if (v.stamps != nullptr) gather_kernel<true><<<grid, 256, 0, stream>>>(v, ids, n, out_dev, ds4);
     else gather_kernel<false><<<grid, 256, 0, stream>>>(v, ids, n, out_dev, ds4);
+    return check_launch();
+}
+
+extern "C" int tpn_gather_blocks(const tpn_state_t* st, const int64_t* ids_dev, int64_t n, float* out_dev,
+                                 void* stream_v) {
+    using namespace tpn;
+    int rc = validate_state(st);
+    if (rc != TPN_OK) return rc;
+    if (n < 0) return TPN_ERR_INVALID_ARGUMENT;
+    if (n == 0) return TPN_OK;
+    if (ids_dev == nullptr || out_dev == nullptr || (reinterpret_cast<uintptr_t>(out_dev) & 15) != 0)
+        return TPN_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    const StateView v = make_view(st);
+    const int ds4 = (int)(st->row_stride / 4);
+    const unsigned grid = (unsigned)((n * 32 + 255) / 256);
+    const long long* ids = reinterpret_cast<const long long*>(ids_dev);
+    if (v.stamps != nullptr) gather_blocks_kernel<true><<<grid, 256, 0, stream>>>(v, ids, n, out_dev, ds4);
+    else gather_blocks_kernel<false><<<grid, 256, 0, stream>>>(v, ids, n, out_dev, ds4);
     return check_launch();
 }
 

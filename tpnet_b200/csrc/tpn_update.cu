@@ -46,6 +46,29 @@ struct DecayArgs {
     int has_decay;
 };
 
+// Where the messages come from.  Edge mode (B > 0): message m < B has target a[m] = src and
+// source b[m] = dst, message m >= B the reverse (the two scatter_add_ of TPNet.py:93-96), both
+// weighted by the edge's timestamp t[m mod B].  Message mode (B == 0, sharded state): message m
+// has target a[m], source b[m] and timestamp t[m]; the given order is the accumulation order.
+struct MsgSource {
+    const long long* a;
+    const long long* b;
+    const double* t;
+    long long B;
+    __device__ __forceinline__ void get(int m, long long& tgt, long long& oth, int& widx) const {
+        if (B > 0) {
+            const int j = m < B ? m : (int)(m - B);
+            tgt = m < B ? a[j] : b[j];
+            oth = m < B ? b[j] : a[j];
+            widx = j;
+        } else {
+            tgt = a[m];
+            oth = b[m];
+            widx = m;
+        }
+    }
+};
+
 struct Workspace {
     float* w;          // [B]
     uint32_t* key_a;   // [E]
@@ -70,7 +93,7 @@ Workspace carve(void* base, int64_t batch, int num_layer, int64_t row_stride) {
     size_t off = 0;
     Workspace ws;
     auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes, 256); return r; };
-    ws.w = reinterpret_cast<float*>(take(sizeof(float) * batch));
+    ws.w = reinterpret_cast<float*>(take(sizeof(float) * E));
     ws.key_a = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.key_b = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.val_a = reinterpret_cast<uint32_t*>(take(4 * E));
@@ -119,8 +142,7 @@ __device__ __forceinline__ void sweep_body(const StateView& st, const DecayArgs&
 }
 
 __global__ void __launch_bounds__(kPrepThreads)
-prep_small_kernel(const long long* __restrict__ src, const long long* __restrict__ dst,
-                  const double* __restrict__ t, int B, float t_last_f, float neg_lambda, long long num_nodes,
+prep_small_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long long num_nodes,
                   uint32_t* __restrict__ skey, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
                   uint32_t* __restrict__ sslot, uint32_t* __restrict__ slen, int* __restrict__ err_flag,
                   float* decay_log, int L, long long new_epoch, DecayArgs decay, StateView st, SweepArgs sweep) {
@@ -130,8 +152,8 @@ prep_small_kernel(const long long* __restrict__ src, const long long* __restrict
         return;
     }
     __shared__ __align__(16) unsigned long long comp[kSmallMaxMsgs];   // (target << 32 | message index)
-    __shared__ float wsm[kSmallMaxMsgs / 2];
-    const int E = 2 * B;
+    __shared__ float wsm[kSmallMaxMsgs];
+    const int n_w = msgs.B > 0 ? (int)msgs.B : E;             // distinct weights (per edge / per message)
     if (threadIdx.x == 0 && decay_log != nullptr && decay.has_decay) {
         for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay.c[l];
     }
@@ -147,21 +169,23 @@ prep_small_kernel(const long long* __restrict__ src, const long long* __restrict
         for (int m = threadIdx.x; m < Epad; m += kPrepThreads) {
             uint32_t key = 0xffffffffu >> 10;                 // padding: above every real key
             if (m < E) {
-                const int j = m < B ? m : m - B;
-                const long long tgt = m < B ? src[j] : dst[j];
-                const long long oth = m < B ? dst[j] : src[j];
+                long long tgt, oth;
+                int widx;
+                msgs.get(m, tgt, oth, widx);
                 const bool ok = tgt >= 0 && tgt < num_nodes && oth >= 0 && oth < num_nodes;
                 if (!ok && err_flag != nullptr) *err_flag = 1;
                 key = ok ? (uint32_t)tgt : (uint32_t)num_nodes;   // sentinel: dropped by walk
-                if (m < B) wsm[m] = edge_weight(t[m], t_last_f, neg_lambda);
+                if (m < n_w) wsm[m] = edge_weight(msgs.t[m], t_last_f, neg_lambda);
             }
             if (narrow) c32[m] = (key << 10) | (uint32_t)m;
             else comp[m] = ((unsigned long long)(m < E ? key : 0xffffffffu) << 32) | (uint32_t)m;
         }
         __syncthreads();
         for (int m = threadIdx.x; m < E; m += kPrepThreads) {
-            const int j = m < B ? m : m - B;
-            const uint32_t other = (uint32_t)(m < B ? dst[j] : src[j]);
+            long long tgt_unused, oth;
+            int j;
+            msgs.get(m, tgt_unused, oth, j);
+            const uint32_t other = (uint32_t)oth;
             int rank = 0, slot = 0, upper = 0;
             uint32_t mykey;
             if (narrow) {
@@ -202,14 +226,14 @@ prep_small_kernel(const long long* __restrict__ src, const long long* __restrict
     for (int m = threadIdx.x; m < P; m += kPrepThreads) {
         unsigned long long c = ~0ull;                         // padding sorts last
         if (m < E) {
-            const int j = m < B ? m : m - B;
-            const long long tgt = m < B ? src[j] : dst[j];
-            const long long oth = m < B ? dst[j] : src[j];
+            long long tgt, oth;
+            int widx;
+            msgs.get(m, tgt, oth, widx);
             const bool ok = tgt >= 0 && tgt < num_nodes && oth >= 0 && oth < num_nodes;
             if (!ok && err_flag != nullptr) *err_flag = 1;
             const uint32_t key = ok ? (uint32_t)tgt : (uint32_t)num_nodes;
             c = ((unsigned long long)key << 32) | (uint32_t)m;
-            if (m < B) wsm[m] = edge_weight(t[m], t_last_f, neg_lambda);
+            if (m < n_w) wsm[m] = edge_weight(msgs.t[m], t_last_f, neg_lambda);
         }
         comp[m] = c;
     }
@@ -231,8 +255,10 @@ prep_small_kernel(const long long* __restrict__ src, const long long* __restrict
         const unsigned long long c = comp[p];
         const uint32_t m = (uint32_t)c;
         const uint32_t mykey = (uint32_t)(c >> 32);
-        const int j = m < (uint32_t)B ? m : m - B;
-        const uint32_t other = (uint32_t)(m < (uint32_t)B ? dst[j] : src[j]);
+        long long tgt_unused, oth;
+        int j;
+        msgs.get((int)m, tgt_unused, oth, j);
+        const uint32_t other = (uint32_t)oth;
         skey[p] = mykey;
         ssrc[p] = other;
         sw[p] = wsm[j];
@@ -256,23 +282,23 @@ prep_small_kernel(const long long* __restrict__ src, const long long* __restrict
 
 // ---------------------------------------------------------------- large path
 __global__ void __launch_bounds__(256)
-prep_large_kernel(const long long* __restrict__ src, const long long* __restrict__ dst,
-                  const double* __restrict__ t, long long B, float t_last_f, float neg_lambda, long long num_nodes,
+prep_large_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long long num_nodes,
                   float* __restrict__ w, uint32_t* __restrict__ key, uint32_t* __restrict__ val,
                   int* __restrict__ err_flag, float* decay_log, int L, long long new_epoch, DecayArgs decay) {
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0 && decay_log != nullptr && decay.has_decay) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m == 0 && decay_log != nullptr && decay.has_decay) {
         for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay.c[l];
     }
-    if (j >= B) return;
-    const long long s = src[j], d = dst[j];
-    const bool ok = s >= 0 && s < num_nodes && d >= 0 && d < num_nodes;
+    if (m >= E) return;
+    long long tgt, oth;
+    int widx;
+    msgs.get(m, tgt, oth, widx);
+    const bool ok = tgt >= 0 && tgt < num_nodes && oth >= 0 && oth < num_nodes;
     if (!ok && err_flag != nullptr) *err_flag = 1;
-    w[j] = edge_weight(t[j], t_last_f, neg_lambda);
-    key[j] = ok ? (uint32_t)s : (uint32_t)num_nodes;
-    key[B + j] = ok ? (uint32_t)d : (uint32_t)num_nodes;
-    val[j] = (uint32_t)j;
-    val[B + j] = (uint32_t)(B + j);
+    const int n_w = msgs.B > 0 ? (int)msgs.B : E;
+    if (m < n_w) w[m] = edge_weight(msgs.t[m], t_last_f, neg_lambda);
+    key[m] = ok ? (uint32_t)tgt : (uint32_t)num_nodes;
+    val[m] = (uint32_t)m;
 }
 
 __global__ void __launch_bounds__(kRadixThreads)
@@ -381,15 +407,16 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
 }
 
 __global__ void __launch_bounds__(256)
-payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ skey,
-               const long long* __restrict__ src, const long long* __restrict__ dst, const float* __restrict__ w,
-               long long B, int E, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
+payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ skey, MsgSource msgs,
+               const float* __restrict__ w, int E, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
                uint32_t* __restrict__ sslot, uint32_t* __restrict__ slen) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= E) return;
     const uint32_t m = order[p];
-    const long long j = m < B ? m : m - B;
-    const uint32_t other = (uint32_t)(m < B ? dst[j] : src[j]);
+    long long tgt_unused, oth;
+    int j;
+    msgs.get((int)m, tgt_unused, oth, j);
+    const uint32_t other = (uint32_t)oth;
     const uint32_t mykey = skey[p];
     ssrc[p] = other;
     sw[p] = w[j];
@@ -588,18 +615,13 @@ extern "C" size_t tpn_update_workspace_bytes(const tpn_state_t* st, int64_t batc
     return tpn::carve(nullptr, batch, st->num_layer, st->row_stride).bytes;
 }
 
-extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t* dst_dev, const double* t_dev,
-                          int64_t batch, double t_last, float neg_lambda, const float* decay, void* ws_dev,
-                          size_t ws_bytes, int32_t* err_flag_dev, void* stream_v) {
-    using namespace tpn;
-    int rc = validate_state(st);
-    if (rc != TPN_OK) return rc;
-    if (batch < 1 || batch > ((int64_t)1 << 26) || src_dev == nullptr || dst_dev == nullptr || t_dev == nullptr ||
-        ws_dev == nullptr || st->num_nodes >= (int64_t)0xffffffffll)
-        return TPN_ERR_INVALID_ARGUMENT;
-    Workspace ws = carve(ws_dev, batch, st->num_layer, st->row_stride);
+namespace tpn {
+namespace {
+
+int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch, double t_last, float neg_lambda,
+                const float* decay, void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, cudaStream_t stream) {
+    Workspace ws = carve(ws_dev, ws_batch, st->num_layer, st->row_stride);
     if (ws.bytes > ws_bytes) return TPN_ERR_WORKSPACE_TOO_SMALL;
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     const bool lazy = st->stamps != nullptr;
     const int L = st->num_layer;
 
@@ -620,13 +642,12 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
         new_epoch = st->epoch + 1;
     }
 
-    const int E = (int)(2 * batch);
     const int ds4 = (int)(st->row_stride / 4);
     const float t_last_f = (float)t_last;
-    const long long* src = reinterpret_cast<const long long*>(src_dev);
-    const long long* dst = reinterpret_cast<const long long*>(dst_dev);
     float* log_w = lazy ? st->decay_log : nullptr;
-    const bool snapshot_path = E <= kSnapMaxMsgs && L >= 1;
+    // message mode (sharded): a source need not be a local target, so the snapshot trick
+    // ("every source is also a target") does not apply — use the per-layer walk
+    const bool snapshot_path = msgs.B > 0 && E <= kSnapMaxMsgs;
     const bool eager_sweep = !lazy && dargs.has_decay;
     const long long sweep_total4 = st->num_nodes * (long long)L * ds4;
 
@@ -642,14 +663,13 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
             const long long want = (sweep_total4 + kPrepThreads - 1) / kPrepThreads;
             grid += (unsigned)(want < 148 * 4 ? (want < 1 ? 1 : want) : 148 * 4);
         }
-        prep_small_kernel<<<grid, kPrepThreads, 0, stream>>>(src, dst, t_dev, (int)batch, t_last_f, neg_lambda,
-                                                             st->num_nodes, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
-                                                             ws.slen, err_flag_dev, log_w, L, new_epoch, dargs, view,
-                                                             sw_args);
+        prep_small_kernel<<<grid, kPrepThreads, 0, stream>>>(msgs, E, t_last_f, neg_lambda, st->num_nodes, ws.key_a,
+                                                             ws.ssrc, ws.sw, ws.sslot, ws.slen, err_flag_dev, log_w, L,
+                                                             new_epoch, dargs, view, sw_args);
     } else {
-        prep_large_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, stream>>>(
-            src, dst, t_dev, batch, t_last_f, neg_lambda, st->num_nodes, ws.w, ws.key_a, ws.val_a, err_flag_dev, log_w,
-            L, new_epoch, dargs);
+        prep_large_kernel<<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(msgs, E, t_last_f, neg_lambda,
+                                                                          st->num_nodes, ws.w, ws.key_a, ws.val_a,
+                                                                          err_flag_dev, log_w, L, new_epoch, dargs);
         int bits = 0;
         while ((1ll << bits) <= st->num_nodes) ++bits;    // keys are in [0, num_nodes] (num_nodes = dropped)
         const int passes = (bits + 7) / 8;
@@ -665,7 +685,7 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
         if (kin != ws.key_a) {       // odd number of passes: sorted keys live in key_b
             cudaMemcpyAsync(ws.key_a, kin, sizeof(uint32_t) * E, cudaMemcpyDeviceToDevice, stream);
         }
-        payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(vin, ws.key_a, src, dst, ws.w, batch, E, ws.ssrc, ws.sw,
+        payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(vin, ws.key_a, msgs, ws.w, E, ws.ssrc, ws.sw,
                                                             snapshot_path ? ws.sslot : nullptr, ws.slen);
         if (eager_sweep) {
             const long long want = (sweep_total4 + 255) / 256;
@@ -704,4 +724,44 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
         }
     }
     return check_launch();
+}
+
+}  // namespace
+}  // namespace tpn
+
+extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t* dst_dev, const double* t_dev,
+                          int64_t batch, double t_last, float neg_lambda, const float* decay, void* ws_dev,
+                          size_t ws_bytes, int32_t* err_flag_dev, void* stream_v) {
+    using namespace tpn;
+    int rc = validate_state(st);
+    if (rc != TPN_OK) return rc;
+    if (batch < 1 || batch > ((int64_t)1 << 26) || src_dev == nullptr || dst_dev == nullptr || t_dev == nullptr ||
+        ws_dev == nullptr || st->num_nodes >= (int64_t)0xffffffffll)
+        return TPN_ERR_INVALID_ARGUMENT;
+    MsgSource msgs;
+    msgs.a = reinterpret_cast<const long long*>(src_dev);
+    msgs.b = reinterpret_cast<const long long*>(dst_dev);
+    msgs.t = t_dev;
+    msgs.B = batch;
+    return update_impl(st, msgs, (int)(2 * batch), batch, t_last, neg_lambda, decay, ws_dev, ws_bytes, err_flag_dev,
+                       reinterpret_cast<cudaStream_t>(stream_v));
+}
+
+extern "C" int tpn_update_messages(tpn_state_t* st, const int64_t* tgt_dev, const int64_t* src_dev,
+                                   const double* t_dev, int64_t num_messages, double t_last, float neg_lambda,
+                                   const float* decay, void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev,
+                                   void* stream_v) {
+    using namespace tpn;
+    int rc = validate_state(st);
+    if (rc != TPN_OK) return rc;
+    if (num_messages < 1 || num_messages > ((int64_t)1 << 27) || tgt_dev == nullptr || src_dev == nullptr ||
+        t_dev == nullptr || ws_dev == nullptr || st->num_nodes >= (int64_t)0xffffffffll)
+        return TPN_ERR_INVALID_ARGUMENT;
+    MsgSource msgs;
+    msgs.a = reinterpret_cast<const long long*>(tgt_dev);
+    msgs.b = reinterpret_cast<const long long*>(src_dev);
+    msgs.t = t_dev;
+    msgs.B = 0;
+    return update_impl(st, msgs, (int)num_messages, (num_messages + 1) / 2, t_last, neg_lambda, decay, ws_dev,
+                       ws_bytes, err_flag_dev, reinterpret_cast<cudaStream_t>(stream_v));
 }

@@ -100,10 +100,12 @@ class _Host:
 class RandomProjectionModule(nn.Module):
     def __init__(self, node_num: int, edge_num: int, dim_factor: int, num_layer: int, time_decay_weight: float,
                  device: str, use_matrix: bool, beginning_time: np.float64, not_scale: bool, enforce_dim: int,
-                 decay_mode: str = 'auto'):
+                 decay_mode: str = 'auto', init_p0: bool = True, state_device=None):
         """Arguments as the reference constructor (TPNet.py:10-26).  ``decay_mode`` in
         {'auto', 'eager', 'lazy'} selects how the time decay of TPNet.py:83-85 is
-        realised; all modes produce the same values."""
+        realised; all modes produce the same values.  ``init_p0=False`` leaves P_0 zero for the
+        caller to fill and ``state_device`` allocates the packed state directly on a device
+        (both for states too large to stage through host memory)."""
         super().__init__()
         if not 1 <= num_layer <= _lib.TPN_MAX_LAYERS:
             raise ValueError(f'num_layer must be in 1..{_lib.TPN_MAX_LAYERS}')
@@ -130,13 +132,13 @@ class RandomProjectionModule(nn.Module):
         self.decay_mode = decay_mode
 
         # packed node-major state; P_l[u] = _state[u, l, :dim]
-        self._state = torch.zeros(self.node_num, self.num_layer + 1, self.row_stride, dtype=torch.float32)
+        self._state = torch.zeros(self.node_num, self.num_layer + 1, self.row_stride, dtype=torch.float32,
+                                  device=state_device)
         if self.use_matrix:
-            first = torch.eye(self.node_num)                              # TPNet.py:48-49
-        else:
+            self._state[:, 0, :self.dim] = torch.eye(self.node_num)      # TPNet.py:48-49
+        elif init_p0:
             # same RNG call as TPNet.py:58 so a seeded run draws the same P_0
-            first = torch.normal(0, 1 / math.sqrt(self.dim), (self.node_num, self.dim))
-        self._state[:, 0, :self.dim] = first
+            self._state[:, 0, :self.dim] = torch.normal(0, 1 / math.sqrt(self.dim), (self.node_num, self.dim))
         self.random_projections = nn.ParameterList(
             [nn.Parameter(self._state[:, i, :self.dim], requires_grad=False) for i in range(self.num_layer + 1)])
         self.pair_wise_feature_dim = (2 * self.num_layer + 2) ** 2        # TPNet.py:63
@@ -145,6 +147,9 @@ class RandomProjectionModule(nn.Module):
 
         # host mirrors / device scratch (not part of state_dict)
         self._h = _Host(float(beginning_time))
+        if self._state.is_cuda:
+            self._h.dev_index = self._state.device.index if self._state.device.index is not None \
+                else torch.cuda.current_device()
         self._stamps: Optional[torch.Tensor] = None
         self._decay_log: Optional[torch.Tensor] = None
         self._ws: Optional[torch.Tensor] = None
