@@ -1,22 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — temporal edges/sec through the walk-projection hot path (update +
-pair-wise encode) on synthetic graphs of the BASELINE.json shapes.
+"""bench.py — temporal edges/sec through the walk-projection hot path (update + pair-wise
+encode) on synthetic graphs of the BASELINE.json shapes.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload reddit|wikipedia|flights] [--no-flush]
+                    [--workload powerlaw|reddit|wikipedia|flights]
 
-One "step" = one batch of B=200 temporal edges through the hot path exactly as one
-TPNet training/eval batch drives it: two encoder calls of 4*B*K
-pairs (positive and negative destinations, models/TPNet.py:313-316), two decoder
-calls of B pairs (models/modules.py:112), then `update` (train_link_prediction.py:372).
-That is p = 8K+2 = 162 pair-encodes per edge at K=20.
+Primary workload (all N): BASELINE.json configs[3], the one its metric ("... at 1/2/4/8 B200;
+% HBM roofline") is quoted on — a power-law temporal graph with 10M nodes, d=210, L=3, lazy
+decay, batches of 100,000 edges, p=2 pair-encodes per edge (the decoder shape of
+models/modules.py:112: (src,dst) and (src,neg)).  It fits one GPU (34.6 GB state) and is
+HBM-bound, so the roofline fraction is a real DRAM figure.  N>1: the state is sharded by node
+id (tpnet_b200/sharded.py), strong scaling of the same graph and batch.
+At N=1 the line also carries `also.reddit`: BASELINE.json configs[1] (Reddit-shaped, B=200,
+K=20, p=162 — one TPNet training batch, latency-bound, state L2-resident).
 
-Prints ONE JSON line (see the driver contract).  `value` = edges/s with all inputs
-resident in HBM (each step replayed as a CUDA graph, L2 flushed between steps,
-device-event timing); `e2e` = the same steps through the module's public numpy API
-(pinned H2D of ids inside the timed region, `self.mlp` included, a scalar result read
-back every step).  `--impl reference` times the CPU port of the reference
-(oracle/cpu_port.py) on the host cores instead.
+One JSON line on stdout (driver contract).  `value`: inputs resident in HBM, CUDA-event time.
+`e2e`: the public numpy API with pinned H2D of the step's inputs, `self.mlp`, and a scalar
+result read back per step.  `--impl reference`: the torch-CPU port of the reference
+(oracle/cpu_port.py) on the host cores.
 """
 from __future__ import annotations
 
@@ -36,47 +37,36 @@ sys.path.insert(0, ROOT)
 
 from tpnet_b200.synth import SHAPES, RecentNeighbors, edge_stream, tpnet_pair_lists  # noqa: E402
 
-BATCH = 200
+BATCH = 200                 # TPNet batch (configs[0..2])
 NUM_NEIGHBORS = 20
 WARM_BATCHES = 400          # untimed: populates P_1..P_L and the neighbour table
+PL_BATCH = 100_000          # power-law batch (configs[3])
+PL_WARM = 12
+METRIC = 'temporal edges/sec (update+pairwise encode)'
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=500)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='reddit', choices=['reddit', 'wikipedia', 'flights'])
+    ap.add_argument('--workload', default='powerlaw', choices=['powerlaw', 'reddit', 'wikipedia', 'flights'])
     ap.add_argument('--decay-mode', default='auto', choices=['auto', 'eager', 'lazy'])
-    ap.add_argument('--no-flush', action='store_true', help='keep L2 warm between steps (reported, not the headline)')
-    ap.add_argument('--cpu-sample-steps', type=int, default=30)
-    ap.add_argument('--warm-batches', type=int, default=WARM_BATCHES, help='untimed batches that fill the state')
+    ap.add_argument('--no-flush', action='store_true', help='small shapes: keep L2 warm between steps')
+    ap.add_argument('--no-also', action='store_true', help='N=1: skip the secondary Reddit-shaped measurement')
+    ap.add_argument('--cpu-sample-steps', type=int, default=None)
+    ap.add_argument('--warm-batches', type=int, default=None, help='untimed batches that fill the state')
+    ap.add_argument('--pl-nodes', type=int, default=None, help='override the power-law node count (debug)')
+    ap.add_argument('--pl-batch', type=int, default=PL_BATCH)
     return ap.parse_args()
 
 
-# ----------------------------------------------------------------------------- workload
-def make_steps(shape, n_steps, seed, warm=WARM_BATCHES):
-    """Returns (warm_batches, steps).  Each step holds the numpy inputs of one batch."""
-    rng = np.random.default_rng(seed + 17)
-    nbr = RecentNeighbors(shape.node_num, NUM_NEIGHBORS)
-    stream = edge_stream(shape, BATCH, warm + n_steps, seed=seed)
-    warm_batches, steps = [], []
-    lo, hi = (shape.num_src + 1, shape.num_src + shape.num_dst + 1) if shape.num_dst else (1, shape.num_src + 1)
-    for i, (s, d, t) in enumerate(stream):
-        if i < warm:
-            warm_batches.append((s, d, t))
-        else:
-            neg = rng.integers(lo, hi, BATCH).astype(np.int64)          # random negative sampling
-            pa, pb = tpnet_pair_lists(nbr, s, d)
-            na, nb = tpnet_pair_lists(nbr, s, neg)
-            steps.append(dict(src=s, dst=d, t=t, neg=neg, enc_pos=(pa, pb), enc_neg=(na, nb)))
-        nbr.insert(s, d)
-    return warm_batches, steps
-
-
-def pairs_per_step():
-    return 8 * BATCH * NUM_NEIGHBORS + 2 * BATCH
+def peak_gbs():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (burst copy)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
 def algorithmic_bytes(shape):
@@ -84,6 +74,13 @@ def algorithmic_bytes(shape):
     per_edge = 24 * L * d + 24
     per_pair = 2 * (L + 1) * d * 4 + (2 * L + 2) ** 2 * 4 + 16
     return per_edge, per_pair
+
+
+def traffic_note(key):
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p)).get(key)
+    return None
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -129,8 +126,31 @@ class ClockSampler:
             self.proc.terminate()
 
 
-# ----------------------------------------------------------------------------- CPU port (baseline / reference arm)
-def cpu_port_run(shape, warm_batches, steps, n_warm, n_timed, threads):
+# ============================================================================= Reddit-shaped (TPNet batch) workload
+def make_steps(shape, n_steps, seed, warm=WARM_BATCHES):
+    """Returns (warm_batches, steps).  Each step holds the numpy inputs of one batch."""
+    rng = np.random.default_rng(seed + 17)
+    nbr = RecentNeighbors(shape.node_num, NUM_NEIGHBORS)
+    stream = edge_stream(shape, BATCH, warm + n_steps, seed=seed)
+    warm_batches, steps = [], []
+    lo, hi = (shape.num_src + 1, shape.num_src + shape.num_dst + 1) if shape.num_dst else (1, shape.num_src + 1)
+    for i, (s, d, t) in enumerate(stream):
+        if i < warm:
+            warm_batches.append((s, d, t))
+        else:
+            neg = rng.integers(lo, hi, BATCH).astype(np.int64)          # random negative sampling
+            pa, pb = tpnet_pair_lists(nbr, s, d)
+            na, nb = tpnet_pair_lists(nbr, s, neg)
+            steps.append(dict(src=s, dst=d, t=t, neg=neg, enc_pos=(pa, pb), enc_neg=(na, nb)))
+        nbr.insert(s, d)
+    return warm_batches, steps
+
+
+def pairs_per_step():
+    return 8 * BATCH * NUM_NEIGHBORS + 2 * BATCH
+
+
+def cpu_port_tpnet(shape, warm_batches, steps, n_warm, n_timed, threads):
     """Times the torch-CPU port of the reference on the host cores: same step shape."""
     from oracle.cpu_port import CpuWalkProjection          # baseline leg only (see oracle/__init__.py)
     torch.set_num_threads(threads)
@@ -154,11 +174,9 @@ def cpu_port_run(shape, warm_batches, steps, n_warm, n_timed, threads):
     t0 = time.perf_counter()
     for st in steps[n_warm:n_warm + n_timed]:
         one(st)
-    dt = time.perf_counter() - t0
-    return dt / n_timed
+    return (time.perf_counter() - t0) / n_timed
 
 
-# ----------------------------------------------------------------------------- ours
 def build_module(shape, device, decay_mode, t0):
     from tpnet_b200 import RandomProjectionModule
     torch.manual_seed(0)
@@ -199,59 +217,17 @@ def api_step(m, st):
     return float(res.item())                                   # D2H read of the step's result
 
 
-def main():
-    args = parse_args()
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    shape = SHAPES[args.workload]
-    K, W = args.steps, max(args.warmup, 3)
+def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
+    """Single-GPU TPNet-batch workload (Reddit / Wikipedia / Flights shapes)."""
     per_edge_B, per_pair_B = algorithmic_bytes(shape)
     pps = pairs_per_step()
-    workload_name = (f'{shape.name}-shaped synthetic graph ({shape.num_nodes} nodes, {shape.num_edges} edges), '
-                     f'd={shape.dim}, L={shape.num_layer}, batch {BATCH}, K={NUM_NEIGHBORS}, '
-                     f'{pps // BATCH} pair-encodes per edge, random negatives')
-    config = {'workload': workload_name, 'batch': BATCH, 'num_neighbors': NUM_NEIGHBORS, 'pairs_per_step': pps,
-              'dim': shape.dim, 'num_layer': shape.num_layer, 'node_num': shape.node_num}
-
-    # ---------------- reference arm: CPU port on the host cores, rank 0 only
-    if args.impl == 'reference':
-        if rank != 0:
-            return
-        threads = os.cpu_count() or 1
-        warm_batches, steps = make_steps(shape, K + W, seed=rank, warm=args.warm_batches)
-        sec = cpu_port_run(shape, warm_batches, steps, W, K, threads)
-        val = BATCH / sec
-        line = {'impl': 'reference', 'metric': 'temporal edges/sec (update+pairwise encode)', 'value': val,
-                'unit': 'edges/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': W, 'ms_per_step': sec * 1e3,
-                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-                'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': val, 'unit': 'edges/s', 'cores': threads, 'kind': 'port',
-                                 'sample': f'{K} steps of the same workload (torch-CPU port of the reference, '
-                                           f'self.mlp included)'},
-                'e2e': {'value': val, 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
-        return
-
-    # ---------------- our arm
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py (impl=ours) needs a CUDA device: there is no CPU fallback')
-    import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    device = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=device)
-    from tpnet_b200 import _lib
-    _lib.load()
-
-    n_steps = 2 * (K + W)
-    warm_batches, steps = make_steps(shape, n_steps, seed=rank, warm=args.warm_batches)   # replicas: own stream per rank
+    warm_n = args.warm_batches if args.warm_batches is not None else WARM_BATCHES
+    warm_batches, steps = make_steps(shape, 2 * (K + W), seed=0, warm=warm_n)
     m = build_module(shape, device, args.decay_mode, warm_batches[0][2][0])
     for s, d, t in warm_batches:
         m.update(s, d, t)
     torch.cuda.synchronize()
 
-    # -- device-resident, graph-replayed steps
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     dsteps = [to_dev(st, device) for st in steps[:K + W]]
     graphs = []
@@ -267,11 +243,6 @@ def main():
     for g in graphs[:W]:
         g.replay()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.3 if sampler else 0)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     wall0 = time.perf_counter()
     for k in range(K):
@@ -281,15 +252,12 @@ def main():
         graphs[W + k].replay()
         ev[k][1].record()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     wall1 = time.perf_counter()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     m.check_errors()
 
-    # -- dominant kernel (the 4BK-pair encoder launch): live CUDA-event timing, L2 flushed.
-    #    Each launch is captured alone in a CUDA graph so that no host launch latency sits
-    #    between the two events (the flush before it gives the host time to enqueue).
+    # dominant kernel (the 4BK-pair encoder launch): each launch alone in a CUDA graph so that no
+    # host launch latency sits between the two events; L2 flushed before each
     n_pair = min(K, 100)
     pair_graphs = []
     with torch.cuda.stream(side):
@@ -306,86 +274,352 @@ def main():
         pair_graphs[k].replay()
         pev[k][1].record()
     torch.cuda.synchronize()
-    pair_ms_avg = float(np.mean([a.elapsed_time(b) for a, b in pev]))
+    pair_ms = float(np.mean([a.elapsed_time(b) for a, b in pev]))
     pairs_per_launch = len(dsteps[0]['enc_pos'][0])
 
-    # -- end to end through the public numpy API (pinned H2D + head + scalar D2H per step)
     api = steps[K + W:]
     for st in api[:W]:
         api_step(m, st)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     e0 = time.perf_counter()
     for st in api[W:W + K]:
         api_step(m, st)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - e0) * 1e3
     h2d = 2 * (2 * 4 * BATCH * NUM_NEIGHBORS * 8) + 2 * (2 * BATCH * 8) + 3 * BATCH * 8
-    clocks = sampler.window(wall0, time.perf_counter()) if sampler else None
-    if sampler:
-        sampler.stop()
 
-    # -- max over ranks
-    t = torch.tensor([dev_ms, e2e_ms, wall1 - wall0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_s = [float(x) for x in t.tolist()]
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    edges = BATCH * K * world
-    value = edges / (dev_ms * 1e-3)
+    peak, peak_src = peak_gbs()
+    achieved = pairs_per_launch * per_pair_B / (pair_ms * 1e-3) / 1e9
     step_bytes = BATCH * per_edge_B + pps * per_pair_B
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (burst copy)'
-    else:
-        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    achieved = pairs_per_launch * per_pair_B / (pair_ms_avg * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('pairwise_kernel_dram_bytes_per_launch')
-    kernels_per_step = 4 + 1 + shape.num_layer + (0 if m.lazy else 1)
-    cpu = None
-    try:
-        threads = os.cpu_count() or 1
-        n_cpu = max(3, args.cpu_sample_steps)
-        sec = cpu_port_run(shape, warm_batches, steps, 2, n_cpu, threads)
-        cpu = {'value': BATCH / sec, 'unit': 'edges/s', 'cores': threads, 'kind': 'port',
-               'sample': f'{n_cpu} steps of the same workload on the host (torch-CPU port of the reference, '
-                         f'self.mlp included, {sec * 1e3:.1f} ms/step)'}
-    except Exception as exc:  # pragma: no cover
-        cpu = {'value': None, 'unit': 'edges/s', 'cores': 0, 'kind': 'port', 'sample': f'failed: {exc}'}
-
-    line = {
-        'metric': 'temporal edges/sec (update+pairwise encode)', 'value': value, 'unit': 'edges/s',
-        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': dev_ms / K, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': dict(config, parallelism=('single GPU' if world == 1 else f'{world} independent replicas'),
-                       decay_mode='lazy' if m.lazy else 'eager', l2='flushed between steps (256 MiB memset, untimed)'
-                       if not args.no_flush else 'warm (no flush)', timing='CUDA events per step, one CUDA graph per step',
-                       algorithmic_bytes_per_step=step_bytes, wall_ms_per_step_incl_flush=wall_s * 1e3 / K),
-        'pairs_per_s': pps * K * world / (dev_ms * 1e-3),
-        'algorithmic_GBps_step': step_bytes * K * world / (dev_ms * 1e-3) / 1e9,
-        'roofline': {'bound': 'hbm', 'kernel': 'tpn::pairwise_kernel (4BK-pair encoder launch)', 'achieved': achieved,
-                     'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                     'peak_source': peak_src, 'launch_us': pair_ms_avg * 1e3, 'pairs_per_launch': pairs_per_launch,
-                     'note': 'state (%.1f MB) is smaller than L2: after the first touch rows are served by L2, so '
-                             'algorithmic bytes/s can exceed the HBM copy peak' %
+    kernels_per_step = 4 + 3                                  # 4 pair-wise + prep(+sweep) + snapshot + walk
+    out = {
+        'value': BATCH * K / (dev_ms * 1e-3), 'unit': 'edges/s', 'steps': K, 'warmup': W, 'ms_per_step': dev_ms / K,
+        'config': {'workload': (f'{shape.name}-shaped synthetic graph ({shape.num_nodes} nodes, {shape.num_edges} '
+                                f'edges), d={shape.dim}, L={shape.num_layer}, batch {BATCH}, K={NUM_NEIGHBORS}, '
+                                f'{pps // BATCH} pair-encodes per edge, random negatives'),
+                   'batch': BATCH, 'num_neighbors': NUM_NEIGHBORS, 'pairs_per_step': pps, 'dim': shape.dim,
+                   'num_layer': shape.num_layer, 'node_num': shape.node_num, 'parallelism': 'single GPU',
+                   'decay_mode': 'lazy' if m.lazy else 'eager',
+                   'l2': 'warm (no flush)' if args.no_flush else 'flushed between steps (256 MiB memset, untimed)',
+                   'timing': 'CUDA events per step, one CUDA graph per step',
+                   'algorithmic_bytes_per_step': step_bytes,
+                   'wall_ms_per_step_incl_flush': (wall1 - wall0) * 1e3 / K},
+        'pairs_per_s': pps * K / (dev_ms * 1e-3),
+        'algorithmic_GBps_step': step_bytes * K / (dev_ms * 1e-3) / 1e9,
+        'roofline': {'bound': 'hbm', 'kernel': 'tpn::pairwise_tma_kernel (4BK-pair encoder launch)',
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': traffic_note('reddit_pairwise_dram_bytes_per_launch'), 'peak_source': peak_src,
+                     'launch_us': pair_ms * 1e3, 'pairs_per_launch': pairs_per_launch,
+                     'note': 'state (%.1f MB) is L2-resident: algorithmic bytes are served from L2 after first '
+                             'touch, so this is a fraction of the HBM copy peak reached out of L2, not DRAM use' %
                              (shape.node_num * (shape.num_layer + 1) * m.row_stride * 4 / 1e6)},
-        'cpu_baseline': cpu,
-        'e2e': {'value': BATCH * K * world / (e2e_ms * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': h2d,
+        'e2e': {'value': BATCH * K / (e2e_ms * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / K,
                 'path': 'RandomProjectionModule.get_pair_wise_feature/update with numpy ids, self.mlp included'},
         'gpu_launches': kernels_per_step * K,
-        'clocks': clocks,
     }
-    print(json.dumps(line))
+    if with_cpu:
+        threads = os.cpu_count() or 1
+        n_cpu = args.cpu_sample_steps or 30
+        sec = cpu_port_tpnet(shape, warm_batches, steps, 2, n_cpu, threads)
+        out['cpu_baseline'] = {'value': BATCH / sec, 'unit': 'edges/s', 'cores': threads, 'kind': 'port',
+                               'sample': f'{n_cpu} steps of the same workload on the host (torch-CPU port of the '
+                                         f'reference, self.mlp included, {sec * 1e3:.1f} ms/step)'}
+    del graphs, pair_graphs, m, flush
+    torch.cuda.empty_cache()
+    return out
+
+
+# ============================================================================= power-law (sharded) workload
+def powerlaw_shape(args):
+    import dataclasses
+    shape = SHAPES['powerlaw']
+    if args.pl_nodes:
+        shape = dataclasses.replace(shape, num_src=int(args.pl_nodes))
+    return shape
+
+
+def powerlaw_steps(shape, B, n, seed=1234):
+    """Replicated on every rank (same seed): (src, dst, t, neg) per step."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for s, d, t in edge_stream(shape, B, n, seed=seed):
+        neg = rng.integers(1, shape.num_src + 1, B).astype(np.int64)
+        out.append((s, d, t, neg))
+    return out
+
+
+def cpu_port_powerlaw(shape, B, n_warm, n_timed, threads, scale_down):
+    """CPU port on a down-scaled replica (the reference's eager decay is N-proportional)."""
+    import dataclasses
+    from oracle.cpu_port import CpuWalkProjection
+    torch.set_num_threads(threads)
+    small = dataclasses.replace(shape, num_src=max(shape.num_src // scale_down, 1000))
+    ref = CpuWalkProjection(small.node_num, shape.dim, shape.num_layer, shape.time_decay_weight, 0.0,
+                            not_scale=False, with_mlp=True, seed=0)
+    steps = powerlaw_steps(small, B, n_warm + n_timed)
+
+    def one(st):
+        s, d, t, neg = st
+        with torch.no_grad():
+            pos = ref.pair_wise(s, d)
+            ng = ref.pair_wise(s, neg)
+            ref.update(s, d, t)
+            return float(pos.sum() - ng.sum())
+
+    for st in steps[:n_warm]:
+        one(st)
+    t0 = time.perf_counter()
+    for st in steps[n_warm:]:
+        one(st)
+    return (time.perf_counter() - t0) / n_timed, small.node_num
+
+
+def run_powerlaw(args, rank, world, device, K, W, sampler):
+    import torch.distributed as dist
+    from tpnet_b200.sharded import ShardedRandomProjection
+    shape = powerlaw_shape(args)
+    B = args.pl_batch
+    per_edge_B, per_pair_B = algorithmic_bytes(shape)
+    warm_n = args.warm_batches if args.warm_batches is not None else PL_WARM
+    n_phase = min(K, 8)
+    steps = powerlaw_steps(shape, B, warm_n + 2 * (K + W) + n_phase)
+    torch.manual_seed(0)
+    m = ShardedRandomProjection(node_num=shape.node_num, edge_num=shape.edge_num, dim_factor=shape.dim_factor,
+                                num_layer=shape.num_layer, time_decay_weight=shape.time_decay_weight,
+                                device=str(device), use_matrix=False, beginning_time=np.float64(0.0),
+                                not_scale=False, enforce_dim=-1, decay_mode='lazy', ext_rows=2 * B + 1024,
+                                p0='device', state_device=device)
+    m = m.to(device)
+    m.init_p0_on_device(seed=0)
+    for s, d, t, _ in steps[:warm_n]:
+        m.update(s, d, t)
+    torch.cuda.synchronize()
+
+    def dev_plan(plan):
+        g = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)     # noqa: E731
+        plan.first_rows, plan.second_rows, plan.send_rows = g(plan.first_rows), g(plan.second_rows), g(plan.send_rows)
+        return plan
+
+    def stage(st):
+        """Resident inputs of one step: the routing plans are a pure function of the batch."""
+        s, d, t, neg = st
+        up, tmsg = m.plan_update(s, d, t)
+        return dict(src=s, dst=d, t=t, up=(dev_plan(up), torch.from_numpy(tmsg).to(device)),
+                    pos=dev_plan(m.plan_pairs(s, d)), neg=dev_plan(m.plan_pairs(s, neg)))
+
+    res = [stage(st) for st in steps[warm_n:warm_n + K + W]]
+
+    def resident(st):
+        m.pair_wise_gram(None, None, plan=st['pos'])
+        m.pair_wise_gram(None, None, plan=st['neg'])
+        m.update(st['src'], st['dst'], st['t'], plan=st['up'])
+
+    for st in res[:W]:
+        resident(st)
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    rows0 = m.exchanged_rows
+    wall0 = time.perf_counter()
+    for k in range(K):
+        ev[k][0].record()
+        resident(res[W + k])
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall1 = time.perf_counter()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    recv_rows_per_step = (m.exchanged_rows - rows0) / K
+    m.check_errors()
+    del res
+
+    # per-phase device time (events around each call) for the roofline of the dominant kernel
+    t_pair, t_upd, n_pairs_local, n_msgs_local = [], [], 0, 0
+    for st in steps[warm_n + K + W:warm_n + K + W + n_phase]:
+        r = stage(st)
+        if world > 1:
+            dist.barrier()
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        m.pair_wise_gram(None, None, plan=r['pos'])
+        b.record()
+        m.update(r['src'], r['dst'], r['t'], plan=r['up'])
+        c.record()
+        torch.cuda.synchronize()
+        t_pair.append(a.elapsed_time(b))
+        t_upd.append(b.elapsed_time(c))
+        n_pairs_local = int(r['pos'].first_rows.shape[0])
+        n_msgs_local = int(r['up'][0].first_rows.shape[0])
+    pair_ms, upd_ms = float(np.mean(t_pair)), float(np.mean(t_upd))
+
+    # end to end: numpy API, plans computed inside the timed region, head + scalar read-back
+    api = steps[warm_n + K + W + n_phase:][:K + W]
+
+    def api_one(st):
+        s, d, t, neg = st
+        with torch.no_grad():
+            _, pos = m.get_pair_wise_feature(s, d)
+            _, ng = m.get_pair_wise_feature(s, neg)
+            m.update(s, d, t)
+            r = pos.sum() - ng.sum()
+        return float(r.item())
+
+    for st in api[:W]:
+        api_one(st)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0 = time.perf_counter()
+    n_api = len(api) - W
+    for st in api[W:]:
+        api_one(st)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_ms = (time.perf_counter() - e0) * 1e3
+    wall_end = time.perf_counter()
+
+    tt = torch.tensor([dev_ms, e2e_ms, pair_ms, upd_ms, recv_rows_per_step], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, pair_ms, upd_ms, recv_rows_per_step = [float(x) for x in tt.tolist()]
+    if rank != 0:
+        return None
+
+    peak, peak_src = peak_gbs()
+    pair_gbs = n_pairs_local * per_pair_B / (pair_ms * 1e-3) / 1e9
+    upd_gbs = n_msgs_local * (per_edge_B / 2) / (upd_ms * 1e-3) / 1e9
+    dominant_is_update = upd_ms >= 2 * pair_ms            # two pair-wise calls per step vs one update
+    step_bytes = B * per_edge_B + 2 * B * per_pair_B
+    block_bytes = (shape.num_layer + 1) * m.row_stride * 4
+    state_gb = shape.node_num * block_bytes / 1e9
+    roof = {'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
+            'phases': {'pairwise': {'what': 'exchange (N>1) + tpn::pairwise_tma_kernel, %d pairs on rank 0' % n_pairs_local,
+                                    'ms': pair_ms, 'achieved': pair_gbs, 'frac': pair_gbs / peak},
+                       'update': {'what': 'exchange (N>1) + radix sort + 3 x tpn::walk_kernel, %d messages on rank 0'
+                                  % n_msgs_local, 'ms': upd_ms, 'achieved': upd_gbs, 'frac': upd_gbs / peak}}}
+    if dominant_is_update:
+        roof.update(kernel='update path (radix sort + per-layer tpn::walk_kernel)', achieved=upd_gbs,
+                    frac=upd_gbs / peak, traffic=traffic_note('powerlaw_update_dram_bytes_per_call'))
+    else:
+        roof.update(kernel='tpn::pairwise_tma_kernel', achieved=pair_gbs, frac=pair_gbs / peak,
+                    traffic=traffic_note('powerlaw_pairwise_dram_bytes_per_launch'))
+    h2d = 3 * B * 8 + 2 * (2 * B * 8)
+    return {
+        'metric': METRIC, 'value': B * K / (dev_ms * 1e-3), 'unit': 'edges/s', 'n_gpus': world, 'steps': K,
+        'warmup': W, 'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': (f'power-law temporal graph, {shape.num_nodes} nodes / {shape.num_edges} edges '
+                                f'(BASELINE configs[3]), d={shape.dim}, L={shape.num_layer}, batch {B}, 2 pair-encodes '
+                                f'per edge (decoder shape), lazy decay'),
+                   'batch': B, 'pairs_per_step': 2 * B, 'dim': shape.dim, 'num_layer': shape.num_layer,
+                   'node_num': shape.node_num, 'state_GB': state_gb,
+                   'parallelism': 'single GPU' if world == 1 else
+                   f'state sharded by node id over {world} GPUs, one all_to_all per call (NCCL)',
+                   'l2': f'no flush needed: {state_gb:.1f} GB state >> 126 MB L2',
+                   'timing': 'CUDA events per step, max over ranks; routing plans are part of the resident inputs',
+                   'algorithmic_bytes_per_step': step_bytes, 'wall_ms_per_step': (wall1 - wall0) * 1e3 / K},
+        'pairs_per_s': 2 * B * K / (dev_ms * 1e-3),
+        'algorithmic_GBps_step': step_bytes * K / (dev_ms * 1e-3) / 1e9,
+        'roofline': roof,
+        'e2e': {'value': B * n_api / (e2e_ms * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / n_api,
+                'path': 'ShardedRandomProjection.get_pair_wise_feature/update with numpy ids (routing plan computed '
+                        'on the host inside the timed region), self.mlp included'},
+        'gpu_launches': K * (2 + 2 + 11 + (6 if world > 1 else 0)),
+        'exchange': None if world == 1 else {'rows_received_per_rank_per_step': recv_rows_per_step,
+                                             'bytes_per_rank_per_step': recv_rows_per_step * block_bytes},
+        'clocks': sampler.window(wall0, wall_end) if sampler else None,
+    }
+
+
+# ============================================================================= main
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    threads = os.cpu_count() or 1
+
+    # ---------------- reference arm: CPU port on the host cores, rank 0 only
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        if args.workload == 'powerlaw':
+            K = min(args.steps or 3, 6)
+            W = min(args.warmup if args.warmup is not None else 1, 2)
+            shape = powerlaw_shape(args)
+            sec, n_small = cpu_port_powerlaw(shape, args.pl_batch, W, K, threads, scale_down=10)
+            val = args.pl_batch / sec
+            sample = (f'{K} batches of {args.pl_batch} edges + 2 pair-encodes per edge on a {n_small}-node replica '
+                      f'(10x fewer nodes: the reference\'s eager decay is N-proportional, so this flatters it)')
+            cfg = {'workload': f'power-law temporal graph (BASELINE configs[3]) d={shape.dim} L={shape.num_layer} '
+                               f'batch {args.pl_batch}, CPU arm on a 10x down-scaled node set', 'batch': args.pl_batch}
+        else:
+            shape = SHAPES[args.workload]
+            K, W = min(args.steps or 30, 60), max(args.warmup or 3, 1)
+            warm_batches, steps = make_steps(shape, K + W, seed=0, warm=60)
+            sec = cpu_port_tpnet(shape, warm_batches, steps, W, K, threads)
+            val = BATCH / sec
+            sample = f'{K} steps of the same workload (torch-CPU port of the reference, self.mlp included)'
+            cfg = {'workload': f'{shape.name}-shaped synthetic graph, batch {BATCH}, K={NUM_NEIGHBORS}', 'batch': BATCH}
+        print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'edges/s', 'n_gpus': args.gpus,
+                          'steps': K, 'warmup': W, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+                          'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+                          'cpu_baseline': {'value': val, 'unit': 'edges/s', 'cores': threads, 'kind': 'port',
+                                           'sample': sample},
+                          'e2e': {'value': val, 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    # ---------------- our arm
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py (impl=ours) needs a CUDA device: there is no CPU fallback')
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    from tpnet_b200 import _lib
+    _lib.load()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3 if sampler else 0)
+
+    if args.workload == 'powerlaw':
+        K, W = args.steps or 20, max(args.warmup if args.warmup is not None else 3, 3)
+        line = run_powerlaw(args, rank, world, device, K, W, sampler)
+        if rank == 0:
+            if world == 1:
+                n_cpu = args.cpu_sample_steps or 3
+                sec, n_small = cpu_port_powerlaw(powerlaw_shape(args), args.pl_batch, 1, n_cpu, threads, scale_down=10)
+                line['cpu_baseline'] = {'value': args.pl_batch / sec, 'unit': 'edges/s', 'cores': threads,
+                                        'kind': 'port',
+                                        'sample': f'{n_cpu} batches on a {n_small}-node replica (10x fewer nodes than '
+                                                  f'the GPU run; torch-CPU port of the reference, self.mlp included, '
+                                                  f'{sec:.2f} s/step)'}
+                if not args.no_also:
+                    line['also'] = {'reddit': run_tpnet_shape(args, SHAPES['reddit'], device, 300, 10, with_cpu=True)}
+            else:
+                line['cpu_baseline'] = None
+    else:
+        if world > 1:
+            raise SystemExit('the TPNet-batch shapes are single-GPU workloads (state 13-32 MB): use --workload powerlaw')
+        K, W = args.steps or 300, max(args.warmup if args.warmup is not None else 10, 3)
+        t0 = time.perf_counter()
+        body = run_tpnet_shape(args, SHAPES[args.workload], device, K, W, with_cpu=True)
+        line = {'metric': METRIC, 'n_gpus': 1, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic'}
+        line.update(body)
+        line['clocks'] = sampler.window(t0, time.perf_counter()) if sampler else None
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -67,6 +67,9 @@ def make_plan(first: np.ndarray, second: np.ndarray, world: int, rank: int, n_lo
     rank q is, by construction, rank q's receive list from rank r (same set, same order)."""
     first = np.asarray(first, dtype=np.int64)
     second = np.asarray(second, dtype=np.int64)
+    if world == 1:                                                   # everything is local
+        return ShardPlan(keep=np.arange(first.shape[0]), first_rows=first, second_rows=second,
+                         send_rows=np.zeros(0, dtype=np.int64), send_counts=[0], recv_counts=[0])
     of, os_ = first % world, second % world
     big = np.int64(max(int(first.max(initial=0)), int(second.max(initial=0))) + 1)
 
@@ -205,11 +208,12 @@ class ShardedRandomProjection(RandomProjectionModule):
         t = np.asarray(node_interact_times, dtype=np.float64)
         if len(t) == 0:
             raise IndexError('index -1 is out of bounds for axis 0 with size 0')
-        src = np.asarray(src_node_ids, dtype=np.int64)
-        dst = np.asarray(dst_node_ids, dtype=np.int64)
-        if src.min() < 0 or dst.min() < 0 or src.max() >= self.global_node_num or dst.max() >= self.global_node_num:
-            raise IndexError(f'index out of range for node_num {self.global_node_num}')
         if plan is None:
+            src = np.asarray(src_node_ids, dtype=np.int64)
+            dst = np.asarray(dst_node_ids, dtype=np.int64)
+            if src.min() < 0 or dst.min() < 0 or src.max() >= self.global_node_num or \
+                    dst.max() >= self.global_node_num:
+                raise IndexError(f'index out of range for node_num {self.global_node_num}')
             plan = self.plan_update(src, dst, t)
         plan, t_msg = plan
         next_time = float(t[-1]) if next_time is None else float(next_time)
