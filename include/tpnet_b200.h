@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define TPN_ABI_VERSION 1
+#define TPN_ABI_VERSION 2
 
 #define TPN_MAX_LAYERS 4
 
@@ -117,15 +117,25 @@ int tpn_update(tpn_state_t* st,
                double t_last, float neg_lambda, const float* decay,
                void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, void* stream);
 
+/* Test hook: selects code paths that are otherwise chosen by size.  Returns the previous flags.
+ *   TPN_DEBUG_PER_LAYER_WALK : large batches use one walk launch per layer (top-down) instead of
+ *                              the pre-batch snapshot + single all-layer launch. */
+#define TPN_DEBUG_PER_LAYER_WALK 1
+int tpn_set_debug_flags(int flags);
+
 /*
  * Message-level form of tpn_update for a node-sharded state (no reference
  * counterpart — the reference is single-device).  Message m adds source row src_dev[m] into
  * target row tgt_dev[m] with the weight of timestamp t_dev[m]; messages of one target are
- * accumulated in the order given.  Ids index rows of `st` (local rows, followed by the rows
- * received from other ranks); received rows must be current and are only ever read.
+ * accumulated in the order given.  Ids index rows of `st`: rows [0, num_local_rows) are this
+ * shard's rows, rows [num_local_rows, num_nodes) hold blocks received from other ranks — they
+ * must be current and are only ever read.  Precondition (true for edge batches, which carry
+ * both directions of every edge): every LOCAL source row is also a target of the same call;
+ * in lazy mode a violation sets *err_flag_dev = 2 (eager mode handles it correctly).
  */
 int tpn_update_messages(tpn_state_t* st,
                         const int64_t* tgt_dev, const int64_t* src_dev, const double* t_dev, int64_t num_messages,
+                        int64_t num_local_rows,
                         double t_last, float neg_lambda, const float* decay,
                         void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, void* stream);
 

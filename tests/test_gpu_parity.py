@@ -164,6 +164,53 @@ def test_update_bit_exact_with_equal_timestamps(B, N, dim, L, mode):
     m.check_errors()
 
 
+@pytest.mark.parametrize('per_layer', [False, True])
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('B,N,dim,L,skew', [(6000, 300, 210, 3, 1.3), (2100, 50, 140, 3, 1.1), (9000, 2000, 36, 4, 1.5),
+                                            (5000, 40, 300, 1, 1.2)])
+def test_hub_walker_bit_exact(B, N, dim, L, skew, mode, per_layer):
+    """Long segments (>= 64 messages on one target) leave the warp walker for the CTA-pipelined
+    hub walker (TMA ring + mbarriers): giant (>= 2048) and regular hubs, rows whose column
+    slices straddle the layer boundary (d=210 -> 216-float rows, 648-float span, 6 slices),
+    both the snapshot + all-layer launch and the per-layer launches, eager and lazy decay.
+    Equal timestamps make w == 1, so everything must equal the oracle bit for bit."""
+    lib = _lib.load()
+    rng = np.random.default_rng(B + N + dim)
+    kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=2e-6, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=dim)
+    o = WalkProjectionOracle(**kw)
+    m = module_from_cfg(kw, o.P[0], mode)
+    old = lib.tpn_set_debug_flags(1 if per_layer else 0)
+    try:
+        for s, d, t in stream(rng, N, B, 5, skew, equal_times=True):
+            o.update(s, d, t)
+            m.update(s, d, t)
+        got = layers(m)
+    finally:
+        lib.tpn_set_debug_flags(old)
+    for i in range(L + 1):
+        assert np.array_equal(got[i], o.P[i]), f'layer {i}'
+    m.check_errors()
+
+
+@pytest.mark.parametrize('mode', MODES)
+def test_hub_walker_weighted_vs_oracle(mode):
+    """Same, with real timestamps (weights != 1): rtol 1e-5 against the oracle."""
+    rng = np.random.default_rng(77)
+    N, B, dim, L = 500, 8000, 210, 3
+    kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=1e-5, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=dim)
+    o = WalkProjectionOracle(**kw)
+    m = module_from_cfg(kw, o.P[0], mode)
+    for s, d, t in stream(rng, N, B, 4, 1.25):
+        o.update(s, d, t)
+        m.update(s, d, t)
+    got = layers(m)
+    for i in range(1, L + 1):
+        scale = np.abs(o.P[i]).max()
+        np.testing.assert_allclose(got[i], o.P[i], rtol=1e-5, atol=1e-6 * max(scale, 1.0))
+
+
 @pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('B,N,dim,L,lam', [(200, 1000, 120, 2, 1e-6), (5000, 3000, 140, 3, 1e-5),
                                            (200, 64, 210, 3, 1e-4)])

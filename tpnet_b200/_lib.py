@@ -19,7 +19,7 @@ TPN_ERR_LOG_FULL = -3
 TPN_ERR_INDEX = -6
 STAGE_RAW, STAGE_ID_WRAP, STAGE_ID = 0, 1, 2
 TPN_MAX_LAYERS = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 #: every symbol include/tpnet_b200.h declares (tests assert the .so exports all of them)
 EXPORTED_SYMBOLS = (
@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     'tpn_update_workspace_bytes', 'tpn_update', 'tpn_pairwise', 'tpn_gather',
     'tpn_materialize', 'tpn_reset_epoch', 'tpn_clear_walk_layers',
     'tpn_stager_create', 'tpn_stager_destroy', 'tpn_stage',
-    'tpn_update_messages', 'tpn_gather_blocks',
+    'tpn_update_messages', 'tpn_gather_blocks', 'tpn_set_debug_flags',
 )
 
 
@@ -71,7 +71,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.tpn_update.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_double, c_float,
                                POINTER(c_float), c_void_p, c_size_t, c_void_p, c_void_p]
     lib.tpn_update_messages.restype = c_int
-    lib.tpn_update_messages.argtypes = lib.tpn_update.argtypes
+    lib.tpn_update_messages.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,
+                                        c_float, POINTER(c_float), c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.tpn_set_debug_flags.restype = c_int
+    lib.tpn_set_debug_flags.argtypes = [c_int]
     lib.tpn_gather_blocks.restype = c_int
     lib.tpn_gather_blocks.argtypes = [POINTER(TpnState), c_void_p, c_int64, c_void_p, c_void_p]
     lib.tpn_pairwise.restype = c_int

@@ -31,20 +31,35 @@ namespace tpn {
 
 namespace {
 
+int g_debug_flags = 0;
+
 constexpr int kSmallMaxMsgs = 4096;      // 2B <= 4096 -> single-CTA sort
 constexpr int kRankMaxMsgs = 1024;       // 2B <= 1024 -> rank sort (one barrier) instead of the bitonic network
-constexpr int kSnapMaxMsgs = 65536;      // 2B <= 65536 -> snapshot + single all-layer walk launch
 constexpr int kPrepThreads = 1024;
 constexpr int kRadixThreads = 256;
 constexpr int kRadixItems = 8;
 constexpr int kRadixTile = kRadixThreads * kRadixItems;   // 2048 keys per block
 constexpr int kRadixBins = 256;
 constexpr int kWalkThreads = 256;
+// CTA-pipelined walker for long segments (hubs)
+constexpr int kHubMin = 64;              // segments at least this long leave the warp walker
+constexpr int kGiantMin = 2048;          // ... and these are scheduled first
+constexpr int kHubConsumers = 4;         // consumer warps (one per SM sub-partition), 1 float per lane
+constexpr int kHubThreads = (kHubConsumers + 1) * 32;      // + 1 producer warp
+constexpr int kHubStages = 4;            // ring stages of 32 messages
+constexpr int kHubSlotFloats = kHubConsumers * 32;         // 128 floats (512 B) per message slot
+constexpr int kHubMetaChunk = 512;       // messages of metadata staged per bulk copy
+constexpr size_t kSnapMaxBytes = (size_t)3 << 29;          // 1.5 GiB: above this the per-layer path is used
 
 struct DecayArgs {
     float c[TPN_MAX_LAYERS];
     int has_decay;
 };
+
+// Snapshot-slot encoding (sslot): sorted position of the head of the source node's own segment, or
+// kDirect: the source is not a target of this call, so its rows are not written by it and are
+// read straight from the state (received rows of a sharded state; never happens in edge mode).
+constexpr uint32_t kDirect = 0x80000000u;
 
 // Where the messages come from.  Edge mode (B > 0): message m < B has target a[m] = src and
 // source b[m] = dst, message m >= B the reverse (the two scatter_add_ of TPNet.py:93-96), both
@@ -55,6 +70,7 @@ struct MsgSource {
     const long long* b;
     const double* t;
     long long B;
+    long long direct_from;   // source rows >= this are read-only and current (received rows of a sharded state)
     __device__ __forceinline__ void get(int m, long long& tgt, long long& oth, int& widx) const {
         if (B > 0) {
             const int j = m < B ? m : (int)(m - B);
@@ -81,8 +97,17 @@ struct Workspace {
     uint32_t* sslot;   // [E] sorted position of the segment head of the p-th message's SOURCE node
     uint32_t* slen;    // [E] number of messages with the same target as the p-th sorted message
     float* snap;       // [E][(L-1)*row_stride] pre-batch rows 1..L-1 of each target (snapshot path only)
+    uint32_t* hub_giant;   // [E / kGiantMin + 2] sorted positions of the heads of giant segments
+    uint32_t* hub_reg;     // [E / kHubMin + 2]   ... of the other long segments
+    uint32_t* ctr;         // [8] 0: #giant, 1: #regular, 2..: work counters of the hub launches
+    int* svst;             // [L-1][E] pre-batch stamp of the source row of each sorted message (lazy, per-layer path)
+    bool has_snap;
     size_t bytes;
 };
+
+inline size_t snap_bytes(size_t E, int num_layer, int64_t row_stride) {
+    return sizeof(float) * E * (size_t)(num_layer - 1) * (size_t)row_stride;
+}
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -103,8 +128,12 @@ Workspace carve(void* base, int64_t batch, int num_layer, int64_t row_stride) {
     ws.hist = reinterpret_cast<uint32_t*>(take(4 * kRadixBins * (nblk + 1)));
     ws.sslot = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.slen = reinterpret_cast<uint32_t*>(take(4 * E));
-    const size_t snap_rows = E <= (size_t)kSnapMaxMsgs ? E : 0;
-    ws.snap = reinterpret_cast<float*>(take(sizeof(float) * snap_rows * (size_t)(num_layer - 1) * row_stride + 16));
+    ws.has_snap = snap_bytes(E, num_layer, row_stride) <= kSnapMaxBytes;
+    ws.snap = reinterpret_cast<float*>(take((ws.has_snap ? snap_bytes(E, num_layer, row_stride) : 0) + 16));
+    ws.hub_giant = reinterpret_cast<uint32_t*>(take(4 * (E / kGiantMin + 2)));
+    ws.hub_reg = reinterpret_cast<uint32_t*>(take(4 * (E / kHubMin + 2)));
+    ws.ctr = reinterpret_cast<uint32_t*>(take(4 * 8));
+    ws.svst = reinterpret_cast<int*>(take(4 * (E + 4) * (size_t)(num_layer > 1 ? num_layer - 1 : 1) + 16));
     ws.bytes = off;
     return ws;
 }
@@ -154,6 +183,8 @@ prep_small_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long 
     __shared__ __align__(16) unsigned long long comp[kSmallMaxMsgs];   // (target << 32 | message index)
     __shared__ float wsm[kSmallMaxMsgs];
     const int n_w = msgs.B > 0 ? (int)msgs.B : E;             // distinct weights (per edge / per message)
+    const bool message_mode = msgs.B == 0;
+    const bool lazy = decay_log != nullptr;
     if (threadIdx.x == 0 && decay_log != nullptr && decay.has_decay) {
         for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay.c[l];
     }
@@ -186,30 +217,38 @@ prep_small_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long 
             int j;
             msgs.get(m, tgt_unused, oth, j);
             const uint32_t other = (uint32_t)oth;
-            int rank = 0, slot = 0, upper = 0;
+            int rank = 0, slot = 0, upper = 0, slot_hi = 0;
             uint32_t mykey;
             if (narrow) {
                 const uint32_t mine = c32[m];
                 mykey = mine >> 10;
-                const uint32_t other_lo = other << 10, next_lo = (mykey + 1) << 10;
+                const uint32_t other_lo = other << 10, next_lo = (mykey + 1) << 10, other_hi = (other + 1) << 10;
                 const uint4* c4 = reinterpret_cast<const uint4*>(c32);
                 for (int i = 0; i < Epad / 4; ++i) {
                     const uint4 c = c4[i];                    // same address across the warp: broadcast
                     rank += (c.x < mine) + (c.y < mine) + (c.z < mine) + (c.w < mine);
                     slot += (c.x < other_lo) + (c.y < other_lo) + (c.z < other_lo) + (c.w < other_lo);
                     upper += (c.x < next_lo) + (c.y < next_lo) + (c.z < next_lo) + (c.w < next_lo);
+                    if (message_mode)
+                        slot_hi += (c.x < other_hi) + (c.y < other_hi) + (c.z < other_hi) + (c.w < other_hi);
                 }
             } else {
                 const unsigned long long mine = comp[m];
                 mykey = (uint32_t)(mine >> 32);
                 const unsigned long long other_lo = (unsigned long long)other << 32;
+                const unsigned long long other_hi = (unsigned long long)(other + 1) << 32;
                 const unsigned long long next_lo = (unsigned long long)(mykey + 1) << 32;
                 for (int i = 0; i < E; ++i) {
                     const unsigned long long c = comp[i];
                     rank += c < mine;
                     slot += c < other_lo;
                     upper += c < next_lo;
+                    slot_hi += c < other_hi;
                 }
+            }
+            if (message_mode && slot_hi == slot) {            // the source is not a target of this call
+                if (lazy && (long long)other < msgs.direct_from && err_flag != nullptr) *err_flag = 2;
+                slot = (int)kDirect;
             }
             const int lower = rank - 0;      // rank counts everything below (key, m); the head is the lower bound
             skey[rank] = mykey;
@@ -270,7 +309,12 @@ prep_small_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long 
             const int mid = (lo + hi) >> 1;
             if (comp[mid] < other_lo) lo = mid + 1; else hi = mid;
         }
-        sslot[p] = (uint32_t)lo;
+        uint32_t slot = (uint32_t)lo;
+        if (message_mode && (lo >= E || (uint32_t)(comp[lo] >> 32) != other)) {
+            if (lazy && (long long)other < msgs.direct_from && err_flag != nullptr) *err_flag = 2;
+            slot = kDirect;
+        }
+        sslot[p] = slot;
         lo = p; hi = E;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -284,11 +328,13 @@ prep_small_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long 
 __global__ void __launch_bounds__(256)
 prep_large_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long long num_nodes,
                   float* __restrict__ w, uint32_t* __restrict__ key, uint32_t* __restrict__ val,
-                  int* __restrict__ err_flag, float* decay_log, int L, long long new_epoch, DecayArgs decay) {
+                  int* __restrict__ err_flag, float* decay_log, int L, long long new_epoch, DecayArgs decay,
+                  uint32_t* __restrict__ ctr) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m == 0 && decay_log != nullptr && decay.has_decay) {
         for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay.c[l];
     }
+    if (m < 8) ctr[m] = 0;                               // hub lists and work counters of this call
     if (m >= E) return;
     long long tgt, oth;
     int widx;
@@ -409,7 +455,9 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
 __global__ void __launch_bounds__(256)
 payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ skey, MsgSource msgs,
                const float* __restrict__ w, int E, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
-               uint32_t* __restrict__ sslot, uint32_t* __restrict__ slen) {
+               uint32_t* __restrict__ sslot, uint32_t* __restrict__ slen, uint32_t* __restrict__ hub_giant,
+               uint32_t* __restrict__ hub_reg, uint32_t* __restrict__ ctr, int* __restrict__ svst,
+               const int* __restrict__ stamps, int L, int E4, long long num_nodes, int* __restrict__ err_flag) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= E) return;
     const uint32_t m = order[p];
@@ -426,7 +474,12 @@ payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ 
             const int mid = (lo + hi) >> 1;
             if (skey[mid] < other) lo = mid + 1; else hi = mid;
         }
-        sslot[p] = (uint32_t)lo;
+        uint32_t slot = (uint32_t)lo;
+        if (msgs.B == 0 && (lo >= E || skey[lo] != other)) {      // message mode: not a target of this call
+            if (stamps != nullptr && (long long)other < msgs.direct_from && err_flag != nullptr) *err_flag = 2;
+            slot = kDirect;
+        }
+        sslot[p] = slot;
     }
     uint32_t len = 0;
     if (p == 0 || skey[p - 1] != mykey) {     // heads only: end of the segment by binary search
@@ -436,8 +489,18 @@ payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ 
             if (skey[mid] <= mykey) lo = mid + 1; else hi = mid;
         }
         len = (uint32_t)(lo - p);
+        // long segments go to the CTA-pipelined walker; integer atomics only (the list order
+        // decides scheduling, never results)
+        if (len >= (uint32_t)kHubMin && (long long)mykey < num_nodes) {
+            if (len >= (uint32_t)kGiantMin) hub_giant[atomicAdd(&ctr[0], 1u)] = (uint32_t)p;
+            else hub_reg[atomicAdd(&ctr[1], 1u)] = (uint32_t)p;
+        }
     }
     slen[p] = len;
+    if (svst != nullptr) {           // lazy per-layer path: pre-batch stamps of the source rows 1..L-1
+        for (int l = 0; l < L - 1; ++l)
+            svst[(size_t)l * E4 + p] = (long long)other < num_nodes ? stamps[(long long)other * L + l] : -1;
+    }
 }
 
 // ---------------------------------------------------------------- eager decay sweep (large path)
@@ -464,7 +527,7 @@ template <int V, int D, bool LAZY, bool ALL>
 __global__ void __launch_bounds__(kWalkThreads)
 walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ssrc,
             const float* __restrict__ sw, const uint32_t* __restrict__ sslot, const uint32_t* __restrict__ slen,
-            const float* __restrict__ snap, int E, int ds4, int write_stamp) {
+            const float* __restrict__ snap, int E, int ds4, int write_stamp, int hub_min, DecayArgs dnow) {
     const int wid = (blockIdx.x * kWalkThreads + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= E) return;
@@ -472,6 +535,7 @@ walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const ui
     const uint32_t prev = wid > 0 ? skey[wid - 1] : 0xffffffffu;
     const int len = (int)slen[wid];
     if ((long long)key >= st.num_nodes || prev == key) return;   // dropped edge / not a segment head
+    if (len >= hub_min) return;                                  // handled by walk_hub_kernel
     const int L = st.num_layer;
     const int span4 = ALL ? L * ds4 : ds4;               // float4 in the target span
     const int snap4 = (L - 1) * ds4;                     // float4 per snapshot slot
@@ -520,13 +584,20 @@ walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const ui
                 vstamp[j] = (!ALL && LAZY) ? __shfl_sync(0xffffffffu, my_vstamp, sl) : 0;
                 const float* sstate = st.data + (long long)v * st.node_stride +
                                       (long long)(ALL ? 0 : layer - 1) * st.row_stride;
-                const float* ssnap = ALL ? snap + (long long)slot * snap4 * 4 : nullptr;
+                const bool direct = ALL && (slot & kDirect) != 0;     // rows 0..L-1 straight from the state
+                const float* ssnap = ALL ? snap + (long long)(slot & ~kDirect) * snap4 * 4 : nullptr;
 #pragma unroll
                 for (int k = 0; k < V; ++k) {
                     const int c = col0 + k * 32;
                     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (jj < nmsg && c < span4) {
-                        if (ALL) val = c < ds4 ? ld4(sstate + 4 * (long long)c) : ld4(ssnap + 4 * (long long)(c - ds4));
+                        if (ALL) {
+                            val = (c < ds4 || direct) ? ld4(sstate + 4 * (long long)c)
+                                                      : ld4(ssnap + 4 * (long long)(c - ds4));
+                            // received rows are current as of the epoch before this call: apply
+                            // this call's decay (lazy mode; the eager sweep already covered them)
+                            if (LAZY && direct && c >= ds4 && dnow.has_decay) scale4(val, dnow.c[c / ds4 - 1]);
+                        }
                         else if (vstamp[j] >= 0) val = ld4(sstate + 4 * (long long)c);
                     }
                     x[j][k] = val;
@@ -592,17 +663,253 @@ stamp_targets_kernel(StateView st, int layer, const uint32_t* __restrict__ skey,
     }
 }
 
+
+// ---------------------------------------------------------------- long segments (hubs)
+// A target's messages must be added one at a time in order (the reference's accumulation order
+// is observable), so a hub of m messages is a dependent chain of m fp32 adds per column.  The
+// warp walker above pays a DRAM round trip per D rows on that chain; here the chain runs out of
+// shared memory instead.  Work item = (long segment, column slice of <= 128 floats), one CTA:
+//   producer warp : stages the segment's metadata (source id, weight, snapshot slot / source
+//                   stamp) in chunks of 512 messages with bulk copies, then every lane issues the
+//                   `cp.async.bulk` (TMA) copy of one message's source-row slice into a ring of
+//                   4 stages x 32 messages (completion on the stage's `full` mbarrier);
+//   4 consumer warps : one float column per lane; per message LDS + FMUL + FADD with the add
+//                   chain as the only dependency (~4 cycles per message), `empty` mbarrier back.
+// CTAs pull work items from an atomic counter, giant segments first.  Same arithmetic as the
+// warp walker: acc = fadd_rn(acc, fmul_rn(source, w)) in sorted-message order.
+struct HubSmem {
+    float ring[kHubStages][32][kHubSlotFloats];
+    float wring[kHubStages][32];
+    int vring[kHubStages][32];
+    uint32_t msrc[2][kHubMetaChunk + 4];
+    float mw[2][kHubMetaChunk + 4];
+    uint32_t mx[2][kHubMetaChunk + 4];
+    uint64_t full[kHubStages];
+    uint64_t empty[kHubStages];
+    uint64_t mfull[2];
+    int item[4];
+};
+
+template <bool LAZY, bool ALL>
+__global__ void __launch_bounds__(kHubThreads)
+walk_hub_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ssrc,
+                const float* __restrict__ sw, const uint32_t* __restrict__ xarr, const uint32_t* __restrict__ slen,
+                const float* __restrict__ snap, const uint32_t* __restrict__ hub_giant,
+                const uint32_t* __restrict__ hub_reg, uint32_t* __restrict__ ctr, int work_ctr, int span,
+                int slice_w, int slices, DecayArgs dnow) {
+    extern __shared__ __align__(128) unsigned char hub_raw[];
+    HubSmem& sm = *reinterpret_cast<HubSmem*>(hub_raw);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int L = st.num_layer;
+    const int rs = (int)st.row_stride;
+    const bool has_x = ALL || (LAZY && layer >= 2);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kHubStages; ++i) {
+            mbar_init(&sm.full[i], 1);
+            mbar_init(&sm.empty[i], kHubConsumers);
+        }
+        mbar_init(&sm.mfull[0], 1);
+        mbar_init(&sm.mfull[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t n_giant = ctr[0], n_reg = ctr[1];
+    const uint32_t total = (n_giant + n_reg) * (uint32_t)slices;
+    uint32_t blk = 0;       // ring blocks produced / consumed so far by this CTA (same count in every warp)
+    uint32_t mit = 0;       // metadata chunks staged so far (producer warp)
+    for (;;) {
+        if (threadIdx.x == 0) sm.item[0] = (int)atomicAdd(&ctr[work_ctr], 1u);
+        __syncthreads();
+        const uint32_t work = (uint32_t)sm.item[0];
+        __syncthreads();
+        if (work >= total) break;
+        const uint32_t it = work / (uint32_t)slices;
+        const int slice = (int)(work - it * (uint32_t)slices);
+        const int head = (int)(it < n_giant ? hub_giant[it] : hub_reg[it - n_giant]);
+        const int len = (int)slen[head];
+        const uint32_t key = skey[head];
+        const int c0 = slice * slice_w;
+        const int c1 = min(span, c0 + slice_w);
+        const uint32_t msg_bytes = (uint32_t)(c1 - c0) * 4u;
+
+        if (warp == kHubConsumers) {
+            // ------------------------------------------------ producer
+            const int nchunk = (len + kHubMetaChunk - 1) / kHubMetaChunk;
+            auto issue_meta = [&](int c, uint32_t m) {
+                const int cs = c * kHubMetaChunk;
+                const int cn = min(kHubMetaChunk, len - cs);
+                const int a0 = (head + cs) & ~3;                         // 16-byte aligned start
+                const uint32_t bytes = (uint32_t)(((head + cs + cn) - a0 + 3) & ~3) * 4u;
+                const int buf = (int)(m & 1u);
+                fence_proxy_async_smem();
+                mbar_expect_tx(&sm.mfull[buf], bytes * (has_x ? 3u : 2u));
+                bulk_g2s(sm.msrc[buf], ssrc + a0, bytes, &sm.mfull[buf]);
+                bulk_g2s(sm.mw[buf], sw + a0, bytes, &sm.mfull[buf]);
+                if (has_x) bulk_g2s(sm.mx[buf], xarr + a0, bytes, &sm.mfull[buf]);
+            };
+            if (lane == 0) issue_meta(0, mit);
+            for (int c = 0; c < nchunk; ++c) {
+                __syncwarp();
+                if (c + 1 < nchunk && lane == 0) issue_meta(c + 1, mit + 1);
+                const int buf = (int)(mit & 1u);
+                mbar_wait(&sm.mfull[buf], (mit >> 1) & 1u);
+                const int cs = c * kHubMetaChunk;
+                const int cn = min(kHubMetaChunk, len - cs);
+                const int off = (head + cs) & 3;
+                for (int b = 0; b < cn; b += 32) {
+                    const int stage = (int)(blk % kHubStages);
+                    if (blk >= (uint32_t)kHubStages) mbar_wait(&sm.empty[stage], ((blk / kHubStages) - 1u) & 1u);
+                    const int j = b + lane;
+                    const bool valid = j < cn;
+                    uint32_t v = 0, x = 0;
+                    if (valid) {
+                        v = sm.msrc[buf][off + j];
+                        sm.wring[stage][lane] = sm.mw[buf][off + j];
+                        if (has_x) x = sm.mx[buf][off + j];
+                        sm.vring[stage][lane] = (int)x;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_expect_tx(&sm.full[stage], (uint32_t)min(32, cn - b) * msg_bytes);
+                    __syncwarp();
+                    if (valid) {
+                        float* dst = &sm.ring[stage][lane][0];
+                        const float* vrow = st.data + (long long)v * st.node_stride;
+                        if (ALL && (x & kDirect) != 0) {
+                            // not a target of this call: rows 0..L-1 are contiguous in the state
+                            bulk_g2s(dst, vrow + c0, msg_bytes, &sm.full[stage]);
+                        } else if (ALL) {
+                            // span columns < row_stride: P_0 of the source (never written);
+                            // the rest: pre-batch rows 1..L-1 from the source's snapshot slot
+                            const int a_end = min(c1, rs);
+                            if (c0 < a_end) bulk_g2s(dst, vrow + c0, (uint32_t)(a_end - c0) * 4u, &sm.full[stage]);
+                            if (c1 > rs) {
+                                const int b0 = max(c0, rs);
+                                bulk_g2s(dst + (b0 - c0), snap + (long long)x * (long long)(L - 1) * rs + (b0 - rs),
+                                         (uint32_t)(c1 - b0) * 4u, &sm.full[stage]);
+                            }
+                        } else {
+                            bulk_g2s(dst, vrow + (long long)(layer - 1) * rs + c0, msg_bytes, &sm.full[stage]);
+                        }
+                    }
+                    ++blk;
+                }
+                ++mit;
+            }
+        } else {
+            // ------------------------------------------------ consumers
+            const int col = c0 + warp * 32 + lane;
+            const bool active = col < c1;
+            const int li = ALL ? (active ? col / rs : 0) : layer - 1;
+            // direct (received) source rows: this call's decay factor of the source row this
+            // column reads (span column -> source row li; P_0 never decays; 1.0f is exact)
+            const float dfac = (ALL && LAZY && dnow.has_decay && li >= 1) ? dnow.c[li - 1] : 1.0f;
+            float* tptr = st.data + (long long)key * st.node_stride + (long long)(ALL ? 1 : layer) * rs + col;
+            float acc = 0.f;
+            if (active) {
+                long long ts = 0;
+                if (LAZY) ts = st.stamps[(long long)key * L + li];
+                if (ts >= 0) {
+                    acc = *tptr;
+                    if (LAZY)
+                        for (long long e = ts + 1; e <= st.epoch; ++e) acc = __fmul_rn(acc, __ldg(st.decay_log + e * L + li));
+                }
+            }
+            const int nblk = (len + 31) >> 5;
+            for (int b = 0; b < nblk; ++b) {
+                const int stage = (int)(blk % kHubStages);
+                mbar_wait(&sm.full[stage], (blk / kHubStages) & 1u);
+                const int nm = min(32, len - b * 32);
+                const float* xs = &sm.ring[stage][0][warp * 32 + lane];
+                const float* ws_ = &sm.wring[stage][0];
+                const int* vs = &sm.vring[stage][0];
+                if (nm == 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = xs[j * kHubSlotFloats];
+                        if (ALL && LAZY) {
+                            if ((uint32_t)vs[j] & kDirect) x = __fmul_rn(x, dfac);
+                        }
+                        if (LAZY && !ALL && layer >= 2) {
+                            const int vst = vs[j];
+                            if (vst < 0) x = 0.f;
+                            else for (long long e = (long long)vst + 1; e <= st.epoch; ++e)
+                                x = __fmul_rn(x, __ldg(st.decay_log + e * L + (layer - 2)));
+                        }
+                        acc = __fadd_rn(acc, __fmul_rn(x, ws_[j]));
+                    }
+                } else {
+                    for (int j = 0; j < nm; ++j) {
+                        float x = xs[j * kHubSlotFloats];
+                        if (ALL && LAZY) {
+                            if ((uint32_t)vs[j] & kDirect) x = __fmul_rn(x, dfac);
+                        }
+                        if (LAZY && !ALL && layer >= 2) {
+                            const int vst = vs[j];
+                            if (vst < 0) x = 0.f;
+                            else for (long long e = (long long)vst + 1; e <= st.epoch; ++e)
+                                x = __fmul_rn(x, __ldg(st.decay_log + e * L + (layer - 2)));
+                        }
+                        acc = __fadd_rn(acc, __fmul_rn(x, ws_[j]));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[stage]);
+                ++blk;
+            }
+            if (active) *tptr = acc;
+        }
+    }
+}
+
+template <bool ALL>
+int launch_walk_hub(const StateView& v, int layer, const Workspace& ws, int E4, bool lazy, const DecayArgs& dnow,
+                    cudaStream_t stream) {
+    static bool configured = false;
+    const int smem = (int)sizeof(HubSmem);
+    if (!configured) {
+        cudaError_t e = cudaSuccess;
+        e = cudaFuncSetAttribute(walk_hub_kernel<false, ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(walk_hub_kernel<true, ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_cuda_error(e);
+            return TPN_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int rs = (int)v.row_stride;
+    const int span = ALL ? v.num_layer * rs : rs;
+    const int slices = (span + kHubSlotFloats - 1) / kHubSlotFloats;
+    const int slice_w = (((span + slices - 1) / slices) + 3) & ~3;
+    const uint32_t* xarr = ALL ? ws.sslot
+                               : (lazy && layer >= 2 ? reinterpret_cast<const uint32_t*>(ws.svst) + (size_t)(layer - 2) * E4
+                                                     : nullptr);
+    const int work_ctr = 2 + (ALL ? 0 : layer - 1);
+    const unsigned grid = 148 * 2;
+    if (lazy)
+        walk_hub_kernel<true, ALL><<<grid, kHubThreads, smem, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, xarr, ws.slen,
+                                                                        ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
+                                                                        work_ctr, span, slice_w, slices, dnow);
+    else
+        walk_hub_kernel<false, ALL><<<grid, kHubThreads, smem, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, xarr, ws.slen,
+                                                                         ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
+                                                                         work_ctr, span, slice_w, slices, dnow);
+    return TPN_OK;
+}
+
 template <int V, int D, bool ALL>
 void launch_walk(const StateView& v, int layer, const Workspace& ws, int E, int ds4, int tiles, bool lazy,
-                 cudaStream_t stream) {
+                 bool hubs, const DecayArgs& dnow, cudaStream_t stream) {
     dim3 grid((unsigned)(((long long)E * 32 + kWalkThreads - 1) / kWalkThreads), (unsigned)tiles);
-    const int write_stamp = (!ALL && tiles == 1) ? 1 : 0;
+    const int write_stamp = (!ALL && tiles == 1 && !hubs) ? 1 : 0;
+    const int hub_min = hubs ? kHubMin : 0x7fffffff;
     if (lazy)
         walk_kernel<V, D, true, ALL><<<grid, kWalkThreads, 0, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
-                                                                        ws.slen, ws.snap, E, ds4, write_stamp);
+                                                                        ws.slen, ws.snap, E, ds4, write_stamp, hub_min, dnow);
     else
         walk_kernel<V, D, false, ALL><<<grid, kWalkThreads, 0, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
-                                                                         ws.slen, ws.snap, E, ds4, write_stamp);
+                                                                         ws.slen, ws.snap, E, ds4, write_stamp, hub_min, dnow);
 }
 
 }  // namespace
@@ -645,9 +952,13 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
     const int ds4 = (int)(st->row_stride / 4);
     const float t_last_f = (float)t_last;
     float* log_w = lazy ? st->decay_log : nullptr;
-    // message mode (sharded): a source need not be a local target, so the snapshot trick
-    // ("every source is also a target") does not apply — use the per-layer walk
-    const bool snapshot_path = msgs.B > 0 && E <= kSnapMaxMsgs;
+    // Snapshot + single all-layer launch whenever the snapshot fits.  Edge mode: every source is
+    // also a target, so every source has a snapshot slot.  Message mode (sharded): sources that
+    // are not targets of this call (received rows) are read straight from the state (kDirect).
+    const bool force_per_layer = (g_debug_flags & TPN_DEBUG_PER_LAYER_WALK) != 0;      // test hook
+    const bool snapshot_path = ws.has_snap && !(force_per_layer && E > kSmallMaxMsgs);
+    const bool hubs = E > kSmallMaxMsgs;            // the single-CTA sort path keeps everything in the warp walker
+    const int E4 = (E + 3) & ~3;                    // layer stride of svst (keeps bulk copies 16-byte aligned)
     const bool eager_sweep = !lazy && dargs.has_decay;
     const long long sweep_total4 = st->num_nodes * (long long)L * ds4;
 
@@ -669,7 +980,8 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
     } else {
         prep_large_kernel<<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(msgs, E, t_last_f, neg_lambda,
                                                                           st->num_nodes, ws.w, ws.key_a, ws.val_a,
-                                                                          err_flag_dev, log_w, L, new_epoch, dargs);
+                                                                          err_flag_dev, log_w, L, new_epoch, dargs,
+                                                                          ws.ctr);
         int bits = 0;
         while ((1ll << bits) <= st->num_nodes) ++bits;    // keys are in [0, num_nodes] (num_nodes = dropped)
         const int passes = (bits + 7) / 8;
@@ -686,7 +998,10 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
             cudaMemcpyAsync(ws.key_a, kin, sizeof(uint32_t) * E, cudaMemcpyDeviceToDevice, stream);
         }
         payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(vin, ws.key_a, msgs, ws.w, E, ws.ssrc, ws.sw,
-                                                            snapshot_path ? ws.sslot : nullptr, ws.slen);
+                                                            snapshot_path ? ws.sslot : nullptr, ws.slen, ws.hub_giant,
+                                                            ws.hub_reg, ws.ctr,
+                                                            (lazy && !snapshot_path && L >= 2) ? ws.svst : nullptr,
+                                                            st->stamps, L, E4, st->num_nodes, err_flag_dev);
         if (eager_sweep) {
             const long long want = (sweep_total4 + 255) / 256;
             const unsigned grid = (unsigned)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
@@ -702,7 +1017,11 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
         }
         // one float4 per lane: a warp covers 512 contiguous bytes of the L*row_stride span
         const int span4 = L * ds4;
-        launch_walk<1, 16, true>(view, 0, ws, E, ds4, (span4 + 31) / 32, lazy, stream);
+        if (hubs) {
+            const int hrc = launch_walk_hub<true>(view, 0, ws, E4, lazy, dargs, stream);
+            if (hrc != TPN_OK) return hrc;
+        }
+        launch_walk<1, 16, true>(view, 0, ws, E, ds4, (span4 + 31) / 32, lazy, hubs, dargs, stream);
         if (lazy) stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, 0, ws.key_a, E);
     } else {
         // per-layer walk: V float4 per lane so that one tile covers rows up to 512 floats
@@ -713,13 +1032,17 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
             vpl = 4;
         }
         for (int layer = L; layer >= 1; --layer) {
-            switch (vpl) {
-                case 1: launch_walk<1, 16, false>(view, layer, ws, E, ds4, tiles, lazy, stream); break;
-                case 2: launch_walk<2, 8, false>(view, layer, ws, E, ds4, tiles, lazy, stream); break;
-                case 3: launch_walk<3, 4, false>(view, layer, ws, E, ds4, tiles, lazy, stream); break;
-                default: launch_walk<4, 4, false>(view, layer, ws, E, ds4, tiles, lazy, stream); break;
+            if (hubs) {
+                const int hrc = launch_walk_hub<false>(view, layer, ws, E4, lazy, dargs, stream);
+                if (hrc != TPN_OK) return hrc;
             }
-            if (lazy && tiles > 1)
+            switch (vpl) {
+                case 1: launch_walk<1, 16, false>(view, layer, ws, E, ds4, tiles, lazy, hubs, dargs, stream); break;
+                case 2: launch_walk<2, 8, false>(view, layer, ws, E, ds4, tiles, lazy, hubs, dargs, stream); break;
+                case 3: launch_walk<3, 4, false>(view, layer, ws, E, ds4, tiles, lazy, hubs, dargs, stream); break;
+                default: launch_walk<4, 4, false>(view, layer, ws, E, ds4, tiles, lazy, hubs, dargs, stream); break;
+            }
+            if (lazy && (tiles > 1 || hubs))
                 stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, layer, ws.key_a, E);
         }
     }
@@ -728,6 +1051,12 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
 
 }  // namespace
 }  // namespace tpn
+
+extern "C" int tpn_set_debug_flags(int flags) {
+    const int old = tpn::g_debug_flags;
+    tpn::g_debug_flags = flags;
+    return old;
+}
 
 extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t* dst_dev, const double* t_dev,
                           int64_t batch, double t_last, float neg_lambda, const float* decay, void* ws_dev,
@@ -743,25 +1072,28 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
     msgs.b = reinterpret_cast<const long long*>(dst_dev);
     msgs.t = t_dev;
     msgs.B = batch;
+    msgs.direct_from = st->num_nodes;
     return update_impl(st, msgs, (int)(2 * batch), batch, t_last, neg_lambda, decay, ws_dev, ws_bytes, err_flag_dev,
                        reinterpret_cast<cudaStream_t>(stream_v));
 }
 
 extern "C" int tpn_update_messages(tpn_state_t* st, const int64_t* tgt_dev, const int64_t* src_dev,
-                                   const double* t_dev, int64_t num_messages, double t_last, float neg_lambda,
-                                   const float* decay, void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev,
-                                   void* stream_v) {
+                                   const double* t_dev, int64_t num_messages, int64_t num_local_rows,
+                                   double t_last, float neg_lambda, const float* decay, void* ws_dev,
+                                   size_t ws_bytes, int32_t* err_flag_dev, void* stream_v) {
     using namespace tpn;
     int rc = validate_state(st);
     if (rc != TPN_OK) return rc;
     if (num_messages < 1 || num_messages > ((int64_t)1 << 27) || tgt_dev == nullptr || src_dev == nullptr ||
-        t_dev == nullptr || ws_dev == nullptr || st->num_nodes >= (int64_t)0xffffffffll)
+        t_dev == nullptr || ws_dev == nullptr || st->num_nodes >= (int64_t)0x7fffffffll || num_local_rows < 0 ||
+        num_local_rows > st->num_nodes)
         return TPN_ERR_INVALID_ARGUMENT;
     MsgSource msgs;
     msgs.a = reinterpret_cast<const long long*>(tgt_dev);
     msgs.b = reinterpret_cast<const long long*>(src_dev);
     msgs.t = t_dev;
     msgs.B = 0;
+    msgs.direct_from = num_local_rows;
     return update_impl(st, msgs, (int)num_messages, (num_messages + 1) / 2, t_last, neg_lambda, decay, ws_dev,
                        ws_bytes, err_flag_dev, reinterpret_cast<cudaStream_t>(stream_v));
 }

@@ -433,6 +433,10 @@ class RandomProjectionModule(nn.Module):
 
     def check_errors(self) -> None:
         """Synchronises and raises IndexError if a device-resident id was out of range."""
-        if self._err is not None and int(self._err.item()) != 0:
+        code = int(self._err.item()) if self._err is not None else 0
+        if code != 0:
             self._err.zero_()
+            if code == 2:
+                raise RuntimeError('tpn_update_messages: a local source row was not a target of the same call '
+                                   '(lazy decay needs both directions of every edge in the message list)')
             raise IndexError(f'node id out of range for node_num {self.node_num} in a device-resident batch')

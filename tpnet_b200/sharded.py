@@ -12,8 +12,9 @@ power-law hubs).  The edge batch is replicated on every rank (24 B/edge).  Per c
   3. ONE ``all_to_all_single`` (NCCL over NVLink/NVSwitch; gloo in the CPU tests) delivers the
      blocks straight into the extension rows that follow the local rows of the state buffer,
      so the kernels address local and received rows uniformly;
-  4. the local kernels run: ``tpn_update_messages`` (per-layer, top-down, same per-row
-     accumulation order as a single GPU, hence bit-identical results) or ``tpn_pairwise``.
+  4. the local kernels run: ``tpn_update_messages`` (pre-batch snapshot of the local targets +
+     one all-layer walk launch; received rows are read in place; same per-row accumulation
+     order as a single GPU, hence bit-identical results) or ``tpn_pairwise``.
 
 Only the exchange is a collective; everything else is rank-local.  The plan is computed on
 the host with numpy from the replicated batch (it can be precomputed for a resident batch).
@@ -233,7 +234,7 @@ class ShardedRandomProjection(RandomProjectionModule):
                 self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
             if self._err is None:
                 self._err = torch.zeros(1, dtype=torch.int32, device=dev)
-            args = (ptrs[0], ptrs[1], ptrs[2], M, next_time, float(np.float32(-lam)), factors,
+            args = (ptrs[0], ptrs[1], ptrs[2], M, self.n_local, next_time, float(np.float32(-lam)), factors,
                     self._ws.data_ptr(), self._ws.numel(), self._err.data_ptr(), self._stream())
             rc = lib.tpn_update_messages(st, *args)
             if rc == _lib.TPN_ERR_LOG_FULL:
