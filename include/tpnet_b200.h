@@ -33,15 +33,19 @@
  *
  * Time decay (TPNet.py:83-85).  The reference multiplies every row of layers
  * 1..L by the fp32 scalar c_l = f32(exp(-lambda*dt)^l) at EVERY update.  Two
- * bit-identical realisations:
- *   eager : stamps == NULL.  tpn_update sweeps the whole state once per call.
- *   lazy  : stamps != NULL.  tpn_update appends (c_1..c_L) to `decay_log` as a
- *           new epoch and touches only the rows of the batch.  A row stored at
- *           epoch s is brought current by replaying, in order, the logged fp32
- *           factors of epochs s+1..epoch — the same rounded multiply chain the
- *           reference executed eagerly, so results are bit-identical, with no
- *           N-proportional traffic.  Every reader (update / pairwise / gather)
- *           replays on the fly; tpn_materialize writes all rows back current.
+ * realisations:
+ *   eager : stamps == NULL.  tpn_update sweeps the whole state once per call:
+ *           the reference's own multiply chain, bit for bit.
+ *   lazy  : stamps != NULL (the per-node rescale of large graphs).  tpn_update
+ *           appends one epoch to `decay_log` and touches only the rows of the
+ *           batch.  Row e of the log holds the f64 cumulative products
+ *           Q_l[e] = c_l(1)*...*c_l(e) of the fp32 factors (row 0 = 1.0).  A row
+ *           last written at epoch s is brought current with ONE multiply by
+ *           f32(Q[epoch]/Q[s]) — the product of exactly the factors the
+ *           reference applied, rounded once instead of once per update
+ *           (relative difference <= (epoch-s+1)*2^-24; identical for epoch-s <= 1).
+ *           No N-proportional traffic.  Every reader (update / pairwise / gather)
+ *           rescales on the fly; tpn_materialize writes all rows back current.
  */
 #ifndef TPNET_B200_H_
 #define TPNET_B200_H_
@@ -53,7 +57,7 @@
 extern "C" {
 #endif
 
-#define TPN_ABI_VERSION 2
+#define TPN_ABI_VERSION 3
 
 #define TPN_MAX_LAYERS 4
 
@@ -61,7 +65,7 @@ enum {
     TPN_OK = 0,
     TPN_ERR_INVALID_ARGUMENT = -1,   /* null pointer, bad shape, misaligned stride            */
     TPN_ERR_WORKSPACE_TOO_SMALL = -2,
-    TPN_ERR_LOG_FULL = -3,           /* lazy mode: decay_log has no free epoch (materialise)   */
+    TPN_ERR_LOG_FULL = -3,           /* lazy mode: decay_log full or products near underflow    */
     TPN_ERR_CUDA = -4,               /* a CUDA runtime call failed; see tpn_last_cuda_error()   */
     TPN_ERR_UNSUPPORTED = -5,        /* num_layer outside 1..TPN_MAX_LAYERS                     */
     TPN_ERR_INDEX = -6               /* tpn_stage: a node id is out of range                    */
@@ -77,9 +81,13 @@ typedef struct tpn_state {
     int64_t  row_stride;    /* floats, multiple of 4, >= dim                                   */
     int64_t  node_stride;   /* floats, multiple of 4, >= (L+1)*row_stride                      */
     int32_t* stamps;        /* device, [num_nodes][L] epoch of last write of layer 1..L; NULL = eager */
-    float*   decay_log;     /* device, [log_capacity][L]; row e = factors applied entering epoch e */
-    int64_t  log_capacity;  /* rows in decay_log (row 0 unused)                                */
+    double*  decay_log;     /* device, [log_capacity][L] f64; row e = cumulative product of the
+                               fp32 factors of epochs 1..e; row 0 MUST be 1.0 (caller-initialised) */
+    int64_t  log_capacity;  /* rows in decay_log                                               */
     int64_t  epoch;         /* current epoch (0 = nothing logged); advanced by tpn_update      */
+    double   cum_floor;     /* host mirror: smallest cumulative product in the log (1.0 at epoch 0);
+                               maintained by tpn_update / tpn_reset_epoch / tpn_clear_walk_layers.
+                               tpn_update returns TPN_ERR_LOG_FULL before it could underflow.   */
 } tpn_state_t;
 
 int tpn_version(void);
@@ -163,7 +171,7 @@ int tpn_pairwise(const tpn_state_t* st, const int64_t* a_ids_dev, const int64_t*
 int tpn_gather(const tpn_state_t* st, const int64_t* ids_dev, int64_t n, float* out_dev, void* stream);
 
 /*
- * Lazy mode only: replay the pending decay of EVERY row, write it back and set
+ * Lazy mode only: apply the pending decay of EVERY row, write it back and set
  * all stamps to the current epoch (used before backup / state_dict / when the
  * log is full; afterwards the caller may reset epoch to 0 with tpn_reset_epoch).
  * No-op in eager mode.

@@ -61,7 +61,12 @@ def main():
             if rank == 0:
                 ref.materialize()
                 for i in range(L + 1):
-                    same = torch.equal(full[i], ref.random_projections[i].data)
+                    want_i = ref.random_projections[i].data
+                    if mode == 'eager':
+                        same = torch.equal(full[i], want_i)
+                    else:       # lazy: a received row is rescaled by the sender and again by this call's
+                        # factor (two roundings), the single-GPU run rescales once: rtol 1e-5
+                        same = torch.allclose(full[i], want_i, rtol=1e-5, atol=1e-6 * max(float(want_i.abs().max()), 1.0))
                     ok &= same
                     if not same:
                         err = (full[i] - ref.random_projections[i].data).abs().max().item()

@@ -41,8 +41,8 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # int64-aligned POD: 8+8+4+4+8+8+8+8+8+8 bytes
-    assert ctypes.sizeof(_lib.TpnState) == 72
+    # int64-aligned POD: 8+8+4+4+8+8+8+8+8+8+8 bytes
+    assert ctypes.sizeof(_lib.TpnState) == 80
 
 
 def test_argument_validation_without_gpu():

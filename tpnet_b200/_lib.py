@@ -19,7 +19,7 @@ TPN_ERR_LOG_FULL = -3
 TPN_ERR_INDEX = -6
 STAGE_RAW, STAGE_ID_WRAP, STAGE_ID = 0, 1, 2
 TPN_MAX_LAYERS = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 #: every symbol include/tpnet_b200.h declares (tests assert the .so exports all of them)
 EXPORTED_SYMBOLS = (
@@ -44,6 +44,7 @@ class TpnState(ctypes.Structure):
         ('decay_log', c_void_p),
         ('log_capacity', c_int64),
         ('epoch', c_int64),
+        ('cum_floor', c_double),
     ]
 
 

@@ -17,8 +17,8 @@ struct StateView {
     long long row_stride;    // floats
     long long node_stride;   // floats
     int* stamps;             // nullptr => eager
-    const float* decay_log;  // [cap][L]
-    long long epoch;         // epoch readers replay up to
+    const double* decay_log; // [cap][L] cumulative products of the per-update fp32 factors (row 0 = 1.0)
+    long long epoch;         // epoch readers bring rows up to
 };
 
 inline StateView make_view(const tpn_state_t* st) {
@@ -71,17 +71,31 @@ __device__ __forceinline__ void axpy4_rn(float4& acc, const float4& x, float w) 
     acc.w = __fadd_rn(acc.w, __fmul_rn(x.w, w));
 }
 
-// Lazy decay: replay the logged fp32 factors of epochs (from, to] of layer index
-// `li` (= layer-1) on V float4 registers — the same rounded multiply chain the
-// reference applies eagerly once per update (TPNet.py:83-85).
-template <int V>
-__device__ __forceinline__ void replay(float4 (&x)[V], const float* __restrict__ log, int L, int li,
-                                       long long from, long long to) {
-    for (long long e = from + 1; e <= to; ++e) {
-        const float f = __ldg(log + e * L + li);
-#pragma unroll
-        for (int k = 0; k < V; ++k) scale4(x[k], f);
-    }
+// Lazy decay (TPNet.py:83-85 deferred).  The reference multiplies every row of layer l by the
+// fp32 scalar c_l at EVERY update.  Row e of the log holds, per layer, the f64 product
+// Q_l[e] = c_l(1) * c_l(2) * ... * c_l(e) of the fp32 factors logged so far (Q[0] = 1), so a row
+// last written at epoch `from` is brought to epoch `to` by ONE multiply with
+// f32(Q[to] / Q[from]): the product of exactly the factors the reference applied, rounded once
+// instead of once per update (|relative difference| <= (to - from + 1) * 2^-24, and exactly
+// equal when to - from <= 1).  from == to gives exactly 1.0f.
+__device__ __forceinline__ float decay_factor(const double* __restrict__ log, int L, int li, long long from,
+                                              long long to) {
+    if (from == to) return 1.0f;            // also keeps a zero product (f32 factor underflow) harmless
+    return (float)(__ldg(log + to * L + li) / __ldg(log + from * L + li));
+}
+__device__ __forceinline__ float decay_factor(const StateView& st, int li, long long from) {
+    return decay_factor(st.decay_log, st.num_layer, li, from, st.epoch);
+}
+
+// Two columns per lane: acc += fl32(x * w) per column.  The product is one packed FMUL2, the adds
+// are SCALAR on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit
+// .rn modifiers and --fmad=false (seen in SASS, CUDA 12.9), which would skip the rounding of the
+// product that the reference performs (TPNet.py:91-96).  Scalar add.rn.f32 is never contracted.
+__device__ __forceinline__ float2 mul2_rn(const float2& a, float b) { return __fmul2_rn(a, make_float2(b, b)); }
+__device__ __forceinline__ void axpy2_rn(float2& acc, const float2& x, float w) {
+    const float2 p = __fmul2_rn(x, make_float2(w, w));
+    acc.x = __fadd_rn(acc.x, p.x);
+    acc.y = __fadd_rn(acc.y, p.y);
 }
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy (TMA) wrappers
@@ -116,6 +130,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // orders prior generic-proxy accesses of shared memory before later async-proxy (bulk copy) writes
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+
+// ---------------------------------------------------------------- cp.async (LDGSTS) wrappers
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+// the mbarrier receives one arrival (pre-counted in its init count) once every cp.async this
+// thread issued so far has landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 }  // namespace tpn

@@ -17,8 +17,8 @@
 // owning NP/G finished entries, applies the epilogue to just those and mirrors them
 // through shared memory; the warp then writes its pairs' R*R outputs as coalesced
 // 128-bit streaming stores.
-// Lazy-decay mode: rows of layers >= 1 are brought current in registers (replay of the
-// logged fp32 factors) before they enter the products; nothing is written back.
+// Lazy-decay mode: rows of layers >= 1 are brought current in registers (one multiply by the
+// row's pending decay factor) before they enter the products; nothing is written back.
 #include "tpn_pairwise.cuh"
 
 namespace tpn {
@@ -54,12 +54,15 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
     const float4* pa = reinterpret_cast<const float4*>(st.data + ida * st.node_stride);
     const float4* pb = reinterpret_cast<const float4*>(st.data + idb * st.node_stride);
 
-    long long stamp[R];
+    // lazy decay: one pending factor per row (stamp < 0: the row is all zero in memory)
+    float fac[R];
     if (LAZY) {
 #pragma unroll
         for (int l = 1; l < H; ++l) {
-            stamp[l] = st.stamps[ida * LAYERS + (l - 1)];
-            stamp[H + l] = st.stamps[idb * LAYERS + (l - 1)];
+            const long long sa = st.stamps[ida * LAYERS + (l - 1)];
+            const long long sb = st.stamps[idb * LAYERS + (l - 1)];
+            fac[l] = sa >= 0 ? decay_factor(st, l - 1, sa) : 1.0f;
+            fac[H + l] = sb >= 0 ? decay_factor(st, l - 1, sb) : 1.0f;
         }
     }
 
@@ -77,17 +80,8 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
         if (LAZY) {
 #pragma unroll
             for (int l = 1; l < H; ++l) {
-                float4 one[1];
-                if (stamp[l] >= 0) {
-                    one[0] = x[l];
-                    replay<1>(one, st.decay_log, LAYERS, l - 1, stamp[l], st.epoch);
-                    x[l] = one[0];
-                }
-                if (stamp[H + l] >= 0) {
-                    one[0] = x[H + l];
-                    replay<1>(one, st.decay_log, LAYERS, l - 1, stamp[H + l], st.epoch);
-                    x[H + l] = one[0];
-                }
+                scale4(x[l], fac[l]);
+                scale4(x[H + l], fac[H + l]);
             }
         }
         gram_step<R>(acc, x);
@@ -175,12 +169,15 @@ pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const lon
             bulk_g2s(wbase + (size_t)(PPW + sub) * block_bytes, st.data + idb * st.node_stride, block_bytes, bar);
     }
 
-    long long stamp[R];
+    // lazy decay: one pending factor per row (stamp < 0: the row is all zero in memory)
+    float fac[R];
     if (LAZY) {
 #pragma unroll
         for (int l = 1; l < H; ++l) {
-            stamp[l] = st.stamps[ida * LAYERS + (l - 1)];
-            stamp[H + l] = st.stamps[idb * LAYERS + (l - 1)];
+            const long long sa = st.stamps[ida * LAYERS + (l - 1)];
+            const long long sb = st.stamps[idb * LAYERS + (l - 1)];
+            fac[l] = sa >= 0 ? decay_factor(st, l - 1, sa) : 1.0f;
+            fac[H + l] = sb >= 0 ? decay_factor(st, l - 1, sb) : 1.0f;
         }
     }
     float2 acc[NU];
@@ -201,17 +198,8 @@ pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const lon
         if (LAZY) {
 #pragma unroll
             for (int l = 1; l < H; ++l) {
-                float4 one[1];
-                if (stamp[l] >= 0) {
-                    one[0] = x[l];
-                    replay<1>(one, st.decay_log, LAYERS, l - 1, stamp[l], st.epoch);
-                    x[l] = one[0];
-                }
-                if (stamp[H + l] >= 0) {
-                    one[0] = x[H + l];
-                    replay<1>(one, st.decay_log, LAYERS, l - 1, stamp[H + l], st.epoch);
-                    x[H + l] = one[0];
-                }
+                scale4(x[l], fac[l]);
+                scale4(x[H + l], fac[H + l]);
             }
         }
         gram_step<R>(acc, x);

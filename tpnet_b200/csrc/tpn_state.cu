@@ -39,12 +39,16 @@ gather_kernel(StateView st, const long long* __restrict__ ids, long long n, floa
     const int d = st.dim;
     for (int l = 0; l <= st.num_layer; ++l) {
         long long stamp = -1;
-        if (LAZY && l >= 1) stamp = st.stamps[id * st.num_layer + (l - 1)];
+        float fac = 1.0f;
+        if (LAZY && l >= 1) {
+            stamp = st.stamps[id * st.num_layer + (l - 1)];
+            if (stamp >= 0) fac = decay_factor(st, l - 1, stamp);
+        }
         float* o = out + ((long long)l * n + i) * d;
         for (int c = lane; c < ds4; c += 32) {
             float4 x[1];
             x[0] = ld4(base + (long long)l * st.row_stride + 4 * c);
-            if (LAZY && stamp >= 0) replay<1>(x, st.decay_log, st.num_layer, l - 1, stamp, st.epoch);
+            if (LAZY && stamp >= 0) scale4(x[0], fac);
             const int k = 4 * c;
             if (k + 3 < d) {
                 o[k] = x[0].x; o[k + 1] = x[0].y; o[k + 2] = x[0].z; o[k + 3] = x[0].w;
@@ -76,7 +80,7 @@ gather_blocks_kernel(StateView st, const long long* __restrict__ ids, long long 
         x[0] = ld4(base + 4 * (long long)c);
         if (LAZY && l >= 1 && l <= st.num_layer) {
             const long long stamp = st.stamps[id * st.num_layer + (l - 1)];
-            if (stamp >= 0) replay<1>(x, st.decay_log, st.num_layer, l - 1, stamp, st.epoch);
+            if (stamp >= 0) scale4(x[0], decay_factor(st, l - 1, stamp));
         }
         st4(o + 4 * (long long)c, x[0]);
     }
@@ -93,11 +97,11 @@ __global__ void __launch_bounds__(256) materialize_kernel(StateView st, long lon
     const long long stamp = st.stamps[r];
     if (stamp < 0 || stamp == st.epoch) return;       // all-zero row, or already current
     float* row = st.data + node * st.node_stride + (long long)(li + 1) * st.row_stride;
+    const float fac = decay_factor(st, li, stamp);
     for (int c = lane; c < ds4; c += 32) {
-        float4 x[1];
-        x[0] = ld4(row + 4 * c);
-        replay<1>(x, st.decay_log, st.num_layer, li, stamp, st.epoch);
-        st4(row + 4 * c, x[0]);
+        float4 x = ld4(row + 4 * c);
+        scale4(x, fac);
+        st4(row + 4 * c, x);
     }
     __syncwarp();
     if (lane == 0) st.stamps[r] = (int)st.epoch;
@@ -224,6 +228,7 @@ extern "C" int tpn_reset_epoch(tpn_state_t* st, void* stream_v) {
     const long long rows = st->num_nodes * st->num_layer;
     restart_stamps_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(st->stamps, rows);
     st->epoch = 0;
+    st->cum_floor = 1.0;
     return check_launch();
 }
 
@@ -240,6 +245,7 @@ extern "C" int tpn_clear_walk_layers(tpn_state_t* st, void* stream_v) {
         const long long rows = st->num_nodes * st->num_layer;
         fill_int_kernel<<<capped_grid(rows, 256), 256, 0, stream>>>(st->stamps, rows, -1);
         st->epoch = 0;
+        st->cum_floor = 1.0;
     }
     return check_launch();
 }

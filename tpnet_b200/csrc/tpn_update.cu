@@ -50,6 +50,15 @@ constexpr int kHubStages = 4;            // ring stages of 32 messages
 constexpr int kHubSlotFloats = kHubConsumers * 32;         // 128 floats (512 B) per message slot
 constexpr int kHubMetaChunk = 512;       // messages of metadata staged per bulk copy
 constexpr size_t kSnapMaxBytes = (size_t)3 << 29;          // 1.5 GiB: above this the per-layer path is used
+// large batches, snapshot path: short segments -> persistent warp walker, long ones -> hub2
+constexpr int kSmallWalkThreads = 256;
+constexpr int kHub2Consumers = 1;        // consumer warps; each lane owns 2 adjacent columns (packed FMUL2/FADD2)
+constexpr int kHub2Producers = 2;        // cp.async producer warps (alternate ring stages)
+constexpr int kHub2Threads = (kHub2Consumers + kHub2Producers) * 32;
+constexpr int kHub2SlotFloats = kHub2Consumers * 64;       // floats of one message held by a ring slot
+constexpr int kHub2Stages = 8;           // ring stages of 32 messages (8 x 32 x 256 B = 64 KB)
+// ctr[] slots (zeroed by prep_large_kernel)
+constexpr int kCtrGiant = 0, kCtrHub = 1, kCtrWork0 = 2, kCtrSmall = 6, kCtrHub2Work = 7;
 
 struct DecayArgs {
     float c[TPN_MAX_LAYERS];
@@ -99,7 +108,9 @@ struct Workspace {
     float* snap;       // [E][(L-1)*row_stride] pre-batch rows 1..L-1 of each target (snapshot path only)
     uint32_t* hub_giant;   // [E / kGiantMin + 2] sorted positions of the heads of giant segments
     uint32_t* hub_reg;     // [E / kHubMin + 2]   ... of the other long segments
-    uint32_t* ctr;         // [8] 0: #giant, 1: #regular, 2..: work counters of the hub launches
+    uint32_t* ctr;         // [8] 0: #giant, 1: #regular, 2..5: work counters of the per-layer hub launches,
+                           //     6: #short segments, 7: work counter of the hub2 launch
+    uint32_t* small_heads; // [E] sorted positions of the heads of short segments (scheduling order only)
     int* svst;             // [L-1][E] pre-batch stamp of the source row of each sorted message (lazy, per-layer path)
     bool has_snap;
     size_t bytes;
@@ -133,6 +144,7 @@ Workspace carve(void* base, int64_t batch, int num_layer, int64_t row_stride) {
     ws.hub_giant = reinterpret_cast<uint32_t*>(take(4 * (E / kGiantMin + 2)));
     ws.hub_reg = reinterpret_cast<uint32_t*>(take(4 * (E / kHubMin + 2)));
     ws.ctr = reinterpret_cast<uint32_t*>(take(4 * 8));
+    ws.small_heads = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.svst = reinterpret_cast<int*>(take(4 * (E + 4) * (size_t)(num_layer > 1 ? num_layer - 1 : 1) + 16));
     ws.bytes = off;
     return ws;
@@ -174,7 +186,7 @@ __global__ void __launch_bounds__(kPrepThreads)
 prep_small_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long long num_nodes,
                   uint32_t* __restrict__ skey, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
                   uint32_t* __restrict__ sslot, uint32_t* __restrict__ slen, int* __restrict__ err_flag,
-                  float* decay_log, int L, long long new_epoch, DecayArgs decay, StateView st, SweepArgs sweep) {
+                  double* decay_log, int L, long long new_epoch, DecayArgs decay, StateView st, SweepArgs sweep) {
     if (blockIdx.x > 0) {
         sweep_body(st, decay, sweep.total4, sweep.ds4, (long long)(blockIdx.x - 1) * kPrepThreads + threadIdx.x,
                    (long long)(gridDim.x - 1) * kPrepThreads);
@@ -186,7 +198,7 @@ prep_small_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long 
     const bool message_mode = msgs.B == 0;
     const bool lazy = decay_log != nullptr;
     if (threadIdx.x == 0 && decay_log != nullptr && decay.has_decay) {
-        for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay.c[l];
+        for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay_log[(new_epoch - 1) * L + l] * (double)decay.c[l];
     }
     if (E <= kRankMaxMsgs) {
         // ---- rank sort.  Keys are packed as (target << 10 | m) in 32 bits when the node ids
@@ -328,11 +340,11 @@ prep_small_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long 
 __global__ void __launch_bounds__(256)
 prep_large_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long long num_nodes,
                   float* __restrict__ w, uint32_t* __restrict__ key, uint32_t* __restrict__ val,
-                  int* __restrict__ err_flag, float* decay_log, int L, long long new_epoch, DecayArgs decay,
+                  int* __restrict__ err_flag, double* decay_log, int L, long long new_epoch, DecayArgs decay,
                   uint32_t* __restrict__ ctr) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m == 0 && decay_log != nullptr && decay.has_decay) {
-        for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay.c[l];
+        for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay_log[(new_epoch - 1) * L + l] * (double)decay.c[l];
     }
     if (m < 8) ctr[m] = 0;                               // hub lists and work counters of this call
     if (m >= E) return;
@@ -456,50 +468,66 @@ __global__ void __launch_bounds__(256)
 payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ skey, MsgSource msgs,
                const float* __restrict__ w, int E, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
                uint32_t* __restrict__ sslot, uint32_t* __restrict__ slen, uint32_t* __restrict__ hub_giant,
-               uint32_t* __restrict__ hub_reg, uint32_t* __restrict__ ctr, int* __restrict__ svst,
-               const int* __restrict__ stamps, int L, int E4, long long num_nodes, int* __restrict__ err_flag) {
+               uint32_t* __restrict__ hub_reg, uint32_t* __restrict__ small_heads, uint32_t* __restrict__ ctr,
+               int* __restrict__ svst, const int* __restrict__ stamps, int L, int E4, long long num_nodes,
+               int* __restrict__ err_flag) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= E) return;
-    const uint32_t m = order[p];
-    long long tgt_unused, oth;
-    int j;
-    msgs.get((int)m, tgt_unused, oth, j);
-    const uint32_t other = (uint32_t)oth;
-    const uint32_t mykey = skey[p];
-    ssrc[p] = other;
-    sw[p] = w[j];
-    if (sslot != nullptr) {          // snapshot path: where the source node's own segment starts
-        int lo = 0, hi = E;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (skey[mid] < other) lo = mid + 1; else hi = mid;
+    const int lane = threadIdx.x & 31;
+    bool small_head = false;
+    if (p < E) {
+        const uint32_t m = order[p];
+        long long tgt_unused, oth;
+        int j;
+        msgs.get((int)m, tgt_unused, oth, j);
+        const uint32_t other = (uint32_t)oth;
+        const uint32_t mykey = skey[p];
+        ssrc[p] = other;
+        float wv = w[j];
+        if (sslot != nullptr) {          // snapshot path: where the source node's own segment starts
+            int lo = 0, hi = E;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (skey[mid] < other) lo = mid + 1; else hi = mid;
+            }
+            uint32_t slot = (uint32_t)lo;
+            if (msgs.B == 0 && (lo >= E || skey[lo] != other)) {      // message mode: not a target of this call
+                if (stamps != nullptr && (long long)other < msgs.direct_from && err_flag != nullptr) *err_flag = 2;
+                slot = kDirect;
+                wv = __int_as_float(__float_as_int(wv) | 0x80000000);  // weights are >= 0: the sign bit marks
+            }                                                          // a source read straight from the state
+            sslot[p] = slot;
         }
-        uint32_t slot = (uint32_t)lo;
-        if (msgs.B == 0 && (lo >= E || skey[lo] != other)) {      // message mode: not a target of this call
-            if (stamps != nullptr && (long long)other < msgs.direct_from && err_flag != nullptr) *err_flag = 2;
-            slot = kDirect;
+        sw[p] = wv;
+        uint32_t len = 0;
+        if (p == 0 || skey[p - 1] != mykey) {     // heads only: end of the segment by binary search
+            int lo = p, hi = E;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (skey[mid] <= mykey) lo = mid + 1; else hi = mid;
+            }
+            len = (uint32_t)(lo - p);
+            // long segments go to the CTA-pipelined walkers; integer atomics only (the list order
+            // decides scheduling, never results)
+            if ((long long)mykey < num_nodes) {
+                if (len >= (uint32_t)kGiantMin) hub_giant[atomicAdd(&ctr[kCtrGiant], 1u)] = (uint32_t)p;
+                else if (len >= (uint32_t)kHubMin) hub_reg[atomicAdd(&ctr[kCtrHub], 1u)] = (uint32_t)p;
+                else small_head = true;
+            }
         }
-        sslot[p] = slot;
+        slen[p] = len;
+        if (svst != nullptr) {           // lazy per-layer path: pre-batch stamps of the source rows 1..L-1
+            for (int l = 0; l < L - 1; ++l)
+                svst[(size_t)l * E4 + p] = (long long)other < num_nodes ? stamps[(long long)other * L + l] : -1;
+        }
     }
-    uint32_t len = 0;
-    if (p == 0 || skey[p - 1] != mykey) {     // heads only: end of the segment by binary search
-        int lo = p, hi = E;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (skey[mid] <= mykey) lo = mid + 1; else hi = mid;
-        }
-        len = (uint32_t)(lo - p);
-        // long segments go to the CTA-pipelined walker; integer atomics only (the list order
-        // decides scheduling, never results)
-        if (len >= (uint32_t)kHubMin && (long long)mykey < num_nodes) {
-            if (len >= (uint32_t)kGiantMin) hub_giant[atomicAdd(&ctr[0], 1u)] = (uint32_t)p;
-            else hub_reg[atomicAdd(&ctr[1], 1u)] = (uint32_t)p;
-        }
-    }
-    slen[p] = len;
-    if (svst != nullptr) {           // lazy per-layer path: pre-batch stamps of the source rows 1..L-1
-        for (int l = 0; l < L - 1; ++l)
-            svst[(size_t)l * E4 + p] = (long long)other < num_nodes ? stamps[(long long)other * L + l] : -1;
+    // compacted list of short-segment heads: one atomic per warp, order within the warp kept
+    const uint32_t mask = __ballot_sync(0xffffffffu, small_head);
+    if (mask != 0) {
+        const int leader = __ffs(mask) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&ctr[kCtrSmall], (uint32_t)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (small_head) small_heads[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)p;
     }
 }
 
@@ -550,11 +578,7 @@ walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const ui
         long long tstamp = 0;
         if (LAZY && c < span4) tstamp = st.stamps[(long long)key * L + tli];
         acc[k] = (c < span4 && tstamp >= 0) ? ld4(tbase + 4 * (long long)c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (LAZY && c < span4 && tstamp >= 0) {
-            float4 one[1] = {acc[k]};
-            replay<1>(one, st.decay_log, L, tli, tstamp, st.epoch);
-            acc[k] = one[0];
-        }
+        if (LAZY && c < span4 && tstamp >= 0) scale4(acc[k], decay_factor(st, tli, tstamp));
     }
 
     for (int base = 0; base < len; base += 32) {
@@ -606,8 +630,11 @@ walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const ui
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 if (j0 + j < nmsg) {
-                    if (!ALL && LAZY && layer >= 2 && vstamp[j] >= 0)      // P_0 never decays
-                        replay<V>(x[j], st.decay_log, L, layer - 2, vstamp[j], st.epoch);
+                    if (!ALL && LAZY && layer >= 2 && vstamp[j] >= 0) {    // P_0 never decays
+                        const float f = decay_factor(st, layer - 2, vstamp[j]);
+#pragma unroll
+                        for (int k = 0; k < V; ++k) scale4(x[j][k], f);
+                    }
 #pragma unroll
                     for (int k = 0; k < V; ++k) axpy4_rn(acc[k], x[j][k], w[j]);
                 }
@@ -641,10 +668,9 @@ snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, int E, int ds4,
         const int li = c / ds4;                         // layer - 1
         long long stamp = 0;
         if (LAZY) stamp = st.stamps[(long long)key * L + li];
-        float4 one[1];
-        one[0] = stamp >= 0 ? ld4(rows + 4 * (long long)c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (LAZY && stamp >= 0) replay<1>(one, st.decay_log, L, li, stamp, st.epoch);
-        st4(slot + 4 * (long long)c, one[0]);
+        float4 one = stamp >= 0 ? ld4(rows + 4 * (long long)c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (LAZY && stamp >= 0) scale4(one, decay_factor(st, li, stamp));
+        st4(slot + 4 * (long long)c, one);
     }
 }
 
@@ -811,8 +837,7 @@ walk_hub_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, cons
                 if (LAZY) ts = st.stamps[(long long)key * L + li];
                 if (ts >= 0) {
                     acc = *tptr;
-                    if (LAZY)
-                        for (long long e = ts + 1; e <= st.epoch; ++e) acc = __fmul_rn(acc, __ldg(st.decay_log + e * L + li));
+                    if (LAZY) acc = __fmul_rn(acc, decay_factor(st, li, ts));
                 }
             }
             const int nblk = (len + 31) >> 5;
@@ -832,9 +857,7 @@ walk_hub_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, cons
                         }
                         if (LAZY && !ALL && layer >= 2) {
                             const int vst = vs[j];
-                            if (vst < 0) x = 0.f;
-                            else for (long long e = (long long)vst + 1; e <= st.epoch; ++e)
-                                x = __fmul_rn(x, __ldg(st.decay_log + e * L + (layer - 2)));
+                            x = vst < 0 ? 0.f : __fmul_rn(x, decay_factor(st, layer - 2, vst));
                         }
                         acc = __fadd_rn(acc, __fmul_rn(x, ws_[j]));
                     }
@@ -846,9 +869,7 @@ walk_hub_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, cons
                         }
                         if (LAZY && !ALL && layer >= 2) {
                             const int vst = vs[j];
-                            if (vst < 0) x = 0.f;
-                            else for (long long e = (long long)vst + 1; e <= st.epoch; ++e)
-                                x = __fmul_rn(x, __ldg(st.decay_log + e * L + (layer - 2)));
+                            x = vst < 0 ? 0.f : __fmul_rn(x, decay_factor(st, layer - 2, vst));
                         }
                         acc = __fadd_rn(acc, __fmul_rn(x, ws_[j]));
                     }
@@ -859,6 +880,381 @@ walk_hub_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, cons
             }
             if (active) *tptr = acc;
         }
+    }
+}
+
+
+// ================================================================ large batches, snapshot path
+__device__ __forceinline__ float pick4(float f0, float f1, float f2, float f3, int i) {
+    return i == 0 ? f0 : (i == 1 ? f1 : (i == 2 ? f2 : f3));
+}
+__device__ __forceinline__ const float* shfl_ptr(const float* p, int src_lane) {
+    unsigned long long v = reinterpret_cast<unsigned long long>(p);
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src_lane);
+    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src_lane);
+    return reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
+}
+
+// Short segments (< kHubMin messages).  Persistent warps stride over the compacted head list
+// (payload_kernel); one warp owns the whole L*row_stride span of a target (V float4 per lane;
+// wider spans are tiled over blockIdx.y).  Per segment: the target span and the first D source
+// spans are requested together (one DRAM round trip), the next segment's metadata and the head
+// after that are prefetched behind them, pending decay is one multiply per register, messages
+// are added in order as fadd_rn(acc, fmul_rn(x, w)), the span is written once.  Source row 0
+// comes from the state (P_0 is never written), rows 1..L-1 from the pre-batch snapshot, or —
+// message mode, weight sign bit set — all of them straight from the state (received rows).
+template <int V, bool LAZY, bool DIRECT>
+__global__ void __launch_bounds__(kSmallWalkThreads, 2)
+walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ssrc,
+                  const float* __restrict__ sw, const uint32_t* __restrict__ sslot,
+                  const uint32_t* __restrict__ slen, const float* __restrict__ snap,
+                  const uint32_t* __restrict__ heads, const uint32_t* __restrict__ ctr, int E, int ds4,
+                  DecayArgs dnow) {
+    constexpr int D = V >= 4 ? 2 : 4;                 // source spans in flight per round
+    const int lane = threadIdx.x & 31;
+    const int warps = gridDim.x * (kSmallWalkThreads / 32);
+    int it = blockIdx.x * (kSmallWalkThreads / 32) + (threadIdx.x >> 5);
+    const int n_items = (int)ctr[kCtrSmall];
+    if (it >= n_items) return;
+    const int L = st.num_layer;
+    const int span4 = L * ds4;
+    const int snap4 = (L - 1) * ds4;
+    int col[V], tl[V];
+    bool in[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        col[k] = blockIdx.y * (32 * V) + k * 32 + lane;
+        in[k] = col[k] < span4;
+        tl[k] = in[k] ? col[k] / ds4 : 0;             // target layer - 1 == source row of this register
+    }
+    struct Meta { uint32_t key, len, v, slot; float w; };
+    auto load_meta = [&](uint32_t p) {
+        Meta m;
+        m.key = skey[p];
+        m.len = slen[p];
+        const uint32_t q = min(p + (uint32_t)lane, (uint32_t)(E - 1));     // lanes >= len read neighbours: unused
+        m.v = ssrc[q];
+        m.w = sw[q];
+        m.slot = sslot[q];
+        return m;
+    };
+    uint32_t p_cur = heads[it];
+    uint32_t p_nxt = it + warps < n_items ? heads[it + warps] : 0u;
+    Meta mc = load_meta(p_cur);
+    for (; it < n_items; it += warps) {
+        const uint32_t p_this = p_cur;
+        const uint32_t key = mc.key;
+        const int len = (int)mc.len;
+        float* tbase = st.data + (long long)key * st.node_stride + st.row_stride;      // rows 1..L
+        float4 acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k)      // rows never written hold zeros, so the load needs no stamp check
+            acc[k] = in[k] ? ld4(tbase + 4 * (long long)col[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        int stamp[TPN_MAX_LAYERS];
+        if (LAZY) {
+#pragma unroll
+            for (int l = 0; l < TPN_MAX_LAYERS; ++l) stamp[l] = l < L ? st.stamps[(long long)key * L + l] : -1;
+        }
+        uint32_t my_v = mc.v, my_slot = mc.slot;
+        float my_w = mc.w;
+        bool first = true;
+        for (int base = 0; base < len; base += 32) {
+            const int nmsg = min(32, len - base);
+            if (base > 0 && lane < nmsg) {            // second round of a 33..63-message segment
+                const uint32_t q = p_this + (uint32_t)(base + lane);
+                my_v = ssrc[q];
+                my_w = sw[q];
+                my_slot = sslot[q];
+            }
+            for (int j0 = 0; j0 < nmsg; j0 += D) {
+                float4 x[D][V];
+                float w[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const int jj = j0 + j;
+                    const int sl = jj < nmsg ? jj : 0;
+                    const uint32_t v = __shfl_sync(0xffffffffu, my_v, sl);
+                    const uint32_t slot = __shfl_sync(0xffffffffu, my_slot, sl);
+                    float wj = __shfl_sync(0xffffffffu, my_w, sl);
+                    const bool direct = DIRECT && (slot & kDirect) != 0;
+                    if (DIRECT) wj = fabsf(wj);
+                    w[j] = wj;
+                    const float* sstate = st.data + (long long)v * st.node_stride;
+                    const float* ssnap = snap + (long long)(slot & ~kDirect) * snap4 * 4;
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (jj < nmsg && in[k]) {
+                            val = (col[k] < ds4 || direct) ? ld4(sstate + 4 * (long long)col[k])
+                                                           : ld4(ssnap + 4 * (long long)(col[k] - ds4));
+                            // received rows are current as of the epoch before this call
+                            if (DIRECT && LAZY && direct && col[k] >= ds4 && dnow.has_decay)
+                                scale4(val, pick4(dnow.c[0], dnow.c[1], dnow.c[2], dnow.c[3], tl[k] - 1));
+                        }
+                        x[j][k] = val;
+                    }
+                }
+                if (first) {
+                    first = false;
+                    // behind the row requests: metadata of the next segment, head of the one after
+                    if (it + warps < n_items) mc = load_meta(p_nxt);
+                    p_cur = p_nxt;
+                    p_nxt = it + 2 * warps < n_items ? heads[it + 2 * warps] : 0u;
+                    if (LAZY) {
+                        float f[TPN_MAX_LAYERS];
+#pragma unroll
+                        for (int l = 0; l < TPN_MAX_LAYERS; ++l)
+                            f[l] = (l < L && stamp[l] >= 0) ? decay_factor(st, l, stamp[l]) : 1.0f;
+#pragma unroll
+                        for (int k = 0; k < V; ++k) scale4(acc[k], pick4(f[0], f[1], f[2], f[3], tl[k]));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    if (j0 + j < nmsg) {
+#pragma unroll
+                        for (int k = 0; k < V; ++k) axpy4_rn(acc[k], x[j][k], w[j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            if (in[k]) st4(tbase + 4 * (long long)col[k], acc[k]);
+    }
+}
+
+// Long segments (>= kHubMin messages).  A target's messages are added one at a time in order,
+// so a hub of m messages is a dependent chain of m fp32 adds per column; the chain runs out of
+// shared memory.  Work item = (segment, column slice of <= 64 floats inside ONE source row), one
+// CTA: two producer warps stage, per ring stage of 32 messages, the weights and the source-row
+// slices with per-lane `cp.async` (LDGSTS: no uniform-datapath serialisation, two messages per
+// warp instruction), completion counted on the stage's `full` mbarrier
+// (cp.async.mbarrier.arrive.noinc); the consumer warp owns two adjacent columns per lane and
+// runs LDS.64 + FMUL2 + 2 FADD per message — fadd_rn(acc, fmul_rn(x, w)) in sorted-message
+// order, exactly the warp walker's arithmetic — then releases the stage (`empty` mbarrier).
+// Slices are narrow on purpose: an SM's L1/LSU path moves 64 B/clk, so 256 B per message keeps
+// the data path at the ~4-cycle add chain; a giant hub is spread over L*ceil(rs/64) SMs.
+// CTAs pull work items from an atomic counter, giant segments first.
+struct Hub2Smem {
+    float ring[kHub2Stages][32][kHub2SlotFloats];
+    float wring[kHub2Stages][32];
+    uint64_t full[kHub2Stages];
+    uint64_t empty[kHub2Stages];
+    int item;
+};
+
+template <bool LAZY, bool DIRECT>
+__global__ void __launch_bounds__(kHub2Threads)
+walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ssrc,
+                 const float* __restrict__ sw, const uint32_t* __restrict__ sslot,
+                 const uint32_t* __restrict__ slen, const float* __restrict__ snap,
+                 const uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ hub_reg,
+                 uint32_t* __restrict__ ctr, int spr, int slice_w, DecayArgs dnow) {
+    extern __shared__ __align__(128) unsigned char hub2_raw[];
+    Hub2Smem& sm = *reinterpret_cast<Hub2Smem*>(hub2_raw);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int L = st.num_layer;
+    const int rs = (int)st.row_stride;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kHub2Stages; ++i) {
+            mbar_init(&sm.full[i], 32);                // the 32 lanes of the producer warp that owns the stage
+            mbar_init(&sm.empty[i], kHub2Consumers);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t n_giant = ctr[kCtrGiant], n_reg = ctr[kCtrHub];
+    const uint32_t slices = (uint32_t)(L * spr);
+    const uint32_t total = (n_giant + n_reg) * slices;
+    uint32_t blk_base = 0;      // ring blocks produced / consumed so far by this CTA (same count in every warp)
+    for (;;) {
+        if (threadIdx.x == 0) sm.item = (int)atomicAdd(&ctr[kCtrHub2Work], 1u);
+        __syncthreads();
+        const uint32_t work = (uint32_t)sm.item;
+        __syncthreads();
+        if (work >= total) break;
+        const uint32_t hub = work / slices;
+        const int slice = (int)(work - hub * slices);
+        const int r = slice / spr;                      // source row 0..L-1 -> target layer r+1
+        const int c0 = (slice - r * spr) * slice_w;     // first column of the slice inside the row
+        const int width = min(rs, c0 + slice_w) - c0;   // floats, multiple of 4
+        const int head = (int)(hub < n_giant ? hub_giant[hub] : hub_reg[hub - n_giant]);
+        const int len = (int)slen[head];
+        const uint32_t key = skey[head];
+        const int nblk = (len + 31) >> 5;
+        if (width > 0) {
+            if (warp >= kHub2Consumers) {
+                // ------------------------------------------------ producers
+                const int pw = warp - kHub2Consumers;
+                const int nvec = width >> 2;            // 16-byte pieces per message (<= 16)
+                const int half = lane >> 4, sub = lane & 15;
+                // metadata (source id, snapshot slot) of this lane's message, kept two rounds ahead
+                // in registers so that its L2 latency never sits in front of a stage fill
+                auto meta = [&](int b, uint32_t& v, uint32_t& x) {
+                    const int j = b * 32 + lane;
+                    v = 0u;
+                    x = 0u;
+                    if (j < len) {
+                        v = ssrc[head + j];
+                        if (r >= 1 || DIRECT) x = sslot[head + j];
+                    }
+                };
+                auto src_ptr = [&](uint32_t v, uint32_t x) -> const float* {
+                    if (DIRECT && (x & kDirect) != 0)   // received row: rows 0..L-1 contiguous in the state
+                        return st.data + (long long)v * st.node_stride + (long long)r * rs + c0;
+                    if (r == 0) return st.data + (long long)v * st.node_stride + c0;      // P_0: never written
+                    return snap + (long long)x * (long long)(L - 1) * rs + (long long)(r - 1) * rs + c0;
+                };
+                uint32_t v0, x0, v1, x1, v2, x2;
+                meta(pw, v0, x0);
+                meta(pw + kHub2Producers, v1, x1);
+                for (int b = pw; b < nblk; b += kHub2Producers) {
+                    meta(b + 2 * kHub2Producers, v2, x2);
+                    const uint32_t g = blk_base + (uint32_t)b;
+                    const int stage = (int)(g % kHub2Stages);
+                    const uint32_t use = g / kHub2Stages;
+                    if (use > 0) mbar_wait(&sm.empty[stage], (use - 1u) & 1u);
+                    const int nm = min(32, len - b * 32);
+                    if (lane < nm) cp_async4(&sm.wring[stage][lane], sw + head + b * 32 + lane);
+                    // this lane's piece of ITS message; lanes exchange pointers by shuffle so that one
+                    // LDGSTS instruction moves two whole messages (2 x 16 lanes x 16 B, coalesced)
+                    const unsigned long long mine = reinterpret_cast<unsigned long long>(src_ptr(v0, x0));
+                    const unsigned plo = (unsigned)mine, phi = (unsigned)(mine >> 32);
+                    float* dst = &sm.ring[stage][half][sub * 4];
+                    if (nm == 32) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; jj += 2) {
+                            const unsigned lo = __shfl_sync(0xffffffffu, plo, jj + half);
+                            const unsigned hi = __shfl_sync(0xffffffffu, phi, jj + half);
+                            const float* pj = reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
+                            if (sub < nvec) cp_async16(dst + jj * kHub2SlotFloats, pj + sub * 4);
+                        }
+                    } else {
+                        for (int jj = 0; jj < nm; jj += 2) {
+                            const unsigned lo = __shfl_sync(0xffffffffu, plo, jj + half);
+                            const unsigned hi = __shfl_sync(0xffffffffu, phi, jj + half);
+                            const float* pj = reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
+                            if (jj + half < nm && sub < nvec) cp_async16(dst + jj * kHub2SlotFloats, pj + sub * 4);
+                        }
+                    }
+                    cp_async_mbar_arrive_noinc(&sm.full[stage]);
+                    v0 = v1; x0 = x1;
+                    v1 = v2; x1 = x2;
+                }
+            } else {
+                // ------------------------------------------------ consumer(s): 2 columns per lane
+                const int col = warp * 64 + 2 * lane;
+                const bool active = col < width;
+                float* tptr = st.data + (long long)key * st.node_stride + (long long)(r + 1) * rs + c0 + col;
+                // received source rows: this call's decay of source row r (P_0 never decays)
+                const float dfac = (DIRECT && LAZY && dnow.has_decay && r >= 1)
+                                       ? pick4(dnow.c[0], dnow.c[1], dnow.c[2], dnow.c[3], r - 1) : 1.0f;
+                float2 acc = make_float2(0.f, 0.f);
+                if (active) {
+                    acc = *reinterpret_cast<const float2*>(tptr);           // zeros if never written
+                    if (LAZY) {
+                        const int ts = st.stamps[(long long)key * L + r];
+                        if (ts >= 0) acc = mul2_rn(acc, decay_factor(st, r, ts));
+                    }
+                }
+                for (int b = 0; b < nblk; ++b) {
+                    const uint32_t g = blk_base + (uint32_t)b;
+                    const int stage = (int)(g % kHub2Stages);
+                    mbar_wait(&sm.full[stage], (g / kHub2Stages) & 1u);
+                    const int nm = min(32, len - b * 32);
+                    const float* xs = &sm.ring[stage][0][col];
+                    const float* ws_ = &sm.wring[stage][0];
+                    auto step = [&](int j) {
+                        float2 x = *reinterpret_cast<const float2*>(xs + j * kHub2SlotFloats);
+                        float w = ws_[j];
+                        if (DIRECT) {
+                            if (__float_as_int(w) < 0) {                   // sign bit: received row
+                                x = mul2_rn(x, dfac);
+                                w = fabsf(w);
+                            }
+                        }
+                        axpy2_rn(acc, x, w);
+                    };
+                    if (nm == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) step(j);
+                    } else {
+                        for (int j = 0; j < nm; ++j) step(j);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.empty[stage]);
+                }
+                if (active) *reinterpret_cast<float2*>(tptr) = acc;
+            }
+        }
+        blk_base += (width > 0) ? (uint32_t)nblk : 0u;
+    }
+}
+
+template <bool DIRECT>
+int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const DecayArgs& dnow, cudaStream_t stream) {
+    static bool configured = false;
+    const int smem = (int)sizeof(Hub2Smem);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(walk_hub2_kernel<false, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(walk_hub2_kernel<true, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_cuda_error(e);
+            return TPN_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int rs = (int)v.row_stride;
+    const int spr = (rs + kHub2SlotFloats - 1) / kHub2SlotFloats;          // slices per row
+    const int slice_w = (((rs + spr - 1) / spr) + 3) & ~3;
+    const unsigned grid = 148 * 3;
+    if (lazy)
+        walk_hub2_kernel<true, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
+                                                                             ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
+                                                                             spr, slice_w, dnow);
+    else
+        walk_hub2_kernel<false, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
+                                                                              ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
+                                                                              spr, slice_w, dnow);
+    return TPN_OK;
+}
+
+template <int V, bool DIRECT>
+void launch_walk_small_v(const StateView& v, const Workspace& ws, int E, int ds4, int tiles, bool lazy,
+                         const DecayArgs& dnow, cudaStream_t stream) {
+    long long want = ((long long)E + kSmallWalkThreads / 32 - 1) / (kSmallWalkThreads / 32);
+    const long long cap = 148 * 2 * 2;                // two resident CTAs per SM, two waves
+    dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)tiles);
+    if (lazy)
+        walk_small_kernel<V, true, DIRECT><<<grid, kSmallWalkThreads, 0, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
+                                                                                   ws.slen, ws.snap, ws.small_heads, ws.ctr,
+                                                                                   E, ds4, dnow);
+    else
+        walk_small_kernel<V, false, DIRECT><<<grid, kSmallWalkThreads, 0, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
+                                                                                    ws.slen, ws.snap, ws.small_heads, ws.ctr,
+                                                                                    E, ds4, dnow);
+}
+
+template <bool DIRECT>
+void launch_walk_small(const StateView& v, const Workspace& ws, int E, int ds4, bool lazy, const DecayArgs& dnow,
+                       cudaStream_t stream) {
+    const int span4 = v.num_layer * ds4;
+    int vpl = (span4 + 31) / 32;
+    int tiles = 1;
+    if (vpl > 6) {
+        tiles = (vpl + 5) / 6;
+        vpl = (vpl + tiles - 1) / tiles;
+    }
+    switch (vpl) {
+        case 1: launch_walk_small_v<1, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
+        case 2: launch_walk_small_v<2, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
+        case 3: launch_walk_small_v<3, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
+        case 4: launch_walk_small_v<4, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
+        case 5: launch_walk_small_v<5, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
+        default: launch_walk_small_v<6, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
     }
 }
 
@@ -946,12 +1342,18 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
     long long new_epoch = st->epoch;
     if (lazy && dargs.has_decay) {
         if (st->epoch + 1 >= st->log_capacity) return TPN_ERR_LOG_FULL;
+        // the log holds f64 cumulative products: restart it (materialise) long before they underflow
+        double cmin = 1.0;
+        for (int l = 0; l < L; ++l) cmin = dargs.c[l] < cmin ? (double)dargs.c[l] : cmin;
+        if (st->epoch == 0) st->cum_floor = 1.0;
+        if (st->epoch > 0 && !(st->cum_floor * cmin >= 1e-200)) return TPN_ERR_LOG_FULL;
+        st->cum_floor *= cmin;      // tiny (or 0) only right after a restart: the next epoch restarts again
         new_epoch = st->epoch + 1;
     }
 
     const int ds4 = (int)(st->row_stride / 4);
     const float t_last_f = (float)t_last;
-    float* log_w = lazy ? st->decay_log : nullptr;
+    double* log_w = lazy ? st->decay_log : nullptr;
     // Snapshot + single all-layer launch whenever the snapshot fits.  Edge mode: every source is
     // also a target, so every source has a snapshot slot.  Message mode (sharded): sources that
     // are not targets of this call (received rows) are read straight from the state (kDirect).
@@ -999,7 +1401,7 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
         }
         payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(vin, ws.key_a, msgs, ws.w, E, ws.ssrc, ws.sw,
                                                             snapshot_path ? ws.sslot : nullptr, ws.slen, ws.hub_giant,
-                                                            ws.hub_reg, ws.ctr,
+                                                            ws.hub_reg, ws.small_heads, ws.ctr,
                                                             (lazy && !snapshot_path && L >= 2) ? ws.svst : nullptr,
                                                             st->stamps, L, E4, st->num_nodes, err_flag_dev);
         if (eager_sweep) {
@@ -1015,13 +1417,20 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
             if (lazy) snapshot_kernel<true><<<grid, 256, 0, stream>>>(view, ws.key_a, E, ds4, ws.snap);
             else snapshot_kernel<false><<<grid, 256, 0, stream>>>(view, ws.key_a, E, ds4, ws.snap);
         }
-        // one float4 per lane: a warp covers 512 contiguous bytes of the L*row_stride span
-        const int span4 = L * ds4;
         if (hubs) {
-            const int hrc = launch_walk_hub<true>(view, 0, ws, E4, lazy, dargs, stream);
+            // large batch: long segments on the CTA-pipelined hub walker, short ones on the
+            // persistent warp walker (disjoint target rows; both read only pre-batch values)
+            const bool direct = msgs.B == 0;
+            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, stream)
+                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, stream);
             if (hrc != TPN_OK) return hrc;
+            if (direct) launch_walk_small<true>(view, ws, E, ds4, lazy, dargs, stream);
+            else launch_walk_small<false>(view, ws, E, ds4, lazy, dargs, stream);
+        } else {
+            // single-CTA sort path: one float4 per lane, a warp covers 512 contiguous bytes of the span
+            const int span4 = L * ds4;
+            launch_walk<1, 16, true>(view, 0, ws, E, ds4, (span4 + 31) / 32, lazy, false, dargs, stream);
         }
-        launch_walk<1, 16, true>(view, 0, ws, E, ds4, (span4 + 31) / 32, lazy, hubs, dargs, stream);
         if (lazy) stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, 0, ws.key_a, E);
     } else {
         // per-layer walk: V float4 per lane so that one tile covers rows up to 512 floats

@@ -15,7 +15,9 @@ sites):
     ``[N, L+1, row_stride]``; ``self.random_projections[i]`` are strided ``[N, d]``
     views of it (values, shapes, dtypes and state_dict keys are the reference's);
   * ``decay_mode='lazy'`` defers the per-update whole-matrix rescale
-    (TPNet.py:83-85) to the rows that are touched; reads through this class's
+    (TPNet.py:83-85) to the rows that are touched (one multiply by the product of
+    the skipped factors: same value up to one fp32 rounding per skipped update,
+    identical when at most one update was skipped); reads through this class's
     methods are always current, raw reads of ``random_projections[i]`` need
     ``materialize()`` first (``state_dict()`` and ``backup_…`` do it themselves);
   * ids may also be passed as int64 CUDA tensors (device-resident pipelines).
@@ -256,12 +258,14 @@ class RandomProjectionModule(nn.Module):
                     has_data = bool((self._state[:, 1:, :] != 0).any().item()) if self._state.numel() else False
                     self._stamps = torch.full((self.node_num, self.num_layer), 0 if has_data else -1,
                                               dtype=torch.int32, device=self._state.device)
-                    self._decay_log = torch.ones(_DEFAULT_LOG_EPOCHS, self.num_layer, dtype=torch.float32,
+                    # f64 cumulative products of the per-update fp32 factors; row 0 = 1.0
+                    self._decay_log = torch.ones(_DEFAULT_LOG_EPOCHS, self.num_layer, dtype=torch.float64,
                                                  device=self._state.device)
                     h.epoch = 0
                 st.stamps = self._stamps.data_ptr()
                 st.decay_log = self._decay_log.data_ptr()
                 st.log_capacity = self._decay_log.shape[0]
+                st.cum_floor = 1.0
             else:
                 st.stamps = None
                 st.decay_log = None

@@ -259,8 +259,12 @@ class ShardedRandomProjection(RandomProjectionModule):
             self._c_state()
             if self._h.epoch + 1 >= self._decay_log.shape[0]:
                 self._restart_log()
+            if self._h.st.cum_floor * min(factors) < 1e-200:
+                self._restart_log()
             self._h.epoch += 1
-            self._decay_log[self._h.epoch].copy_(torch.tensor(list(factors), dtype=torch.float32))
+            f = torch.tensor([float(x) for x in factors], dtype=torch.float64, device=self._decay_log.device)
+            self._decay_log[self._h.epoch] = self._decay_log[self._h.epoch - 1] * f      # cumulative products
+            self._h.st.cum_floor *= float(min(factors))
         else:
             with torch.no_grad():
                 for i in range(1, self.num_layer + 1):
