@@ -402,18 +402,36 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
         return plan
 
     def stage(st):
-        """Resident inputs of one step: the routing plans are a pure function of the batch."""
+        """Resident inputs of one step.  One GPU: the edge batch itself as device tensors (the
+        plain edge-batch path).  Sharded: the routing plans, a pure function of the batch."""
         s, d, t, neg = st
+        if world == 1:
+            g = lambda a: torch.from_numpy(a).to(device)     # noqa: E731
+            return dict(src=g(s), dst=g(d), t=g(t), neg=g(neg), t_last=float(t[-1]))
         up, tmsg = m.plan_update(s, d, t)
         return dict(src=s, dst=d, t=t, up=(dev_plan(up), torch.from_numpy(tmsg).to(device)),
                     pos=dev_plan(m.plan_pairs(s, d)), neg=dev_plan(m.plan_pairs(s, neg)))
 
     res = [stage(st) for st in steps[warm_n:warm_n + K + W]]
 
-    def resident(st):
-        m.pair_wise_gram(None, None, plan=st['pos'])
-        m.pair_wise_gram(None, None, plan=st['neg'])
+    def resident_pairs(st, which):
+        if world == 1:
+            m.pair_wise_gram(st['src'], st['dst' if which == 'pos' else 'neg'])
+            return B
+        m.pair_wise_gram(None, None, plan=st[which])
+        return int(st[which].first_rows.shape[0])
+
+    def resident_update(st):
+        if world == 1:
+            m.update(st['src'], st['dst'], st['t'], next_time=st['t_last'])
+            return 2 * B
         m.update(st['src'], st['dst'], st['t'], plan=st['up'])
+        return int(st['up'][0].first_rows.shape[0])
+
+    def resident(st):
+        resident_pairs(st, 'pos')
+        resident_pairs(st, 'neg')
+        resident_update(st)
 
     for st in res[:W]:
         resident(st)
@@ -445,15 +463,13 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
             dist.barrier()
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record()
-        m.pair_wise_gram(None, None, plan=r['pos'])
+        n_pairs_local = resident_pairs(r, 'pos')
         b.record()
-        m.update(r['src'], r['dst'], r['t'], plan=r['up'])
+        n_msgs_local = resident_update(r)
         c.record()
         torch.cuda.synchronize()
         t_pair.append(a.elapsed_time(b))
         t_upd.append(b.elapsed_time(c))
-        n_pairs_local = int(r['pos'].first_rows.shape[0])
-        n_msgs_local = int(r['up'][0].first_rows.shape[0])
     pair_ms, upd_ms = float(np.mean(t_pair)), float(np.mean(t_upd))
 
     # end to end: numpy API, plans computed inside the timed region, head + scalar read-back
@@ -500,10 +516,11 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
     roof = {'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
             'phases': {'pairwise': {'what': 'exchange (N>1) + tpn::pairwise_tma_kernel, %d pairs on rank 0' % n_pairs_local,
                                     'ms': pair_ms, 'achieved': pair_gbs, 'frac': pair_gbs / peak},
-                       'update': {'what': 'exchange (N>1) + radix sort + 3 x tpn::walk_kernel, %d messages on rank 0'
+                       'update': {'what': 'exchange (N>1) + radix sort + snapshot + tpn::walk_small_kernel || '
+                                          'tpn::walk_hub2_kernel, %d messages on rank 0'
                                   % n_msgs_local, 'ms': upd_ms, 'achieved': upd_gbs, 'frac': upd_gbs / peak}}}
     if dominant_is_update:
-        roof.update(kernel='update path (radix sort + per-layer tpn::walk_kernel)', achieved=upd_gbs,
+        roof.update(kernel='update path (radix sort + snapshot + walk_small || walk_hub2)', achieved=upd_gbs,
                     frac=upd_gbs / peak, traffic=traffic_note('powerlaw_update_dram_bytes_per_call'))
     else:
         roof.update(kernel='tpn::pairwise_tma_kernel', achieved=pair_gbs, frac=pair_gbs / peak,
@@ -530,7 +547,9 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
                 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / n_api,
                 'path': 'ShardedRandomProjection.get_pair_wise_feature/update with numpy ids (routing plan computed '
                         'on the host inside the timed region), self.mlp included'},
-        'gpu_launches': K * (2 + 2 + 11 + (6 if world > 1 else 0)),
+        # per step: 2 pair-wise + update (prep, 3 x (hist + prefix + scatter), payload, giant sort, snapshot,
+        # hub2, small, stamps)
+        'gpu_launches': K * (2 + 16 + (6 if world > 1 else 0)),
         'exchange': None if world == 1 else {'rows_received_per_rank_per_step': recv_rows_per_step,
                                              'bytes_per_rank_per_step': recv_rows_per_step * block_bytes},
         'clocks': sampler.window(wall0, wall_end) if sampler else None,

@@ -129,7 +129,12 @@ int tpn_update(tpn_state_t* st,
  *   TPN_DEBUG_PER_LAYER_WALK : large batches use one walk launch per layer (top-down) instead of
  *                              the pre-batch snapshot + single all-layer launch. */
 #define TPN_DEBUG_PER_LAYER_WALK 1
+/*   TPN_DEBUG_SERIAL_WALK    : large batches run the hub walker and the short-segment walker one
+ *                              after the other on the caller's stream (default: concurrently, the
+ *                              hub walker on a library-owned side stream forked/joined by events). */
+#define TPN_DEBUG_SERIAL_WALK 2
 int tpn_set_debug_flags(int flags);
+
 
 /*
  * Message-level form of tpn_update for a node-sharded state (no reference

@@ -176,15 +176,16 @@ def test_update_bit_exact_with_equal_timestamps(B, N, dim, L, mode):
     m.check_errors()
 
 
-@pytest.mark.parametrize('per_layer', [False, True])
+@pytest.mark.parametrize('flags', [0, 1, 2], ids=['concurrent', 'per-layer', 'serial'])
 @pytest.mark.parametrize('mode', ['eager', 'lazy', 'lazy-frozen'])
 @pytest.mark.parametrize('B,N,dim,L,skew', [(6000, 300, 210, 3, 1.3), (2100, 50, 140, 3, 1.1), (9000, 2000, 36, 4, 1.5),
                                             (5000, 40, 300, 1, 1.2), (3000, 30, 64, 2, 1.05), (4000, 60, 1000, 2, 1.3)])
-def test_hub_walker_bit_exact(B, N, dim, L, skew, mode, per_layer):
+def test_hub_walker_bit_exact(B, N, dim, L, skew, mode, flags):
     """Long segments (>= 64 messages on one target) leave the warp walker for the CTA-pipelined
     hub walkers (cp.async / TMA rings + mbarriers): giant (>= 2048) and regular hubs, 64-float
     column slices (d=210 -> 216-float rows -> 4 slices of 56/56/56/48 per row; d=1000 -> 16),
-    both the snapshot + all-layer launch and the per-layer launches, eager and lazy decay.
+    the snapshot + all-layer launches (hub walker on the side stream concurrently with the
+    short-segment walker, or serially) and the per-layer launches, eager and lazy decay.
     Equal timestamps make w == 1, so eager (and lazy with a frozen clock) must equal the
     oracle bit for bit."""
     frozen = mode == 'lazy-frozen'
@@ -195,7 +196,7 @@ def test_hub_walker_bit_exact(B, N, dim, L, skew, mode, per_layer):
               beginning_time=0.0, not_scale=False, enforce_dim=dim)
     o = WalkProjectionOracle(**kw)
     m = module_from_cfg(kw, o.P[0], mode)
-    old = lib.tpn_set_debug_flags(1 if per_layer else 0)
+    old = lib.tpn_set_debug_flags(flags)
     try:
         for s, d, t in stream(rng, N, B, 5, skew, equal_times=True, frozen=frozen):
             o.update(s, d, t)

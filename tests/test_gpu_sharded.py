@@ -31,14 +31,16 @@ def test_sharded_single_rank_equals_plain_module():
             d = rng.integers(1, 301, B).astype(np.int64)
             ts = np.sort(t + rng.random(B) * 100.0)
             t = ts[-1]
-            sh.update(s, d, ts)
+            sh.update(s, d, ts, plan=sh.plan_update(s, d, ts))      # explicit plan: the message-mode path
             ref.update(s, d, ts)
         sh.materialize(); ref.materialize()
         for i in range(4):
             assert torch.equal(sh.random_projections[i].data[:301], ref.random_projections[i].data), (mode, i)
         a = rng.integers(0, 301, 500).astype(np.int64)
         b = rng.integers(0, 301, 500).astype(np.int64)
-        keep, feat = sh.pair_wise_gram(a, b)
+        keep, feat = sh.pair_wise_gram(a, b, plan=sh.plan_pairs(a, b))
+        assert len(keep) == 500 and torch.equal(feat, ref.pair_wise_gram(a, b))
+        keep, feat = sh.pair_wise_gram(a, b)                        # world 1 without a plan: the plain path
         assert len(keep) == 500 and torch.equal(feat, ref.pair_wise_gram(a, b))
 
 

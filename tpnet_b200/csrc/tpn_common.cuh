@@ -140,6 +140,11 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
 __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {      // at most N committed groups of this thread still in flight
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 // the mbarrier receives one arrival (pre-counted in its init count) once every cp.async this
 // thread issued so far has landed
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {

@@ -10,8 +10,9 @@
 //                  (batch order within the src role, then the dst role).
 //                    2B <= 1024 : one CTA, rank sort in shared memory (one barrier)
 //                    2B <= 4096 : one CTA, bitonic network on (target << 32 | m)
-//                    larger     : LSD radix sort, 8-bit digits, warp-match ranking
-//                                 (integer atomics only on histogram counts).
+//                    larger     : LSD radix sort, 8-bit digits, two launches per pass (block
+//                                 histograms; scatter with in-kernel offsets + warp-match
+//                                 ranking); integer atomics only on histogram counts.
 //   3. sweep     : eager mode only — P_l *= c_l over the whole state          (TPNet.py:83-85).
 //                  For 2B <= 4096 it runs in the SAME launch as prep (block 0 sorts while
 //                  the other blocks sweep).
@@ -25,6 +26,8 @@
 //                        launch updates all layers, reading layer 0 from the state and
 //                        layers >= 1 from the snapshot;
 //                    larger : one launch per layer, top-down (no extra traffic).
+#include <stdlib.h>
+
 #include "tpn_common.cuh"
 
 namespace tpn {
@@ -40,6 +43,7 @@ constexpr int kRadixThreads = 256;
 constexpr int kRadixItems = 8;
 constexpr int kRadixTile = kRadixThreads * kRadixItems;   // 2048 keys per block
 constexpr int kRadixBins = 256;
+constexpr int kRadixDirectBlocks = 16;    // up to this many tiles the scatter sums the block histograms itself
 constexpr int kWalkThreads = 256;
 // CTA-pipelined walker for long segments (hubs)
 constexpr int kHubMin = 64;              // segments at least this long leave the warp walker
@@ -52,13 +56,17 @@ constexpr int kHubMetaChunk = 512;       // messages of metadata staged per bulk
 constexpr size_t kSnapMaxBytes = (size_t)3 << 29;          // 1.5 GiB: above this the per-layer path is used
 // large batches, snapshot path: short segments -> persistent warp walker, long ones -> hub2
 constexpr int kSmallWalkThreads = 256;
-constexpr int kHub2Consumers = 1;        // consumer warps; each lane owns 2 adjacent columns (packed FMUL2/FADD2)
-constexpr int kHub2Producers = 2;        // cp.async producer warps (alternate ring stages)
-constexpr int kHub2Threads = (kHub2Consumers + kHub2Producers) * 32;
-constexpr int kHub2SlotFloats = kHub2Consumers * 64;       // floats of one message held by a ring slot
-constexpr int kHub2Stages = 8;           // ring stages of 32 messages (8 x 32 x 256 B = 64 KB)
+constexpr int kHub2Producers = 7;        // producer warps: each keeps one ring stage (32 messages) of loads in flight
+constexpr int kHub2Threads = (1 + kHub2Producers) * 32;    // + the consumer warp (warp 0)
+constexpr int kHub2SlotFloats = 64;      // floats of one message held by a ring slot (consumer: 2 columns per lane)
+constexpr int kHub2GiantFloats = 16;     // slice width of giant segments: an SM sustains ~10 B/clk of row gathers
+                                         // (outstanding-miss capacity), so 64 B per message keeps its data path
+                                         // near the add chain's 4-6 cycles per message
+constexpr int kHub2Stages = kHub2Producers + 4;            // ring stages of 32 messages (8 KB each)
 // ctr[] slots (zeroed by prep_large_kernel)
-constexpr int kCtrGiant = 0, kCtrHub = 1, kCtrWork0 = 2, kCtrSmall = 6, kCtrHub2Work = 7;
+constexpr int kCtrGiant = 0, kCtrHub = 1, kCtrWork0 = 2, kCtrSmall = 6, kCtrHub2Work = 7, kCtrHub2Giant = 8;
+constexpr int kCtrSmClaim = 16;          // [256] first hub2 CTA of each SM claims the SM's giant-segment slot
+constexpr int kCtrSlots = kCtrSmClaim + 256;
 
 struct DecayArgs {
     float c[TPN_MAX_LAYERS];
@@ -108,8 +116,8 @@ struct Workspace {
     float* snap;       // [E][(L-1)*row_stride] pre-batch rows 1..L-1 of each target (snapshot path only)
     uint32_t* hub_giant;   // [E / kGiantMin + 2] sorted positions of the heads of giant segments
     uint32_t* hub_reg;     // [E / kHubMin + 2]   ... of the other long segments
-    uint32_t* ctr;         // [8] 0: #giant, 1: #regular, 2..5: work counters of the per-layer hub launches,
-                           //     6: #short segments, 7: work counter of the hub2 launch
+    uint32_t* ctr;         // [kCtrSlots] 0: #giant, 1: #regular, 2..5: work counters of the per-layer hub launches,
+                           //     6: #short segments, 7/8: work counters of the hub2 launch, 16..: SM claims
     uint32_t* small_heads; // [E] sorted positions of the heads of short segments (scheduling order only)
     int* svst;             // [L-1][E] pre-batch stamp of the source row of each sorted message (lazy, per-layer path)
     bool has_snap;
@@ -143,7 +151,7 @@ Workspace carve(void* base, int64_t batch, int num_layer, int64_t row_stride) {
     ws.snap = reinterpret_cast<float*>(take((ws.has_snap ? snap_bytes(E, num_layer, row_stride) : 0) + 16));
     ws.hub_giant = reinterpret_cast<uint32_t*>(take(4 * (E / kGiantMin + 2)));
     ws.hub_reg = reinterpret_cast<uint32_t*>(take(4 * (E / kHubMin + 2)));
-    ws.ctr = reinterpret_cast<uint32_t*>(take(4 * 8));
+    ws.ctr = reinterpret_cast<uint32_t*>(take(4 * kCtrSlots));
     ws.small_heads = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.svst = reinterpret_cast<int*>(take(4 * (E + 4) * (size_t)(num_layer > 1 ? num_layer - 1 : 1) + 16));
     ws.bytes = off;
@@ -346,7 +354,7 @@ prep_large_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long 
     if (m == 0 && decay_log != nullptr && decay.has_decay) {
         for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay_log[(new_epoch - 1) * L + l] * (double)decay.c[l];
     }
-    if (m < 8) ctr[m] = 0;                               // hub lists and work counters of this call
+    if (m < kCtrSlots) ctr[m] = 0;                       // hub lists, work counters and SM claims of this call
     if (m >= E) return;
     long long tgt, oth;
     int widx;
@@ -371,53 +379,37 @@ radix_hist_kernel(const uint32_t* __restrict__ key, int E, int shift, uint32_t* 
         if (idx < E) atomicAdd(&bins[(key[idx] >> shift) & 0xff], 1u);     // integer count: order-independent
     }
     __syncthreads();
-    hist[threadIdx.x * nblk + blockIdx.x] = bins[threadIdx.x];
+    hist[blockIdx.x * kRadixBins + threadIdx.x] = bins[threadIdx.x];     // [block][digit]
 }
 
-// exclusive scan of `total` uint32 in place, one CTA
-__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ hist, int total) {
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    const int per = (total + 1023) / 1024;
-    const int lo = tid * per, hi = min(lo + per, total);
-    uint32_t local = 0;
-    for (int i = lo; i < hi; ++i) local += hist[i];
-    uint32_t inc = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += n;
-    }
-    if (lane == 31) warp_sum[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t v = warp_sum[lane];
-        uint32_t s = v;
+// Many tiles (nblk > kRadixDirectBlocks): per digit, the exclusive prefix over blocks and the digit
+// total, one warp per digit, in place ([block][digit] counts -> prefixes; totals in row nblk).
+__global__ void __launch_bounds__(256) radix_prefix_kernel(uint32_t* __restrict__ hist, int nblk) {
+    const int dgt = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    uint32_t carry = 0;
+    for (int b0 = 0; b0 < nblk; b0 += 32) {
+        const int b = b0 + lane;
+        const uint32_t c = b < nblk ? hist[b * kRadixBins + dgt] : 0u;
+        uint32_t inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += n;
+            const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nb;
         }
-        warp_sum[lane] = s - v;     // exclusive
+        if (b < nblk) hist[b * kRadixBins + dgt] = carry + inc - c;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    __syncthreads();
-    uint32_t run = warp_sum[wid] + inc - local;
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t v = hist[i];
-        hist[i] = run;
-        run += v;
-    }
+    if (lane == 0) hist[nblk * kRadixBins + dgt] = carry;
 }
 
 __global__ void __launch_bounds__(kRadixThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
                      uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, int E, int shift,
-                     const uint32_t* __restrict__ offs, int nblk) {
+                     const uint32_t* __restrict__ offs, int nblk, int prefixed) {
     constexpr int kWarps = kRadixThreads / 32;
     __shared__ uint32_t wcount[kWarps][kRadixBins + 1];
+    __shared__ uint32_t wtot[kWarps];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < kWarps * (kRadixBins + 1); i += kRadixThreads) (&wcount[0][0])[i] = 0;
     __syncthreads();
@@ -441,9 +433,38 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
         rank[i] = before + __popc(peers & lt_mask);
     }
     __syncthreads();
-    {   // per digit: global offset of this block + exclusive prefix over warps
+    {   // per digit: global offset of this block + exclusive prefix over warps.  The global offset
+        // of (digit, block) = keys with a smaller digit + keys with this digit in earlier blocks,
+        // summed here from the [block][digit] histogram (coalesced, L2-resident) — no scan launch.
         const int dgt = tid;    // kRadixThreads == kRadixBins
-        uint32_t run = offs[dgt * nblk + blockIdx.x];
+        uint32_t before = 0, total = 0;
+        if (prefixed) {          // radix_prefix_kernel ran: prefixes in place, totals in row nblk
+            before = offs[blockIdx.x * kRadixBins + dgt];
+            total = offs[nblk * kRadixBins + dgt];
+        } else {
+            for (int b0 = 0; b0 < nblk; b0 += 16) {          // 16 independent L2 loads per round
+                uint32_t c[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) c[i] = b0 + i < nblk ? offs[(b0 + i) * kRadixBins + dgt] : 0u;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    total += c[i];
+                    before += b0 + i < (int)blockIdx.x ? c[i] : 0u;
+                }
+            }
+        }
+        uint32_t inc = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nb;
+        }
+        if (lane == 31) wtot[wid] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) wbase += w < wid ? wtot[w] : 0u;
+        uint32_t run = wbase + inc - total + before;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
             const uint32_t c = wcount[w][dgt];
@@ -528,6 +549,27 @@ payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ 
         if (lane == leader) base = atomicAdd(&ctr[kCtrSmall], (uint32_t)__popc(mask));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (small_head) small_heads[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)p;
+    }
+}
+
+// Longest giant segments first: their add chains are the critical path of the hub walker.
+// (Scheduling order only — results do not depend on it.)
+constexpr int kGiantSortMax = 2048;
+__global__ void __launch_bounds__(1024)
+sort_giants_kernel(uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ slen, const uint32_t* __restrict__ ctr) {
+    __shared__ uint32_t head_s[kGiantSortMax], len_s[kGiantSortMax];
+    const int n = (int)ctr[kCtrGiant];
+    if (n < 2 || n > kGiantSortMax) return;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        head_s[i] = hub_giant[i];
+        len_s[i] = slen[head_s[i]];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t li = len_s[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (len_s[j] > li || (len_s[j] == li && j < i)) ? 1 : 0;
+        hub_giant[rank] = head_s[i];
     }
 }
 
@@ -1024,133 +1066,176 @@ walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_
     }
 }
 
-// Long segments (>= kHubMin messages).  A target's messages are added one at a time in order,
-// so a hub of m messages is a dependent chain of m fp32 adds per column; the chain runs out of
-// shared memory.  Work item = (segment, column slice of <= 64 floats inside ONE source row), one
-// CTA: two producer warps stage, per ring stage of 32 messages, the weights and the source-row
-// slices with per-lane `cp.async` (LDGSTS: no uniform-datapath serialisation, two messages per
-// warp instruction), completion counted on the stage's `full` mbarrier
-// (cp.async.mbarrier.arrive.noinc); the consumer warp owns two adjacent columns per lane and
-// runs LDS.64 + FMUL2 + 2 FADD per message — fadd_rn(acc, fmul_rn(x, w)) in sorted-message
-// order, exactly the warp walker's arithmetic — then releases the stage (`empty` mbarrier).
-// Slices are narrow on purpose: an SM's L1/LSU path moves 64 B/clk, so 256 B per message keeps
-// the data path at the ~4-cycle add chain; a giant hub is spread over L*ceil(rs/64) SMs.
-// CTAs pull work items from an atomic counter, giant segments first.
-struct Hub2Smem {
-    float ring[kHub2Stages][32][kHub2SlotFloats];
-    float wring[kHub2Stages][32];
-    uint64_t full[kHub2Stages];
-    uint64_t empty[kHub2Stages];
-    int item;
-};
+// Long segments (>= kHubMin messages).  A target's messages are added one at a time in order
+// (the reference's accumulation order is observable), so a hub of m messages is a dependent
+// chain of m fp32 adds per column.  The chain must see nothing but the add: everything else is
+// moved off it.  Work item = (segment, column slice inside ONE source row), one CTA:
+//   8 producer warps : warp p owns ring stages b = p, p+8, ... of 32 messages.  Each lane fetches
+//       the (source id, snapshot slot, weight) of one message, lanes exchange row pointers by
+//       shuffle so that every 128-bit load instruction covers 2 (4 for giants) whole message
+//       slices, coalesced; all loads of the stage are in flight together, then the slices are
+//       scaled — fmul_rn(x, w), the reference's rounded product (TPNet.py:91-96), plus this
+//       call's decay for received rows of a sharded state — and stored to the stage, published
+//       with the stage's `full` mbarrier.  Eight stages in flight hide DRAM latency.
+//   1 consumer warp  : two adjacent columns per lane; per message one LDS.64 and two scalar
+//       FADDs, acc = fadd_rn(acc, product) in sorted-message order — bit-identical to the warp
+//       walker — then the stage goes back through its `empty` mbarrier.
+// Giant segments (>= kGiantMin messages) are cut into <= 16-float slices, sorted longest first,
+// and taken only by ONE CTA per SM (first CTA to claim its SM), so a critical chain never shares
+// its SM's load/store path with another; everything else uses <= 64-float slices.  CTAs pull work
+// items from atomic counters.  Shared memory: ring[stages][32][64] floats | full | empty | item.
+__host__ __device__ inline size_t hub2_smem_bytes() {
+    return (size_t)kHub2Stages * (32 * kHub2SlotFloats * 4 + 16) + 16;
+}
 
 template <bool LAZY, bool DIRECT>
-__global__ void __launch_bounds__(kHub2Threads)
+__global__ void __launch_bounds__(kHub2Threads, 2)
 walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ssrc,
                  const float* __restrict__ sw, const uint32_t* __restrict__ sslot,
                  const uint32_t* __restrict__ slen, const float* __restrict__ snap,
                  const uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ hub_reg,
-                 uint32_t* __restrict__ ctr, int spr, int slice_w, DecayArgs dnow) {
+                 uint32_t* __restrict__ ctr, int spr_g, int slice_w_g, int spr_r, int slice_w_r, DecayArgs dnow) {
     extern __shared__ __align__(128) unsigned char hub2_raw[];
-    Hub2Smem& sm = *reinterpret_cast<Hub2Smem*>(hub2_raw);
+    float* const ring = reinterpret_cast<float*>(hub2_raw);                       // [stages][32][kHub2SlotFloats]
+    uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)kHub2Stages * 32 * kHub2SlotFloats);
+    uint64_t* const empty = full + kHub2Stages;
+    int* const item = reinterpret_cast<int*>(empty + kHub2Stages);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int L = st.num_layer;
     const int rs = (int)st.row_stride;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kHub2Stages; ++i) {
-            mbar_init(&sm.full[i], 32);                // the 32 lanes of the producer warp that owns the stage
-            mbar_init(&sm.empty[i], kHub2Consumers);
+            mbar_init(&full[i], 32);                   // every lane of the producer warp arrives after its stores
+            mbar_init(&empty[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        *item = (smid < 256u && atomicAdd(&ctr[kCtrSmClaim + smid], 1u) == 0u) ? 1 : 0;
     }
     __syncthreads();
+    const bool prefer_giant = *item != 0;          // this CTA holds its SM's giant-segment slot
+    __syncthreads();
     const uint32_t n_giant = ctr[kCtrGiant], n_reg = ctr[kCtrHub];
-    const uint32_t slices = (uint32_t)(L * spr);
-    const uint32_t total = (n_giant + n_reg) * slices;
+    const uint32_t slices_g = (uint32_t)(L * spr_g), slices_r = (uint32_t)(L * spr_r);
+    const uint32_t total_g = n_giant * slices_g, total_r = n_reg * slices_r;
     uint32_t blk_base = 0;      // ring blocks produced / consumed so far by this CTA (same count in every warp)
     for (;;) {
-        if (threadIdx.x == 0) sm.item = (int)atomicAdd(&ctr[kCtrHub2Work], 1u);
+        if (threadIdx.x == 0) {
+            int w = -1;          // >= 0: giant item, <= -2: regular item -(w + 2), -1: nothing left
+            if (prefer_giant && total_g > 0) {
+                const uint32_t g = atomicAdd(&ctr[kCtrHub2Giant], 1u);
+                if (g < total_g) w = (int)g;
+            }
+            if (w == -1 && total_r > 0) {
+                const uint32_t q = atomicAdd(&ctr[kCtrHub2Work], 1u);
+                if (q < total_r) w = -(int)q - 2;
+            }
+            *item = w;
+        }
         __syncthreads();
-        const uint32_t work = (uint32_t)sm.item;
+        const int work = *item;
         __syncthreads();
-        if (work >= total) break;
-        const uint32_t hub = work / slices;
-        const int slice = (int)(work - hub * slices);
+        if (work == -1) break;
+        const bool giant = work >= 0;
+        const uint32_t idx = giant ? (uint32_t)work : (uint32_t)(-(work + 2));
+        const int spr = giant ? spr_g : spr_r;
+        const int slice_w = giant ? slice_w_g : slice_w_r;
+        const uint32_t slices = giant ? slices_g : slices_r;
+        const uint32_t hub = idx / slices;
+        const int slice = (int)(idx - hub * slices);
         const int r = slice / spr;                      // source row 0..L-1 -> target layer r+1
         const int c0 = (slice - r * spr) * slice_w;     // first column of the slice inside the row
         const int width = min(rs, c0 + slice_w) - c0;   // floats, multiple of 4
-        const int head = (int)(hub < n_giant ? hub_giant[hub] : hub_reg[hub - n_giant]);
+        const int head = (int)(giant ? hub_giant[hub] : hub_reg[hub]);
         const int len = (int)slen[head];
         const uint32_t key = skey[head];
-        const int nblk = (len + 31) >> 5;
+        // a ring stage (8 KB) holds 32 messages of <= 64 floats, or — giants — 128 messages of <= 16 floats:
+        // four times fewer full/empty handshakes on the critical chain
+        const int spm = giant ? 4 : 1;                  // 32-message sub-blocks per stage
+        const int slot = giant ? kHub2GiantFloats : kHub2SlotFloats;      // floats between messages of a stage
+        const int mps = 32 * spm;                       // messages per stage
+        const int nblk = (len + mps - 1) / mps;
         if (width > 0) {
-            if (warp >= kHub2Consumers) {
+            if (warp >= 1) {
                 // ------------------------------------------------ producers
-                const int pw = warp - kHub2Consumers;
-                const int nvec = width >> 2;            // 16-byte pieces per message (<= 16)
-                const int half = lane >> 4, sub = lane & 15;
-                // metadata (source id, snapshot slot) of this lane's message, kept two rounds ahead
-                // in registers so that its L2 latency never sits in front of a stage fill
-                auto meta = [&](int b, uint32_t& v, uint32_t& x) {
-                    const int j = b * 32 + lane;
-                    v = 0u;
-                    x = 0u;
-                    if (j < len) {
-                        v = ssrc[head + j];
-                        if (r >= 1 || DIRECT) x = sslot[head + j];
-                    }
-                };
-                auto src_ptr = [&](uint32_t v, uint32_t x) -> const float* {
-                    if (DIRECT && (x & kDirect) != 0)   // received row: rows 0..L-1 contiguous in the state
-                        return st.data + (long long)v * st.node_stride + (long long)r * rs + c0;
-                    if (r == 0) return st.data + (long long)v * st.node_stride + c0;      // P_0: never written
-                    return snap + (long long)x * (long long)(L - 1) * rs + (long long)(r - 1) * rs + c0;
-                };
-                uint32_t v0, x0, v1, x1, v2, x2;
-                meta(pw, v0, x0);
-                meta(pw + kHub2Producers, v1, x1);
-                for (int b = pw; b < nblk; b += kHub2Producers) {
-                    meta(b + 2 * kHub2Producers, v2, x2);
-                    const uint32_t g = blk_base + (uint32_t)b;
-                    const int stage = (int)(g % kHub2Stages);
-                    const uint32_t use = g / kHub2Stages;
-                    if (use > 0) mbar_wait(&sm.empty[stage], (use - 1u) & 1u);
-                    const int nm = min(32, len - b * 32);
-                    if (lane < nm) cp_async4(&sm.wring[stage][lane], sw + head + b * 32 + lane);
-                    // this lane's piece of ITS message; lanes exchange pointers by shuffle so that one
-                    // LDGSTS instruction moves two whole messages (2 x 16 lanes x 16 B, coalesced)
-                    const unsigned long long mine = reinterpret_cast<unsigned long long>(src_ptr(v0, x0));
-                    const unsigned plo = (unsigned)mine, phi = (unsigned)(mine >> 32);
-                    float* dst = &sm.ring[stage][half][sub * 4];
-                    if (nm == 32) {
-#pragma unroll
-                        for (int jj = 0; jj < 32; jj += 2) {
-                            const unsigned lo = __shfl_sync(0xffffffffu, plo, jj + half);
-                            const unsigned hi = __shfl_sync(0xffffffffu, phi, jj + half);
-                            const float* pj = reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
-                            if (sub < nvec) cp_async16(dst + jj * kHub2SlotFloats, pj + sub * 4);
-                        }
-                    } else {
-                        for (int jj = 0; jj < nm; jj += 2) {
-                            const unsigned lo = __shfl_sync(0xffffffffu, plo, jj + half);
-                            const unsigned hi = __shfl_sync(0xffffffffu, phi, jj + half);
-                            const float* pj = reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
-                            if (jj + half < nm && sub < nvec) cp_async16(dst + jj * kHub2SlotFloats, pj + sub * 4);
-                        }
-                    }
-                    cp_async_mbar_arrive_noinc(&sm.full[stage]);
-                    v0 = v1; x0 = x1;
-                    v1 = v2; x1 = x2;
-                }
-            } else {
-                // ------------------------------------------------ consumer(s): 2 columns per lane
-                const int col = warp * 64 + 2 * lane;
-                const bool active = col < width;
-                float* tptr = st.data + (long long)key * st.node_stride + (long long)(r + 1) * rs + c0 + col;
-                // received source rows: this call's decay of source row r (P_0 never decays)
+                const int pw = warp - 1;
+                const int nvec = width >> 2;            // 16-byte pieces per message (<= 4 giant, <= 16 otherwise)
+                const int lpm_shift = giant ? 2 : 4;    // lanes per message: 4 or 16
+                const int grp = lane >> lpm_shift, sub = lane & ((1 << lpm_shift) - 1);
+                // received source rows (sharded state): this call's decay of source row r (P_0 never decays)
                 const float dfac = (DIRECT && LAZY && dnow.has_decay && r >= 1)
                                        ? pick4(dnow.c[0], dnow.c[1], dnow.c[2], dnow.c[3], r - 1) : 1.0f;
+                const int mpi = 32 >> lpm_shift;              // messages per load instruction: 8 (giant) or 2
+                const int ipb = 32 / mpi;                     // load instructions per 32-message sub-block: 4 or 16
+                auto row_ptr = [&](uint32_t v, uint32_t x) -> const float* {
+                    if (DIRECT && (x & kDirect) != 0)         // received row: rows 0..L-1 contiguous in the state
+                        return st.data + (long long)v * st.node_stride + (long long)r * rs + c0;
+                    if (r == 0) return st.data + (long long)v * st.node_stride + c0;            // P_0: never written
+                    return snap + (long long)x * (long long)(L - 1) * rs + (long long)(r - 1) * rs + c0;
+                };
+                for (int b = pw; b < nblk; b += kHub2Producers) {
+                    const uint32_t g = blk_base + (uint32_t)b;
+                    const uint32_t use = g / (uint32_t)kHub2Stages;
+                    const int stage = (int)(g - use * (uint32_t)kHub2Stages);
+                    // (1) metadata of this lane's message in each sub-block of the stage (all in flight together)
+                    unsigned plo[4], phi[4];
+                    float wl[4], fl[4];
+#pragma unroll
+                    for (int sb = 0; sb < 4; ++sb) {
+                        const int j = (b * spm + sb) * 32 + lane;
+                        const float* ptr = st.data;
+                        wl[sb] = 0.f;
+                        fl[sb] = 1.0f;
+                        if (sb < spm && j < len) {
+                            const uint32_t v = ssrc[head + j];
+                            const uint32_t x = (r >= 1 || DIRECT) ? sslot[head + j] : 0u;
+                            float w = sw[head + j];
+                            if (DIRECT) {                     // sign bit of the weight = "received row"
+                                fl[sb] = __float_as_int(w) < 0 ? dfac : 1.0f;
+                                w = fabsf(w);
+                            }
+                            wl[sb] = w;
+                            ptr = row_ptr(v, x);
+                        }
+                        const unsigned long long mine = reinterpret_cast<unsigned long long>(ptr);
+                        plo[sb] = (unsigned)mine;
+                        phi[sb] = (unsigned)(mine >> 32);
+                    }
+                    // (2) 16 load instructions in flight: the whole stage (32 x 64 floats or 128 x 16 floats)
+                    const int nm = min(mps, len - b * mps);   // messages of this stage that exist
+                    float4 xv[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int sb = giant ? (q >> 2) : 0;
+                        const int i = giant ? (q & 3) : q;
+                        const int m = mpi * i + grp;                       // message inside the sub-block
+                        const unsigned lo = __shfl_sync(0xffffffffu, giant ? plo[q >> 2] : plo[0], m);
+                        const unsigned hi = __shfl_sync(0xffffffffu, giant ? phi[q >> 2] : phi[0], m);
+                        const float* pj = reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
+                        xv[q] = (sb * 32 + m < nm && sub < nvec) ? ld4(pj + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    // (3) the stage is free again? then scale and store
+                    if (use > 0) mbar_wait(&empty[stage], (use - 1u) & 1u);
+                    float* dst = ring + (size_t)stage * (32 * kHub2SlotFloats) + (size_t)grp * slot + sub * 4;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int sb = giant ? (q >> 2) : 0;
+                        const int i = giant ? (q & 3) : q;
+                        const int m = mpi * i + grp;
+                        const float w = __shfl_sync(0xffffffffu, giant ? wl[q >> 2] : wl[0], m);
+                        if (DIRECT) scale4(xv[q], __shfl_sync(0xffffffffu, giant ? fl[q >> 2] : fl[0], m));   // x * 1.0f is exact
+                        scale4(xv[q], w);
+                        if (sub < nvec) st4(dst + (size_t)(sb * 32 + mpi * i) * slot, xv[q]);
+                    }
+                    mbar_arrive(&full[stage]);         // release: this lane's stores are visible to the waiter
+                }
+            } else {
+                // ------------------------------------------------ consumer: 2 columns per lane
+                const int col = 2 * lane;
+                const bool active = col < width;
+                float* tptr = st.data + (long long)key * st.node_stride + (long long)(r + 1) * rs + c0 + col;
                 float2 acc = make_float2(0.f, 0.f);
                 if (active) {
                     acc = *reinterpret_cast<const float2*>(tptr);           // zeros if never written
@@ -1161,30 +1246,27 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                 }
                 for (int b = 0; b < nblk; ++b) {
                     const uint32_t g = blk_base + (uint32_t)b;
-                    const int stage = (int)(g % kHub2Stages);
-                    mbar_wait(&sm.full[stage], (g / kHub2Stages) & 1u);
-                    const int nm = min(32, len - b * 32);
-                    const float* xs = &sm.ring[stage][0][col];
-                    const float* ws_ = &sm.wring[stage][0];
-                    auto step = [&](int j) {
-                        float2 x = *reinterpret_cast<const float2*>(xs + j * kHub2SlotFloats);
-                        float w = ws_[j];
-                        if (DIRECT) {
-                            if (__float_as_int(w) < 0) {                   // sign bit: received row
-                                x = mul2_rn(x, dfac);
-                                w = fabsf(w);
-                            }
-                        }
-                        axpy2_rn(acc, x, w);
-                    };
-                    if (nm == 32) {
+                    const uint32_t use = g / (uint32_t)kHub2Stages;
+                    const int stage = (int)(g - use * (uint32_t)kHub2Stages);
+                    mbar_wait(&full[stage], use & 1u);
+                    const int nm = min(mps, len - b * mps);
+                    const float* xs = ring + (size_t)stage * (32 * kHub2SlotFloats) + col;
+                    int j0 = 0;
+                    for (; j0 + 32 <= nm; j0 += 32) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) step(j);
-                    } else {
-                        for (int j = 0; j < nm; ++j) step(j);
+                        for (int j = 0; j < 32; ++j) {
+                            const float2 p = *reinterpret_cast<const float2*>(xs + (j0 + j) * slot);
+                            acc.x = __fadd_rn(acc.x, p.x);
+                            acc.y = __fadd_rn(acc.y, p.y);
+                        }
+                    }
+                    for (; j0 < nm; ++j0) {
+                        const float2 p = *reinterpret_cast<const float2*>(xs + j0 * slot);
+                        acc.x = __fadd_rn(acc.x, p.x);
+                        acc.y = __fadd_rn(acc.y, p.y);
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.empty[stage]);
+                    if (lane == 0) mbar_arrive(&empty[stage]);
                 }
                 if (active) *reinterpret_cast<float2*>(tptr) = acc;
             }
@@ -1196,7 +1278,7 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
 template <bool DIRECT>
 int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const DecayArgs& dnow, cudaStream_t stream) {
     static bool configured = false;
-    const int smem = (int)sizeof(Hub2Smem);
+    const int smem = (int)hub2_smem_bytes();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(walk_hub2_kernel<false, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess)
@@ -1208,17 +1290,19 @@ int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const D
         configured = true;
     }
     const int rs = (int)v.row_stride;
-    const int spr = (rs + kHub2SlotFloats - 1) / kHub2SlotFloats;          // slices per row
-    const int slice_w = (((rs + spr - 1) / spr) + 3) & ~3;
-    const unsigned grid = 148 * 3;
+    const int spr_r = (rs + kHub2SlotFloats - 1) / kHub2SlotFloats;       // slices per row: regular hubs (<= 64 floats)
+    const int slice_w_r = (((rs + spr_r - 1) / spr_r) + 3) & ~3;
+    const int spr_g = (rs + kHub2GiantFloats - 1) / kHub2GiantFloats;     // giants (<= 32 floats)
+    const int slice_w_g = (((rs + spr_g - 1) / spr_g) + 3) & ~3;
+    const unsigned grid = 148 * 2;                                        // 2 CTAs (96 KB of ring each) per SM
     if (lazy)
         walk_hub2_kernel<true, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                              ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
-                                                                             spr, slice_w, dnow);
+                                                                             spr_g, slice_w_g, spr_r, slice_w_r, dnow);
     else
         walk_hub2_kernel<false, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                               ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
-                                                                              spr, slice_w, dnow);
+                                                                              spr_g, slice_w_g, spr_r, slice_w_r, dnow);
     return TPN_OK;
 }
 
@@ -1256,6 +1340,29 @@ void launch_walk_small(const StateView& v, const Workspace& ws, int E, int ds4, 
         case 5: launch_walk_small_v<5, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
         default: launch_walk_small_v<6, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
     }
+}
+
+// Library-owned side stream per device: the hub walker runs on it concurrently with the
+// short-segment walker (disjoint target rows), forked from / joined back into the caller's stream
+// with events, so the caller still sees one stream-ordered call (also valid under graph capture).
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int state = 0;          // 0: not created, 1: ready, -1: creation failed (run serially)
+};
+SideStream* side_stream() {
+    static SideStream table[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& s = table[dev];
+    if (s.state == 0) {
+        bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) (void)cudaGetLastError();
+        s.state = ok ? 1 : -1;
+    }
+    return s.state == 1 ? &s : nullptr;
 }
 
 template <bool ALL>
@@ -1391,8 +1498,10 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
         uint32_t *kin = ws.key_a, *kout = ws.key_b, *vin = ws.val_a, *vout = ws.val_b;
         for (int p = 0; p < passes; ++p) {
             radix_hist_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, E, 8 * p, ws.hist, nblk);
-            radix_scan_kernel<<<1, 1024, 0, stream>>>(ws.hist, kRadixBins * nblk);
-            radix_scatter_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, vin, kout, vout, E, 8 * p, ws.hist, nblk);
+            const int prefixed = nblk > kRadixDirectBlocks ? 1 : 0;      // few tiles: the scatter sums the columns itself
+            if (prefixed) radix_prefix_kernel<<<kRadixBins / 8, 256, 0, stream>>>(ws.hist, nblk);
+            radix_scatter_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, vin, kout, vout, E, 8 * p, ws.hist, nblk,
+                                                                     prefixed);
             uint32_t* tk = kin; kin = kout; kout = tk;
             uint32_t* tv = vin; vin = vout; vout = tv;
         }
@@ -1404,6 +1513,7 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
                                                             ws.hub_reg, ws.small_heads, ws.ctr,
                                                             (lazy && !snapshot_path && L >= 2) ? ws.svst : nullptr,
                                                             st->stamps, L, E4, st->num_nodes, err_flag_dev);
+        if (snapshot_path) sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr);
         if (eager_sweep) {
             const long long want = (sweep_total4 + 255) / 256;
             const unsigned grid = (unsigned)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
@@ -1421,11 +1531,27 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
             // large batch: long segments on the CTA-pipelined hub walker, short ones on the
             // persistent warp walker (disjoint target rows; both read only pre-batch values)
             const bool direct = msgs.B == 0;
-            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, stream)
-                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, stream);
+            SideStream* side = (g_debug_flags & TPN_DEBUG_SERIAL_WALK) ? nullptr : side_stream();
+            cudaStream_t hub_stream = stream;
+            if (side != nullptr) {
+                if (cudaEventRecord(side->fork, stream) == cudaSuccess &&
+                    cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess)
+                    hub_stream = side->stream;
+                else
+                    (void)cudaGetLastError();
+            }
+            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, hub_stream)
+                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, hub_stream);
             if (hrc != TPN_OK) return hrc;
             if (direct) launch_walk_small<true>(view, ws, E, ds4, lazy, dargs, stream);
             else launch_walk_small<false>(view, ws, E, ds4, lazy, dargs, stream);
+            if (hub_stream != stream) {
+                if (cudaEventRecord(side->join, hub_stream) != cudaSuccess ||
+                    cudaStreamWaitEvent(stream, side->join, 0) != cudaSuccess) {
+                    set_cuda_error(cudaGetLastError());
+                    return TPN_ERR_CUDA;
+                }
+            }
         } else {
             // single-CTA sort path: one float4 per lane, a warp covers 512 contiguous bytes of the span
             const int span4 = L * ds4;

@@ -155,6 +155,7 @@ class ShardedRandomProjection(RandomProjectionModule):
                 self.random_projections[0][:self.n_local].copy_(mine)
         self.exchanged_rows = 0          # rows received so far (bench accounting)
         self._send_buf: Optional[torch.Tensor] = None
+        self._all_keep: Optional[np.ndarray] = None
 
     # ------------------------------------------------------------------ helpers
     def init_p0_on_device(self, seed: int) -> None:
@@ -204,6 +205,9 @@ class ShardedRandomProjection(RandomProjectionModule):
 
     def update(self, src_node_ids, dst_node_ids, node_interact_times, next_time=None, plan=None):
         """TPNet.py:67-99 on the sharded state.  All ranks must call it with the same batch."""
+        if self.world == 1 and plan is None:
+            # one shard = the whole graph: the plain edge-batch path (no message list, no exchange)
+            return RandomProjectionModule.update(self, src_node_ids, dst_node_ids, node_interact_times, next_time)
         dev = self._require_cuda()
         lib = _lib.load()
         t = np.asarray(node_interact_times, dtype=np.float64)
@@ -277,6 +281,11 @@ class ShardedRandomProjection(RandomProjectionModule):
     def pair_wise_gram(self, src_node_ids, dst_node_ids, plan: Optional[ShardPlan] = None):
         """Features (input of self.mlp, TPNet.py:119-128) of the pairs whose first endpoint this
         rank owns.  Returns (positions in the batch, float32 [m, (2L+2)^2])."""
+        if self.world == 1 and plan is None:
+            n = int(len(src_node_ids))
+            if self._all_keep is None or self._all_keep.shape[0] != n:
+                self._all_keep = np.arange(n)
+            return self._all_keep, RandomProjectionModule.pair_wise_gram(self, src_node_ids, dst_node_ids)
         dev = self._require_cuda()
         lib = _lib.load()
         if plan is None:
