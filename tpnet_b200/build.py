@@ -29,6 +29,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_flags() -> List[str]:
+    # profiling builds, e.g. TPN_EXTRA_NVCC_FLAGS=-DTPN_HUB2_TIMELINE
+    return os.environ.get('TPN_EXTRA_NVCC_FLAGS', '').split()
+
+
 def _nvcc() -> str:
     cand = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     if not os.path.exists(cand):
@@ -48,7 +53,7 @@ def _fingerprint() -> str:
         h.update(f.encode())
         with open(f, 'rb') as fh:
             h.update(fh.read())
-    h.update(' '.join(NVCC_FLAGS).encode())
+    h.update(' '.join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -66,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     log = []
     for src in _sources():
         obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + '.o')
-        cmd = [nvcc, *NVCC_FLAGS, '-I', os.path.join(ROOT, 'include'), '-I', CSRC, '-c', src, '-o', obj]
+        cmd = [nvcc, *NVCC_FLAGS, *_extra_flags(), '-I', os.path.join(ROOT, 'include'), '-I', CSRC, '-c', src, '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)
         if r.returncode != 0:

@@ -1084,6 +1084,16 @@ walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_
 // and taken only by ONE CTA per SM (first CTA to claim its SM), so a critical chain never shares
 // its SM's load/store path with another; everything else uses <= 64-float slices.  CTAs pull work
 // items from atomic counters.  Shared memory: ring[stages][32][64] floats | full | empty | item.
+#ifdef TPN_HUB2_TIMELINE
+// profiling build only (-DTPN_HUB2_TIMELINE): SM-clock timestamps of the first giant work item,
+// [warp][pass][event]; read with tpn_debug_hub_timeline (not part of the shipped ABI)
+__device__ unsigned long long g_hub2_timeline[8 * 256 * 8];
+#define HUB2_STAMP(pass, ev) \
+    do { if (work == 0 && lane == 0 && (pass) < 256) g_hub2_timeline[(warp * 256 + (pass)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define HUB2_STAMP(pass, ev) do { } while (0)
+#endif
+
 __host__ __device__ inline size_t hub2_smem_bytes() {
     return (size_t)kHub2Stages * (32 * kHub2SlotFloats * 4 + 16) + 16;
 }
@@ -1179,6 +1189,8 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                     const uint32_t g = blk_base + (uint32_t)b;
                     const uint32_t use = g / (uint32_t)kHub2Stages;
                     const int stage = (int)(g - use * (uint32_t)kHub2Stages);
+                    const int pass = b / kHub2Producers;
+                    HUB2_STAMP(pass, 0);
                     // (1) metadata of this lane's message in each sub-block of the stage (all in flight together)
                     unsigned plo[4], phi[4];
                     float wl[4], fl[4];
@@ -1205,6 +1217,7 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                     }
                     // (2) 16 load instructions in flight: the whole stage (32 x 64 floats or 128 x 16 floats)
                     const int nm = min(mps, len - b * mps);   // messages of this stage that exist
+                    HUB2_STAMP(pass, 1);
                     float4 xv[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
@@ -1217,8 +1230,14 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                         xv[q] = (sb * 32 + m < nm && sub < nvec) ? ld4(pj + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     // (3) the stage is free again? then scale and store
+                    HUB2_STAMP(pass, 2);
                     if (use > 0) mbar_wait(&empty[stage], (use - 1u) & 1u);
+                    HUB2_STAMP(pass, 3);
                     float* dst = ring + (size_t)stage * (32 * kHub2SlotFloats) + (size_t)grp * slot + sub * 4;
+#ifdef TPN_HUB2_TIMELINE
+                    if (xv[0].x == 12345.678f) HUB2_STAMP(pass, 7);      // touch the first row so that stamp 4 sees its arrival
+                    HUB2_STAMP(pass, 4);
+#endif
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
                         const int sb = giant ? (q >> 2) : 0;
@@ -1229,16 +1248,22 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                         scale4(xv[q], w);
                         if (sub < nvec) st4(dst + (size_t)(sb * 32 + mpi * i) * slot, xv[q]);
                     }
+                    HUB2_STAMP(pass, 5);
                     mbar_arrive(&full[stage]);         // release: this lane's stores are visible to the waiter
+                    HUB2_STAMP(pass, 6);
                 }
             } else {
-                // ------------------------------------------------ consumer: 2 columns per lane
-                const int col = 2 * lane;
+                // ------------------------------------------------ consumer
+                // regular slices (<= 64 floats): 2 columns per lane; giant slices (<= 16 floats): ONE column
+                // per lane — per message one LDS + one FADD, so the warp issues less than the 4-cycle
+                // latency of the add chain it is bound by
+                const int col = giant ? lane : 2 * lane;
                 const bool active = col < width;
                 float* tptr = st.data + (long long)key * st.node_stride + (long long)(r + 1) * rs + c0 + col;
                 float2 acc = make_float2(0.f, 0.f);
                 if (active) {
-                    acc = *reinterpret_cast<const float2*>(tptr);           // zeros if never written
+                    if (giant) acc.x = *tptr;
+                    else acc = *reinterpret_cast<const float2*>(tptr);      // zeros if never written
                     if (LAZY) {
                         const int ts = st.stamps[(long long)key * L + r];
                         if (ts >= 0) acc = mul2_rn(acc, decay_factor(st, r, ts));
@@ -1248,27 +1273,42 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                     const uint32_t g = blk_base + (uint32_t)b;
                     const uint32_t use = g / (uint32_t)kHub2Stages;
                     const int stage = (int)(g - use * (uint32_t)kHub2Stages);
+                    HUB2_STAMP(b, 0);
                     mbar_wait(&full[stage], use & 1u);
+                    HUB2_STAMP(b, 1);
                     const int nm = min(mps, len - b * mps);
                     const float* xs = ring + (size_t)stage * (32 * kHub2SlotFloats) + col;
                     int j0 = 0;
-                    for (; j0 + 32 <= nm; j0 += 32) {
+                    if (giant) {
+                        for (; j0 + 32 <= nm; j0 += 32) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float2 p = *reinterpret_cast<const float2*>(xs + (j0 + j) * slot);
+                            for (int j = 0; j < 32; ++j) acc.x = __fadd_rn(acc.x, xs[(j0 + j) * kHub2GiantFloats]);
+                        }
+                        for (; j0 < nm; ++j0) acc.x = __fadd_rn(acc.x, xs[j0 * kHub2GiantFloats]);
+                    } else {
+                        for (; j0 + 32 <= nm; j0 += 32) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float2 p = *reinterpret_cast<const float2*>(xs + (j0 + j) * kHub2SlotFloats);
+                                acc.x = __fadd_rn(acc.x, p.x);
+                                acc.y = __fadd_rn(acc.y, p.y);
+                            }
+                        }
+                        for (; j0 < nm; ++j0) {
+                            const float2 p = *reinterpret_cast<const float2*>(xs + j0 * kHub2SlotFloats);
                             acc.x = __fadd_rn(acc.x, p.x);
                             acc.y = __fadd_rn(acc.y, p.y);
                         }
                     }
-                    for (; j0 < nm; ++j0) {
-                        const float2 p = *reinterpret_cast<const float2*>(xs + j0 * slot);
-                        acc.x = __fadd_rn(acc.x, p.x);
-                        acc.y = __fadd_rn(acc.y, p.y);
-                    }
+                    HUB2_STAMP(b, 2);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[stage]);
+                    HUB2_STAMP(b, 3);
                 }
-                if (active) *reinterpret_cast<float2*>(tptr) = acc;
+                if (active) {
+                    if (giant) *tptr = acc.x;
+                    else *reinterpret_cast<float2*>(tptr) = acc;
+                }
             }
         }
         blk_base += (width > 0) ? (uint32_t)nblk : 0u;
@@ -1294,7 +1334,7 @@ int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const D
     const int slice_w_r = (((rs + spr_r - 1) / spr_r) + 3) & ~3;
     const int spr_g = (rs + kHub2GiantFloats - 1) / kHub2GiantFloats;     // giants (<= 32 floats)
     const int slice_w_g = (((rs + spr_g - 1) / spr_g) + 3) & ~3;
-    const unsigned grid = 148 * 2;                                        // 2 CTAs (96 KB of ring each) per SM
+    const unsigned grid = 148 * 2;                                        // 2 CTAs (88 KB of ring each) per SM
     if (lazy)
         walk_hub2_kernel<true, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                              ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
@@ -1586,6 +1626,15 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
 
 }  // namespace
 }  // namespace tpn
+
+#ifdef TPN_HUB2_TIMELINE
+extern "C" int tpn_debug_hub_timeline(unsigned long long* host_out, size_t count) {
+    const size_t have = sizeof(tpn::g_hub2_timeline) / sizeof(unsigned long long);
+    if (host_out == nullptr || count > have) return TPN_ERR_INVALID_ARGUMENT;
+    return cudaMemcpyFromSymbol(host_out, tpn::g_hub2_timeline, count * sizeof(unsigned long long)) == cudaSuccess
+               ? TPN_OK : TPN_ERR_CUDA;
+}
+#endif
 
 extern "C" int tpn_set_debug_flags(int flags) {
     const int old = tpn::g_debug_flags;
