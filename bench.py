@@ -35,7 +35,8 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from tpnet_b200.synth import SHAPES, RecentNeighbors, edge_stream, tpnet_pair_lists  # noqa: E402
+from tpnet_b200.synth import (SHAPES, RecentNeighbors, edge_stream, tpnet_neighbor_batch,  # noqa: E402
+                               tpnet_pair_lists)
 
 BATCH = 200                 # TPNet batch (configs[0..2])
 NUM_NEIGHBORS = 20
@@ -141,7 +142,8 @@ def make_steps(shape, n_steps, seed, warm=WARM_BATCHES):
             neg = rng.integers(lo, hi, BATCH).astype(np.int64)          # random negative sampling
             pa, pb = tpnet_pair_lists(nbr, s, d)
             na, nb = tpnet_pair_lists(nbr, s, neg)
-            steps.append(dict(src=s, dst=d, t=t, neg=neg, enc_pos=(pa, pb), enc_neg=(na, nb)))
+            steps.append(dict(src=s, dst=d, t=t, neg=neg, enc_pos=(pa, pb), enc_neg=(na, nb),
+                              nbr_pos=tpnet_neighbor_batch(nbr, s, d), nbr_neg=tpnet_neighbor_batch(nbr, s, neg)))
         nbr.insert(s, d)
     return warm_batches, steps
 
@@ -191,15 +193,15 @@ def to_dev(st, device):
     g = lambda a, dt: torch.from_numpy(a).to(device=device, dtype=dt)     # noqa: E731
     return dict(src=g(st['src'], torch.int64), dst=g(st['dst'], torch.int64), t=g(st['t'], torch.float64),
                 neg=g(st['neg'], torch.int64), t_last=float(st['t'][-1]),
-                enc_pos=tuple(g(a, torch.int64) for a in st['enc_pos']),
-                enc_neg=tuple(g(a, torch.int64) for a in st['enc_neg']))
+                nbr_pos=tuple(g(a, torch.int64) for a in st['nbr_pos']),
+                nbr_neg=tuple(g(a, torch.int64) for a in st['nbr_neg']))
 
 
 def resident_step(m, ds):
     """One step with device-resident inputs: kernels only (no head, no H2D).  The feature
     tensors are dropped at once: inside a capture their memory returns to the graph pool."""
-    m.pair_wise_gram(*ds['enc_pos'])
-    m.pair_wise_gram(*ds['enc_neg'])
+    m.neighbor_pair_wise_gram(*ds['nbr_pos'])      # encoder: [2B, K, 2, F] = 4BK pair blocks (TPNet.py:313-324)
+    m.neighbor_pair_wise_gram(*ds['nbr_neg'])
     m.pair_wise_gram(ds['src'], ds['dst'])
     m.pair_wise_gram(ds['src'], ds['neg'])
     m.update(ds['src'], ds['dst'], ds['t'], next_time=ds['t_last'])
@@ -208,8 +210,8 @@ def resident_step(m, ds):
 def api_step(m, st):
     """One step through the public numpy API, head included, scalar result read back."""
     with torch.no_grad():
-        m.get_pair_wise_feature(*st['enc_pos'])                # encoder features (feed the Mixer in TPNet)
-        m.get_pair_wise_feature(*st['enc_neg'])
+        m.get_neighbor_pair_wise_feature(*st['nbr_pos'])       # encoder features (feed the Mixer in TPNet)
+        m.get_neighbor_pair_wise_feature(*st['nbr_neg'])
         pos = m.get_pair_wise_feature(st['src'], st['dst'])    # decoder features -> the step's scalar result
         neg = m.get_pair_wise_feature(st['src'], st['neg'])
         m.update(st['src'], st['dst'], st['t'])
@@ -264,7 +266,7 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
         for k in range(n_pair):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, stream=side):
-                m.pair_wise_gram(*dsteps[W + k]['enc_pos'])
+                m.neighbor_pair_wise_gram(*dsteps[W + k]['nbr_pos'])
             pair_graphs.append(g)
     torch.cuda.synchronize()
     pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_pair)]
@@ -275,7 +277,7 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
         pev[k][1].record()
     torch.cuda.synchronize()
     pair_ms = float(np.mean([a.elapsed_time(b) for a, b in pev]))
-    pairs_per_launch = len(dsteps[0]['enc_pos'][0])
+    pairs_per_launch = 2 * dsteps[0]['nbr_pos'][0].numel()        # two pair blocks per (row, neighbour)
 
     api = steps[K + W:]
     for st in api[:W]:
@@ -286,7 +288,7 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
         api_step(m, st)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - e0) * 1e3
-    h2d = 2 * (2 * 4 * BATCH * NUM_NEIGHBORS * 8) + 2 * (2 * BATCH * 8) + 3 * BATCH * 8
+    h2d = 2 * ((2 * BATCH * NUM_NEIGHBORS + 4 * BATCH) * 8) + 2 * (2 * BATCH * 8) + 3 * BATCH * 8
 
     peak, peak_src = peak_gbs()
     achieved = pairs_per_launch * per_pair_B / (pair_ms * 1e-3) / 1e9
@@ -306,7 +308,7 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
                    'wall_ms_per_step_incl_flush': (wall1 - wall0) * 1e3 / K},
         'pairs_per_s': pps * K / (dev_ms * 1e-3),
         'algorithmic_GBps_step': step_bytes * K / (dev_ms * 1e-3) / 1e9,
-        'roofline': {'bound': 'hbm', 'kernel': 'tpn::pairwise_tma_kernel (4BK-pair encoder launch)',
+        'roofline': {'bound': 'hbm', 'kernel': 'tpn::pairwise_nbr_kernel (encoder launch: 2B rows x K neighbours = 4BK pair blocks)',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic_note('reddit_pairwise_dram_bytes_per_launch'), 'peak_source': peak_src,
                      'launch_us': pair_ms * 1e3, 'pairs_per_launch': pairs_per_launch,

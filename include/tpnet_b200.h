@@ -57,7 +57,7 @@
 extern "C" {
 #endif
 
-#define TPN_ABI_VERSION 3
+#define TPN_ABI_VERSION 4
 
 #define TPN_MAX_LAYERS 4
 
@@ -167,6 +167,28 @@ int tpn_gather_blocks(const tpn_state_t* st, const int64_t* ids_dev, int64_t n, 
  */
 int tpn_pairwise(const tpn_state_t* st, const int64_t* a_ids_dev, const int64_t* b_ids_dev, int64_t n,
                  int apply_log_scale, float* out_dev, void* stream);
+
+/*
+ * The encoder's structured pair-wise call — the index construction and re-split around
+ * get_pair_wise_feature at models/TPNet.py:313-324, without the trainable head:
+ *   for every row n < m and neighbour k < num_neighbors
+ *     out[n][k][0][:] = pair-wise block of (nbr[n][k], src[n])
+ *     out[n][k][1][:] = pair-wise block of (nbr[n][k], dst[n])
+ *   each block as tpn_pairwise writes it ((2L+2)^2 floats, rows [nbr:P_0..P_L, src|dst:P_0..P_L]).
+ * This is the reference's
+ *   get_pair_wise_feature(np.tile(nbr.reshape(-1), 2),
+ *                         np.concatenate([np.repeat(src, K), np.repeat(dst, K)]))
+ * followed by torch.cat([f[:m*K], f[m*K:]], dim=1).reshape(m, K, -1), with `self.mlp` applied
+ * by the caller to the [m*K*2, (2L+2)^2] view of `out` (the head acts on each block alone).
+ *   nbr_dev          : int64[m][num_neighbors] device (id 0 = padding neighbour: an ordinary row)
+ *   src_dev, dst_dev : int64[m] device
+ *   out_dev          : float32[m][num_neighbors][2][(2L+2)^2] device, 16-byte aligned
+ * Returns TPN_ERR_UNSUPPORTED when one node block does not fit the shared-memory staging
+ * (rows wider than ~8,000 floats, i.e. use_matrix on a large graph): call tpn_pairwise instead.
+ */
+int tpn_pairwise_neighbors(const tpn_state_t* st, const int64_t* nbr_dev, const int64_t* src_dev,
+                           const int64_t* dst_dev, int64_t m, int num_neighbors, int apply_log_scale,
+                           float* out_dev, void* stream);
 
 /*
  * RandomProjectionModule.get_random_projections — TPNet.py:101-110.

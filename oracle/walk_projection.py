@@ -179,6 +179,24 @@ class WalkProjectionOracle:
         g = np.where(g < 0, F32(0), g)
         return np.log(g + F32(1.0)).astype(F32)
 
+    def neighbor_pair_lists(self, nbr: np.ndarray, src: np.ndarray, dst: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """The two id lists the encoder builds at TPNet.py:313-316 for m rows with K neighbours:
+        ``np.tile(nbr.reshape(-1), 2)`` and ``concat(repeat(src, K), repeat(dst, K))``."""
+        k = nbr.shape[1]
+        a = np.tile(nbr.reshape(-1), 2)
+        b = np.concatenate([np.repeat(src, k), np.repeat(dst, k)])
+        return a.astype(np.int64), b.astype(np.int64)
+
+    def neighbor_pair_wise_gram(self, nbr: np.ndarray, src: np.ndarray, dst: np.ndarray, exact: bool = False
+                                ) -> np.ndarray:
+        """TPNet.py:313-324 without the head: the generic pair encoder over the 2mK pairs of
+        ``neighbor_pair_lists``, then ``cat([f[:mK], f[mK:]], dim=1).reshape(m, K, -1)`` -> [m, K, 2F]
+        (the head acts on each F-block separately, so it commutes with the re-split)."""
+        m, k = nbr.shape
+        a, b = self.neighbor_pair_lists(nbr, src, dst)
+        f = self.pair_wise_gram(a, b, exact=exact)
+        return np.concatenate([f[:m * k], f[m * k:]], axis=1).reshape(m, k, -1)
+
     def pair_norm_bound(self, a_ids: np.ndarray, b_ids: np.ndarray) -> np.ndarray:
         """sqrt(G_rr * G_cc) per output element — the Cauchy-Schwarz scale that
         fp32 summation-order noise of a dot product is proportional to."""

@@ -111,6 +111,35 @@ def run_case(name, *, node_num, edge_num, dim_factor, num_layer, lam, use_matrix
     for i in range(num_layer + 1):
         assert np.array_equal(gathered[i].numpy(), pinned.get_random_projections(pair_a)[i])
 
+    # the encoder's structured call, TPNet.py:313-324 verbatim (m rows, K neighbours, front-padded with id 0)
+    nrng = np.random.default_rng(1000 + seed)
+    m_rows, K = 10, 5 if num_layer != 3 else 6
+    nbr = nrng.integers(1, node_num, (m_rows, K)).astype(np.int64)
+    nbr[0, :] = 0
+    nbr[1, :3] = 0
+    nsrc = nrng.integers(1, node_num, m_rows).astype(np.int64)
+    ndst = nrng.integers(1, node_num, m_rows).astype(np.int64)
+    nbr[2, -1] = nsrc[2]                                   # a neighbour that is the row's own source
+    ndst[3] = nsrc[3]                                      # src == dst
+    with torch.no_grad():
+        concat_neighbor_random_features = ref.get_pair_wise_feature(
+            src_node_ids=np.tile(nbr.reshape(-1), 2),
+            dst_node_ids=np.concatenate([np.repeat(nsrc, K), np.repeat(ndst, K)]))
+        neighbor_random_features = torch.cat(
+            [concat_neighbor_random_features[:m_rows * K], concat_neighbor_random_features[m_rows * K:]],
+            dim=1).reshape(m_rows, K, -1)
+    nfeat = neighbor_random_features.numpy().copy()
+    out['nbr'], out['nbr_src'], out['nbr_dst'], out['nbr_feat'] = nbr, nsrc, ndst, nfeat
+    o_nfeat = pinned.neighbor_pair_wise_gram(nbr, nsrc, ndst)
+    assert o_nfeat.shape == nfeat.shape
+    la, lb = pinned.neighbor_pair_lists(nbr, nsrc, ndst)
+    nscale = pinned.pair_norm_bound(la, lb)
+    nscale = np.concatenate([nscale[:m_rows * K], nscale[m_rows * K:]], axis=1).reshape(m_rows, K, -1)
+    if not_scale:
+        assert np.all(np.abs(o_nfeat - nfeat) <= 1e-5 * np.abs(nfeat) + 2e-6 * nscale), f'{name}: neighbour gram'
+    else:
+        np.testing.assert_allclose(o_nfeat, nfeat, rtol=1e-5, atol=2e-6)
+
     if saved is not None:
         ref.reload_random_projections(saved)
         pinned.reload(saved_or)

@@ -110,6 +110,103 @@ def test_pairwise_and_gather_match_reference_fixture(name, mode):
     assert torch.allclose(full, m.mlp(torch.from_numpy(got).to(DEV)))
 
 
+def nbr_tol(o, nbr, src, dst, ref, not_scale):
+    """Per-element tolerance of the [m, K, 2F] neighbour features (same rule as pair_tol)."""
+    m, k = nbr.shape
+    a, b = o.neighbor_pair_lists(nbr, src, dst)
+    keep = o.not_scale
+    o.not_scale = True
+    raw = o.pair_wise_gram(a, b, exact=True)
+    o.not_scale = keep
+    scale = o.pair_norm_bound(a, b) if not_scale else pair_tol(o, a, b, raw)
+    scale = np.concatenate([scale[:m * k], scale[m * k:]], axis=1).reshape(m, k, -1)
+    return 1e-5 * np.abs(ref) + 2e-6 * scale + 1e-7
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('name', CASES)
+def test_neighbor_pairwise_matches_reference_fixture(name, mode):
+    """tpn_pairwise_neighbors vs the reference's TPNet.py:313-324 output (fixture)."""
+    z, cfg, batches = load_case(name)
+    kw = oracle_kwargs(cfg)
+    m = module_from_cfg(kw, z['p0'], mode)
+    o = WalkProjectionOracle(p0=None if kw['use_matrix'] else z['p0'], **kw)
+    for s, d, t, w in batches:
+        m.update(s, d, t)
+        o.update(s, d, t, weights=w)
+    nbr, src, dst, ref = z['nbr'], z['nbr_src'], z['nbr_dst'], z['nbr_feat']
+    rows, k = nbr.shape
+    F = m.pair_wise_feature_dim
+    got = m.neighbor_pair_wise_gram(nbr, src, dst)
+    assert got.shape == (rows, k, 2, F)
+    got = got.cpu().numpy().reshape(rows, k, 2 * F)
+    tol = nbr_tol(o, nbr, src, dst, ref, kw['not_scale'])
+    assert np.all(np.abs(got - ref) <= tol), float(np.max(np.abs(got - ref) - tol))
+    with torch.no_grad():
+        full = m.get_neighbor_pair_wise_feature(nbr, src, dst)
+        a, b = o.neighbor_pair_lists(nbr, src, dst)
+        generic = m.get_pair_wise_feature(a, b)                      # the reference's own call sequence
+        generic = torch.cat([generic[:rows * k], generic[rows * k:]], dim=1).reshape(rows, k, -1)
+    assert full.shape == (rows, k, 2 * F)
+    # same head on the same blocks (fp32 GEMM over a different batch shape: compare at the output's scale)
+    assert float((full - generic).abs().max()) <= 1e-5 * max(float(generic.abs().max()), 1.0)
+    m.check_errors()
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('N,dim,L,rows,K', [(3000, 140, 3, 400, 20), (500, 120, 2, 37, 7), (800, 210, 3, 64, 33),
+                                            (300, 64, 1, 50, 1), (200, 36, 4, 21, 10)])
+def test_neighbor_pairwise_vs_oracle(N, dim, L, rows, K, mode):
+    """TPNet batch shape (2B rows x K neighbours) and ragged K (not a multiple of 4, more than one
+    pass per warp) against the oracle; device-resident ids; structural identities."""
+    rng = np.random.default_rng(5)
+    kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=1e-5, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=dim)
+    o = WalkProjectionOracle(**kw)
+    m = module_from_cfg(kw, o.P[0], mode)
+    for s, d, t in stream(rng, N, 600, 5, 1.25):
+        o.update(s, d, t)
+        m.update(s, d, t)
+    nbr = rng.integers(0, N, (rows, K)).astype(np.int64)
+    nbr[0, :] = 0                                             # an all-padding row
+    nbr[1, :K // 2] = 0                                       # front padding, as the `recent` sampler pads
+    src = rng.integers(1, N, rows).astype(np.int64)
+    dst = rng.integers(1, N, rows).astype(np.int64)
+    dst[2] = src[2]
+    nbr[3, -1] = src[3]
+    F = (2 * L + 2) ** 2
+    ref = o.neighbor_pair_wise_gram(nbr, src, dst)
+    got = m.neighbor_pair_wise_gram(nbr, src, dst).cpu().numpy().reshape(rows, K, 2 * F)
+    tol = nbr_tol(o, nbr, src, dst, ref, False)
+    assert np.all(np.abs(got - ref) <= tol), float(np.max(np.abs(got - ref) - tol))
+    # device-resident ids give the same bits
+    dev_ids = [torch.from_numpy(x).to(DEV) for x in (nbr, src, dst)]
+    again = m.neighbor_pair_wise_gram(*dev_ids).cpu().numpy().reshape(rows, K, 2 * F)
+    assert np.array_equal(again, got)
+    # structure: every block is symmetric; the W.W corner is shared by both blocks of (n, k); the
+    # S.S / D.D corner is shared by all K neighbours of a row; src == dst gives two equal blocks
+    g = got.reshape(rows, K, 2, 2 * L + 2, 2 * L + 2)
+    H = L + 1
+    assert np.array_equal(g, g.transpose(0, 1, 2, 4, 3))
+    assert np.array_equal(g[:, :, 0, :H, :H], g[:, :, 1, :H, :H])
+    assert np.array_equal(g[:, :, :, H:, H:], np.broadcast_to(g[:, :1, :, H:, H:], g[:, :, :, H:, H:].shape))
+    assert np.array_equal(g[2, :, 0], g[2, :, 1])
+    # raw (not_scale) features
+    m.not_scale = True
+    o.not_scale = True
+    raw_ref = o.neighbor_pair_wise_gram(nbr, src, dst)
+    raw = m.neighbor_pair_wise_gram(nbr, src, dst).cpu().numpy().reshape(rows, K, 2 * F)
+    tolr = nbr_tol(o, nbr, src, dst, raw_ref, True)
+    assert np.all(np.abs(raw - raw_ref) <= tolr)
+    # empty inputs
+    assert m.neighbor_pair_wise_gram(np.zeros((0, K), np.int64), src[:0], dst[:0]).shape == (0, K, 2, F)
+    with pytest.raises(IndexError):
+        bad = nbr.copy()
+        bad[5, 0] = N
+        m.neighbor_pair_wise_gram(bad, src, dst)
+    m.check_errors()
+
+
 @pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('name', ['wiki_tiny', 'flights_tiny'])
 def test_backup_reload_match_reference_fixture(name, mode):

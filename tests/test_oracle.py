@@ -62,6 +62,32 @@ def test_oracle_pairwise_and_gather(name):
     assert len(rows) == kw['num_layer'] + 1 and rows[0].shape == (len(a), o.dim)
 
 
+@pytest.mark.parametrize('name', CASES)
+def test_oracle_neighbor_pairwise_matches_reference_fixture(name):
+    """TPNet.py:313-324 (index lists + re-split) restated in the oracle vs the reference's output."""
+    z, cfg, batches = load_case(name)
+    kw = oracle_kwargs(cfg)
+    o = WalkProjectionOracle(p0=None if kw['use_matrix'] else z['p0'], **kw)
+    for s, d, t, w in batches:
+        o.update(s, d, t, weights=w)
+    nbr, src, dst, ref = z['nbr'], z['nbr_src'], z['nbr_dst'], z['nbr_feat']
+    m, k = nbr.shape
+    F = (2 * kw['num_layer'] + 2) ** 2
+    got = o.neighbor_pair_wise_gram(nbr, src, dst)
+    assert got.shape == ref.shape == (m, k, 2 * F)
+    a, b = o.neighbor_pair_lists(nbr, src, dst)
+    assert len(a) == len(b) == 2 * m * k
+    if kw['not_scale']:
+        scale = o.pair_norm_bound(a, b)
+        scale = np.concatenate([scale[:m * k], scale[m * k:]], axis=1).reshape(m, k, -1)
+        assert np.all(np.abs(got - ref) <= 1e-5 * np.abs(ref) + 2e-6 * scale)
+    else:
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6)
+    # block [n, k, 0] is the pair (nbr[n,k], src[n]); block [n, k, 1] the pair (nbr[n,k], dst[n])
+    one = o.pair_wise_gram(nbr[4], np.repeat(dst[4], k))
+    assert np.array_equal(got[4, :, F:], one)
+
+
 @pytest.mark.parametrize('name', ['wiki_tiny', 'flights_tiny'])
 def test_oracle_backup_reload(name):
     z, cfg, batches = load_case(name)

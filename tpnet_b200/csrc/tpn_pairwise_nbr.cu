@@ -23,7 +23,7 @@
 namespace tpn {
 namespace {
 
-constexpr int kNbrMaxWarps = 8;
+constexpr int kNbrMaxWarps = 5;     // K = 20 (the reference default) = 5 quads: one pass, 3 CTAs per SM
 constexpr int kNbrG = 8;            // lanes per neighbour
 constexpr int kNbrPPW = 4;          // neighbours per warp pass
 
@@ -77,7 +77,7 @@ __device__ __forceinline__ float epilogue(float g, int apply_log_scale) {
 }
 
 template <int LAYERS, bool LAZY>
-__global__ void __launch_bounds__(kNbrMaxWarps * 32)
+__global__ void __launch_bounds__(kNbrMaxWarps * 32, LAYERS <= 3 ? 3 : 2)
 pairwise_nbr_kernel(StateView st, const long long* __restrict__ nbr, const long long* __restrict__ src,
                     const long long* __restrict__ dst, int K, int apply_log_scale, float* __restrict__ out,
                     int ds4, uint32_t warp_bytes) {
@@ -270,7 +270,7 @@ int launch_nbr(const StateView& v, const long long* nbr, const long long* src, c
     constexpr int F = 4 * (LAYERS + 1) * (LAYERS + 1);
     const size_t block_bytes = (size_t)(LAYERS + 1) * v.row_stride * 4;
     const size_t wb = nbr_warp_bytes(block_bytes, F);
-    const size_t budget = 100 * 1024;               // two CTAs per SM
+    const size_t budget = (LAYERS <= 3 ? 72 : 100) * 1024;      // three (two) CTAs per SM
     if ((block_bytes & 15) != 0 || (v.node_stride & 3) != 0 || 2 * block_bytes + wb > 200 * 1024)
         return TPN_ERR_UNSUPPORTED;                 // rows too wide for the shared-memory staging
     int nw = (K + kNbrPPW - 1) / kNbrPPW;

@@ -386,6 +386,50 @@ class RandomProjectionModule(nn.Module):
         (the projections are ``requires_grad=False``)."""
         return self.mlp(self.pair_wise_gram(src_node_ids, dst_node_ids))
 
+    def neighbor_pair_wise_gram(self, neighbor_node_ids: IdArray, src_node_ids: IdArray,
+                                dst_node_ids: IdArray) -> torch.Tensor:
+        """Input of ``self.mlp`` for the encoder's structured call (TPNet.py:313-324), as
+        ``[m, K, 2, F]``: block ``[n, k, 0]`` is the pair ``(nbr[n, k], src[n])`` and block
+        ``[n, k, 1]`` the pair ``(nbr[n, k], dst[n])``.  One kernel, no index lists, no re-split."""
+        dev = self._require_cuda()
+        lib = _lib.load()
+        if neighbor_node_ids.ndim != 2:
+            raise ValueError('neighbor_node_ids must be [m, num_neighbors]')
+        m, k = int(neighbor_node_ids.shape[0]), int(neighbor_node_ids.shape[1])
+        if len(src_node_ids) != m or len(dst_node_ids) != m:
+            raise ValueError('src and dst id arrays must have one entry per row of neighbor_node_ids')
+        f = self.pair_wise_feature_dim
+        out = torch.empty(m, k, 2, f, dtype=torch.float32, device=dev)
+        if m == 0 or k == 0:
+            return out
+        flat = neighbor_node_ids.reshape(-1)
+        ptrs = self._ids_to_device([flat, src_node_ids, dst_node_ids], ['id', 'id', 'id'])
+        rc = lib.tpn_pairwise_neighbors(self._c_state(), ptrs[0], ptrs[1], ptrs[2], m, k, 0 if self.not_scale else 1,
+                                        out.data_ptr(), self._stream())
+        if rc == _lib.TPN_ERR_UNSUPPORTED:
+            # node blocks too wide for the shared-memory staging (use_matrix on a large graph):
+            # the generic pair kernel on device-built index lists, as TPNet.py:313-316 builds them
+            nb = torch.from_numpy(np.ascontiguousarray(flat)).to(dev) if isinstance(flat, np.ndarray) else flat
+            for j, ids in enumerate((src_node_ids, dst_node_ids)):
+                e = torch.from_numpy(np.ascontiguousarray(ids)).to(dev) if isinstance(ids, np.ndarray) else ids
+                out[:, :, j, :] = self.pair_wise_gram(nb, e.repeat_interleave(k).contiguous()).view(m, k, f)
+            return out
+        if rc:
+            _lib.check(rc, 'tpn_pairwise_neighbors')
+        self._h.launches += 1
+        return out
+
+    def get_neighbor_pair_wise_feature(self, neighbor_node_ids: IdArray, src_node_ids: IdArray,
+                                       dst_node_ids: IdArray) -> torch.Tensor:
+        """Drop-in for TPNet.py:313-324: returns ``neighbor_random_features`` ``[m, K, 2F]`` — what
+        the reference obtains from ``get_pair_wise_feature(np.tile(nbr.reshape(-1), 2),
+        np.concatenate([np.repeat(src, K), np.repeat(dst, K)]))`` followed by the split / ``cat`` /
+        ``reshape``.  ``self.mlp`` acts on every F-block on its own, so it is applied to the
+        ``[m*K*2, F]`` view (same values, same gradients to the head)."""
+        g = self.neighbor_pair_wise_gram(neighbor_node_ids, src_node_ids, dst_node_ids)
+        m, k = g.shape[0], g.shape[1]
+        return self.mlp(g.view(m * k * 2, self.pair_wise_feature_dim)).view(m, k, 2 * self.pair_wise_feature_dim)
+
     def reset_random_projections(self):
         """TPNet.py:131-139."""
         self._require_cuda()

@@ -109,12 +109,19 @@ class RecentNeighbors:
             tab[v, -1] = u
 
 
-def tpnet_pair_lists(nbr: RecentNeighbors, src: np.ndarray, dst: np.ndarray):
-    """The (a_ids, b_ids) of the encoder call for one (src, dst) batch — the index
-    construction of ``models/TPNet.py:206-219`` + ``:313-316``: 4*B*K pairs."""
+def tpnet_neighbor_batch(nbr: RecentNeighbors, src: np.ndarray, dst: np.ndarray):
+    """Inputs of the encoder's structured call for one (src, dst) batch (``models/TPNet.py:206-219``):
+    rows = concat(src, dst) (2B of them), their K recent neighbours, and the (src, dst) each row
+    is encoded against — ``(neighbours [2B, K], src tiled [2B], dst tiled [2B])``."""
     node_ids = np.concatenate([src, dst])
-    s2, d2 = np.tile(src, 2), np.tile(dst, 2)
-    neighbours = nbr.lookup(node_ids)                                   # [2B, K]
+    return (nbr.lookup(node_ids).astype(np.int64), np.tile(src, 2).astype(np.int64),
+            np.tile(dst, 2).astype(np.int64))
+
+
+def tpnet_pair_lists(nbr: RecentNeighbors, src: np.ndarray, dst: np.ndarray):
+    """The (a_ids, b_ids) the reference builds from that batch (``models/TPNet.py:313-316``):
+    4*B*K pairs."""
+    neighbours, s2, d2 = tpnet_neighbor_batch(nbr, src, dst)
     a = np.tile(neighbours.reshape(-1), 2)
     b = np.concatenate([np.repeat(s2, nbr.k), np.repeat(d2, nbr.k)])
     return a.astype(np.int64), b.astype(np.int64)
