@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument('--workload', default='powerlaw', choices=['powerlaw', 'reddit', 'wikipedia', 'flights'])
     ap.add_argument('--decay-mode', default='auto', choices=['auto', 'eager', 'lazy'])
     ap.add_argument('--no-flush', action='store_true', help='small shapes: keep L2 warm between steps')
+    ap.add_argument('--no-graphs', action='store_true', help='power-law, 1 GPU: launch the steps eagerly instead of as CUDA graphs')
     ap.add_argument('--no-also', action='store_true', help='N=1: skip the secondary Reddit-shaped measurement')
     ap.add_argument('--cpu-sample-steps', type=int, default=None)
     ap.add_argument('--warm-batches', type=int, default=None, help='untimed batches that fill the state')
@@ -435,8 +436,28 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
         resident_pairs(st, 'neg')
         resident_update(st)
 
-    for st in res[:W]:
-        resident(st)
+    # One GPU: every step is captured once into a CUDA graph and replayed once, in order (the host-side
+    # launch latency of the ~20 small kernels of a step would otherwise show up as idle gaps).
+    # Sharded: the all_to_all exchange stays an eager NCCL call.
+    use_graphs = world == 1 and not args.no_graphs
+    side = torch.cuda.Stream(device)
+    pool = torch.cuda.graph_pool_handle() if use_graphs else None
+
+    def capture(fn, *a):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=pool, stream=side):
+            fn(*a)
+        return g
+
+    if use_graphs:
+        with torch.cuda.stream(side):
+            graphs = [capture(resident, st) for st in res]
+        torch.cuda.synchronize()
+        run_step = lambda i: graphs[i].replay()              # noqa: E731
+    else:
+        run_step = lambda i: resident(res[i])                # noqa: E731
+    for i in range(W):
+        run_step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -446,7 +467,7 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
     wall0 = time.perf_counter()
     for k in range(K):
         ev[k][0].record()
-        resident(res[W + k])
+        run_step(W + k)
         ev[k][1].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -456,6 +477,8 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
     recv_rows_per_step = (m.exchanged_rows - rows0) / K
     m.check_errors()
     del res
+    if use_graphs:
+        del graphs
 
     # per-phase device time (events around each call) for the roofline of the dominant kernel
     t_pair, t_upd, n_pairs_local, n_msgs_local = [], [], 0, 0
@@ -464,11 +487,22 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
         if world > 1:
             dist.barrier()
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record()
-        n_pairs_local = resident_pairs(r, 'pos')
-        b.record()
-        n_msgs_local = resident_update(r)
-        c.record()
+        if use_graphs:
+            n_pairs_local, n_msgs_local = B, 2 * B
+            with torch.cuda.stream(side):
+                gp, gu = capture(resident_pairs, r, 'pos'), capture(resident_update, r)
+            torch.cuda.synchronize()
+            a.record()
+            gp.replay()
+            b.record()
+            gu.replay()
+            c.record()
+        else:
+            a.record()
+            n_pairs_local = resident_pairs(r, 'pos')
+            b.record()
+            n_msgs_local = resident_update(r)
+            c.record()
         torch.cuda.synchronize()
         t_pair.append(a.elapsed_time(b))
         t_upd.append(b.elapsed_time(c))
@@ -540,7 +574,8 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
                    'parallelism': 'single GPU' if world == 1 else
                    f'state sharded by node id over {world} GPUs, one all_to_all per call (NCCL)',
                    'l2': f'no flush needed: {state_gb:.1f} GB state >> 126 MB L2',
-                   'timing': 'CUDA events per step, max over ranks; routing plans are part of the resident inputs',
+                   'timing': ('CUDA events per step, one CUDA graph per step' if use_graphs else
+                              'CUDA events per step, max over ranks; routing plans are part of the resident inputs'),
                    'algorithmic_bytes_per_step': step_bytes, 'wall_ms_per_step': (wall1 - wall0) * 1e3 / K},
         'pairs_per_s': 2 * B * K / (dev_ms * 1e-3),
         'algorithmic_GBps_step': step_bytes * K / (dev_ms * 1e-3) / 1e9,

@@ -1,0 +1,15 @@
+set -x
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "pairwise or pair" 2>&1 | tail -5 )
+( timeout 600 python bench.py --no-also --cpu-sample-steps 1 ) > gpurun_out/bench_pl.json 2> gpurun_out/bench_pl.err; echo "bench rc=$?"
+tail -c 600 gpurun_out/bench_pl.err
+python - <<'PY'
+import json
+try:
+    d=json.load(open('gpurun_out/bench_pl.json'))
+    p=d['roofline']['phases']
+    print('ms/step', round(d['ms_per_step'],4), 'value', round(d['value']/1e6,1), 'M edges/s | pair ms', round(p['pairwise']['ms'],4), 'update ms', round(p['update']['ms'],4), '| e2e ms', round(d['e2e']['ms_per_step'],3))
+except Exception as e: print('no bench json', e)
+PY
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_pl.csv python bench.py --steps 2 --warmup 3 --no-also --cpu-sample-steps 1 > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
+python profiles/launch_summary.py gpurun_out/launches_pl.csv | grep -E "tpn::|launches" | head -8

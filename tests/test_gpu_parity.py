@@ -276,7 +276,8 @@ def test_update_bit_exact_with_equal_timestamps(B, N, dim, L, mode):
 @pytest.mark.parametrize('flags', [0, 1, 2], ids=['concurrent', 'per-layer', 'serial'])
 @pytest.mark.parametrize('mode', ['eager', 'lazy', 'lazy-frozen'])
 @pytest.mark.parametrize('B,N,dim,L,skew', [(6000, 300, 210, 3, 1.3), (2100, 50, 140, 3, 1.1), (9000, 2000, 36, 4, 1.5),
-                                            (5000, 40, 300, 1, 1.2), (3000, 30, 64, 2, 1.05), (4000, 60, 1000, 2, 1.3)])
+                                            (5000, 40, 300, 1, 1.2), (3000, 30, 64, 2, 1.05), (4000, 60, 1000, 2, 1.3),
+                                            (3000, 70000, 16, 2, 1.2)])      # 1, 2 and 3 radix passes
 def test_hub_walker_bit_exact(B, N, dim, L, skew, mode, flags):
     """Long segments (>= 64 messages on one target) leave the warp walker for the CTA-pipelined
     hub walkers (cp.async / TMA rings + mbarriers): giant (>= 2048) and regular hubs, 64-float
@@ -366,6 +367,41 @@ def test_update_and_pairwise_vs_oracle(B, N, dim, L, lam, mode):
     gs = m.pair_wise_gram(b, a).cpu().numpy().reshape(n, 2 * L + 2, 2 * L + 2)
     H = L + 1
     assert np.array_equal(gs[:, :H, :H], g[:, H:, H:]) and np.array_equal(gs[:, :H, H:], g[:, H:, :H])
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('N,dim,L,n', [(5000, 210, 3, 40003), (3000, 140, 3, 33000), (2000, 120, 2, 36001),
+                                       (1500, 64, 1, 32770), (1200, 72, 4, 34000)])
+def test_pairwise_large_call(N, dim, L, n, mode):
+    """Decoder-sized calls (tens of thousands of pairs, ragged tail): same bits as the same pairs
+    encoded in 5,000-pair calls, and the oracle's values."""
+    rng = np.random.default_rng(23)
+    kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=2e-5, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=dim)
+    o = WalkProjectionOracle(**kw)
+    m = module_from_cfg(kw, o.P[0], mode)
+    for s, d, t in stream(rng, N, 1500, 5, 1.25):
+        o.update(s, d, t)
+        m.update(s, d, t)
+    a = rng.integers(0, N, n).astype(np.int64)
+    b = rng.integers(0, N, n).astype(np.int64)
+    b[:100] = a[:100]
+    big = m.pair_wise_gram(a, b).cpu().numpy()
+    # >= 5,000-pair calls (same kernel, same 4-pair groups; the remainder rides with the last call)
+    cuts = list(range(0, n - 5000, 5000)) + [n]
+    small = np.concatenate([m.pair_wise_gram(a[i:j], b[i:j]).cpu().numpy() for i, j in zip(cuts[:-1], cuts[1:])])
+    assert np.array_equal(big, small)
+    ref = o.pair_wise_gram(a, b)
+    o.not_scale = True
+    raw = o.pair_wise_gram(a, b, exact=True)
+    tol = 1e-5 * np.abs(ref) + 2e-6 * pair_tol(o, a, b, raw) + 1e-7
+    assert np.all(np.abs(big - ref) <= tol), float(np.max(np.abs(big - ref) - tol))
+    assert np.all(np.abs(small - ref) <= tol)
+    g = big.reshape(n, 2 * L + 2, 2 * L + 2)
+    assert np.array_equal(g, g.transpose(0, 2, 1))
+    dev_ids = [torch.from_numpy(x).to(DEV) for x in (a, b)]
+    assert np.array_equal(m.pair_wise_gram(*dev_ids).cpu().numpy(), big)
+    m.check_errors()
 
 
 def test_lazy_matches_eager_and_log_restart(monkeypatch):

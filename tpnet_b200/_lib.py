@@ -115,6 +115,8 @@ def load() -> ctypes.CDLL:
     _declare(lib)
     if lib.tpn_version() != ABI_VERSION:
         raise RuntimeError(f'{LIB_PATH} has ABI version {lib.tpn_version()}, expected {ABI_VERSION}; rebuild')
+    if os.environ.get('TPN_DEBUG_FLAGS'):           # A/B measurements only (include/tpnet_b200.h, TPN_DEBUG_*)
+        lib.tpn_set_debug_flags(int(os.environ['TPN_DEBUG_FLAGS']))
     _lib = lib
     return lib
 

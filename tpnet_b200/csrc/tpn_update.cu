@@ -345,48 +345,68 @@ prep_small_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long 
 }
 
 // ---------------------------------------------------------------- large path
-__global__ void __launch_bounds__(256)
-prep_large_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long long num_nodes,
-                  float* __restrict__ w, uint32_t* __restrict__ key, uint32_t* __restrict__ val,
-                  int* __restrict__ err_flag, double* decay_log, int L, long long new_epoch, DecayArgs decay,
-                  uint32_t* __restrict__ ctr) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m == 0 && decay_log != nullptr && decay.has_decay) {
-        for (int l = 0; l < L; ++l) decay_log[new_epoch * L + l] = decay_log[(new_epoch - 1) * L + l] * (double)decay.c[l];
+struct PrepArgs {
+    MsgSource msgs;
+    int E;
+    float t_last_f, neg_lambda;
+    long long num_nodes;
+    float* w;
+    uint32_t* key;
+    uint32_t* val;
+    int* err_flag;
+    double* decay_log;
+    int L;
+    long long new_epoch;
+    DecayArgs decay;
+    uint32_t* ctr;
+};
+
+__device__ __forceinline__ void prep_body(const PrepArgs& a, int m) {
+    if (m == 0 && a.decay_log != nullptr && a.decay.has_decay) {
+        for (int l = 0; l < a.L; ++l)
+            a.decay_log[a.new_epoch * a.L + l] = a.decay_log[(a.new_epoch - 1) * a.L + l] * (double)a.decay.c[l];
     }
-    if (m < kCtrSlots) ctr[m] = 0;                       // hub lists, work counters and SM claims of this call
-    if (m >= E) return;
+    if (m < kCtrSlots) a.ctr[m] = 0;                     // hub lists, work counters and SM claims of this call
+    if (m >= a.E) return;
     long long tgt, oth;
     int widx;
-    msgs.get(m, tgt, oth, widx);
-    const bool ok = tgt >= 0 && tgt < num_nodes && oth >= 0 && oth < num_nodes;
-    if (!ok && err_flag != nullptr) *err_flag = 1;
-    const int n_w = msgs.B > 0 ? (int)msgs.B : E;
-    if (m < n_w) w[m] = edge_weight(msgs.t[m], t_last_f, neg_lambda);
-    key[m] = ok ? (uint32_t)tgt : (uint32_t)num_nodes;
-    val[m] = (uint32_t)m;
+    a.msgs.get(m, tgt, oth, widx);
+    const bool ok = tgt >= 0 && tgt < a.num_nodes && oth >= 0 && oth < a.num_nodes;
+    if (!ok && a.err_flag != nullptr) *a.err_flag = 1;
+    const int n_w = a.msgs.B > 0 ? (int)a.msgs.B : a.E;
+    if (m < n_w) a.w[m] = edge_weight(a.msgs.t[m], a.t_last_f, a.neg_lambda);
+    a.key[m] = ok ? (uint32_t)tgt : (uint32_t)a.num_nodes;
+    a.val[m] = (uint32_t)m;
 }
 
-__global__ void __launch_bounds__(kRadixThreads)
-radix_hist_kernel(const uint32_t* __restrict__ key, int E, int shift, uint32_t* __restrict__ hist, int nblk) {
-    __shared__ uint32_t bins[kRadixBins];
+__global__ void __launch_bounds__(256) prep_large_kernel(PrepArgs a) {
+    prep_body(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// one 2048-key tile: digit counts -> hist[tile][digit]  (bins: 256 shared counters)
+__device__ __forceinline__ void hist_tile(uint32_t* bins, const uint32_t* __restrict__ key, int E, int shift,
+                                          uint32_t* __restrict__ hist, int tile) {
     bins[threadIdx.x] = 0;
     __syncthreads();
-    const int base = blockIdx.x * kRadixTile;
+    const int base = tile * kRadixTile;
 #pragma unroll
     for (int i = 0; i < kRadixItems; ++i) {
         const int idx = base + i * kRadixThreads + threadIdx.x;
         if (idx < E) atomicAdd(&bins[(key[idx] >> shift) & 0xff], 1u);     // integer count: order-independent
     }
     __syncthreads();
-    hist[blockIdx.x * kRadixBins + threadIdx.x] = bins[threadIdx.x];     // [block][digit]
+    hist[tile * kRadixBins + threadIdx.x] = bins[threadIdx.x];     // [tile][digit]
+}
+
+__global__ void __launch_bounds__(kRadixThreads)
+radix_hist_kernel(const uint32_t* __restrict__ key, int E, int shift, uint32_t* __restrict__ hist, int nblk) {
+    __shared__ uint32_t bins[kRadixBins];
+    hist_tile(bins, key, E, shift, hist, blockIdx.x);
 }
 
 // Many tiles (nblk > kRadixDirectBlocks): per digit, the exclusive prefix over blocks and the digit
 // total, one warp per digit, in place ([block][digit] counts -> prefixes; totals in row nblk).
-__global__ void __launch_bounds__(256) radix_prefix_kernel(uint32_t* __restrict__ hist, int nblk) {
-    const int dgt = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void prefix_digit(uint32_t* __restrict__ hist, int nblk, int dgt, int lane) {
     uint32_t carry = 0;
     for (int b0 = 0; b0 < nblk; b0 += 32) {
         const int b = b0 + lane;
@@ -403,19 +423,30 @@ __global__ void __launch_bounds__(256) radix_prefix_kernel(uint32_t* __restrict_
     if (lane == 0) hist[nblk * kRadixBins + dgt] = carry;
 }
 
-__global__ void __launch_bounds__(kRadixThreads)
-radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
-                     uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, int E, int shift,
-                     const uint32_t* __restrict__ offs, int nblk, int prefixed) {
-    constexpr int kWarps = kRadixThreads / 32;
-    __shared__ uint32_t wcount[kWarps][kRadixBins + 1];
-    __shared__ uint32_t wtot[kWarps];
+__global__ void __launch_bounds__(256) radix_prefix_kernel(uint32_t* __restrict__ hist, int nblk) {
+    prefix_digit(hist, nblk, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
+constexpr int kRadixWarps = kRadixThreads / 32;
+struct ScatterSmem {
+    uint32_t wcount[kRadixWarps][kRadixBins + 1];
+    uint32_t wtot[kRadixWarps];
+};
+
+// one 2048-key tile of a stable LSD pass
+__device__ __forceinline__ void scatter_tile(ScatterSmem& sm, const uint32_t* __restrict__ kin,
+                                             const uint32_t* __restrict__ vin, uint32_t* __restrict__ kout,
+                                             uint32_t* __restrict__ vout, int E, int shift,
+                                             const uint32_t* __restrict__ offs, int nblk, int prefixed, int tile) {
+    constexpr int kWarps = kRadixWarps;
+    uint32_t (&wcount)[kRadixWarps][kRadixBins + 1] = sm.wcount;
+    uint32_t (&wtot)[kRadixWarps] = sm.wtot;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < kWarps * (kRadixBins + 1); i += kRadixThreads) (&wcount[0][0])[i] = 0;
     __syncthreads();
     // warp `wid` owns the contiguous chunk [base, base + 32*items): order inside the
     // tile is (warp, item, lane), which is the input order — the pass is stable.
-    const int base = blockIdx.x * kRadixTile + wid * (32 * kRadixItems);
+    const int base = tile * kRadixTile + wid * (32 * kRadixItems);
     uint32_t k[kRadixItems], v[kRadixItems], rank[kRadixItems];
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
@@ -439,7 +470,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
         const int dgt = tid;    // kRadixThreads == kRadixBins
         uint32_t before = 0, total = 0;
         if (prefixed) {          // radix_prefix_kernel ran: prefixes in place, totals in row nblk
-            before = offs[blockIdx.x * kRadixBins + dgt];
+            before = offs[tile * kRadixBins + dgt];
             total = offs[nblk * kRadixBins + dgt];
         } else {
             for (int b0 = 0; b0 < nblk; b0 += 16) {          // 16 independent L2 loads per round
@@ -449,7 +480,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     total += c[i];
-                    before += b0 + i < (int)blockIdx.x ? c[i] : 0u;
+                    before += b0 + i < tile ? c[i] : 0u;
                 }
             }
         }
@@ -485,14 +516,56 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
     }
 }
 
-__global__ void __launch_bounds__(256)
-payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ skey, MsgSource msgs,
-               const float* __restrict__ w, int E, uint32_t* __restrict__ ssrc, float* __restrict__ sw,
-               uint32_t* __restrict__ sslot, uint32_t* __restrict__ slen, uint32_t* __restrict__ hub_giant,
-               uint32_t* __restrict__ hub_reg, uint32_t* __restrict__ small_heads, uint32_t* __restrict__ ctr,
-               int* __restrict__ svst, const int* __restrict__ stamps, int L, int E4, long long num_nodes,
-               int* __restrict__ err_flag) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kRadixThreads)
+radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                     uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, int E, int shift,
+                     const uint32_t* __restrict__ offs, int nblk, int prefixed) {
+    __shared__ ScatterSmem sm;
+    scatter_tile(sm, kin, vin, kout, vout, E, shift, offs, nblk, prefixed, blockIdx.x);
+}
+
+struct PayloadArgs {
+    const uint32_t* order;     // sorted message ids
+    const uint32_t* skey;      // sorted targets (where the sort left them)
+    uint32_t* key_out;         // != skey: the sorted targets are also copied here (odd number of passes)
+    MsgSource msgs;
+    const float* w;
+    int E;
+    uint32_t* ssrc;
+    float* sw;
+    uint32_t* sslot;
+    uint32_t* slen;
+    uint32_t* hub_giant;
+    uint32_t* hub_reg;
+    uint32_t* small_heads;
+    uint32_t* ctr;
+    int* svst;
+    const int* stamps;
+    int L, E4;
+    long long num_nodes;
+    int* err_flag;
+};
+
+// sorted position p (whole warps call it together: p may be >= E)
+__device__ __forceinline__ void payload_body(const PayloadArgs& a, int p) {
+    const uint32_t* __restrict__ order = a.order;
+    const uint32_t* __restrict__ skey = a.skey;
+    const MsgSource& msgs = a.msgs;
+    const float* __restrict__ w = a.w;
+    const int E = a.E;
+    uint32_t* __restrict__ ssrc = a.ssrc;
+    float* __restrict__ sw = a.sw;
+    uint32_t* __restrict__ sslot = a.sslot;
+    uint32_t* __restrict__ slen = a.slen;
+    uint32_t* __restrict__ hub_giant = a.hub_giant;
+    uint32_t* __restrict__ hub_reg = a.hub_reg;
+    uint32_t* __restrict__ small_heads = a.small_heads;
+    uint32_t* __restrict__ ctr = a.ctr;
+    int* __restrict__ svst = a.svst;
+    const int* __restrict__ stamps = a.stamps;
+    const int L = a.L, E4 = a.E4;
+    const long long num_nodes = a.num_nodes;
+    int* __restrict__ err_flag = a.err_flag;
     const int lane = threadIdx.x & 31;
     bool small_head = false;
     if (p < E) {
@@ -502,6 +575,7 @@ payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ 
         msgs.get((int)m, tgt_unused, oth, j);
         const uint32_t other = (uint32_t)oth;
         const uint32_t mykey = skey[p];
+        if (a.key_out != skey) a.key_out[p] = mykey;
         ssrc[p] = other;
         float wv = w[j];
         if (sslot != nullptr) {          // snapshot path: where the source node's own segment starts
@@ -552,25 +626,36 @@ payload_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ 
     }
 }
 
+__global__ void __launch_bounds__(256) payload_kernel(PayloadArgs a) {
+    payload_body(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 // Longest giant segments first: their add chains are the critical path of the hub walker.
 // (Scheduling order only — results do not depend on it.)
 constexpr int kGiantSortMax = 2048;
-__global__ void __launch_bounds__(1024)
-sort_giants_kernel(uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ slen, const uint32_t* __restrict__ ctr) {
-    __shared__ uint32_t head_s[kGiantSortMax], len_s[kGiantSortMax];
+struct GiantSmem {
+    uint32_t head_s[kGiantSortMax], len_s[kGiantSortMax];
+};
+__device__ __forceinline__ void sort_giants_body(GiantSmem& sm, uint32_t* __restrict__ hub_giant,
+                                                 const uint32_t* __restrict__ slen, const uint32_t* __restrict__ ctr) {
     const int n = (int)ctr[kCtrGiant];
     if (n < 2 || n > kGiantSortMax) return;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        head_s[i] = hub_giant[i];
-        len_s[i] = slen[head_s[i]];
+        sm.head_s[i] = hub_giant[i];
+        sm.len_s[i] = slen[sm.head_s[i]];
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t li = len_s[i];
+        const uint32_t li = sm.len_s[i];
         int rank = 0;
-        for (int j = 0; j < n; ++j) rank += (len_s[j] > li || (len_s[j] == li && j < i)) ? 1 : 0;
-        hub_giant[rank] = head_s[i];
+        for (int j = 0; j < n; ++j) rank += (sm.len_s[j] > li || (sm.len_s[j] == li && j < i)) ? 1 : 0;
+        hub_giant[rank] = sm.head_s[i];
     }
+}
+__global__ void __launch_bounds__(1024)
+sort_giants_kernel(uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ slen, const uint32_t* __restrict__ ctr) {
+    __shared__ GiantSmem sm;
+    sort_giants_body(sm, hub_giant, slen, ctr);
 }
 
 // ---------------------------------------------------------------- eager decay sweep (large path)
@@ -706,13 +791,35 @@ snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, int E, int ds4,
     const int snap4 = (L - 1) * ds4;
     const float* rows = st.data + (long long)key * st.node_stride + st.row_stride;    // row 1
     float* slot = snap + (long long)p * snap4 * 4;
-    for (int c = lane; c < snap4; c += 32) {
-        const int li = c / ds4;                         // layer - 1
-        long long stamp = 0;
-        if (LAZY) stamp = st.stamps[(long long)key * L + li];
-        float4 one = stamp >= 0 ? ld4(rows + 4 * (long long)c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (LAZY && stamp >= 0) scale4(one, decay_factor(st, li, stamp));
-        st4(slot + 4 * (long long)c, one);
+    // pending decay of rows 1..L-1: lane l fetches the stamp of layer l + 1 and computes its factor
+    // (one f64 division per layer, not per lane and column step); rows never written hold zeros,
+    // so they are loaded unconditionally and any factor is right for them
+    float fmine = 1.0f;
+    if (LAZY && lane < L - 1) {
+        const long long stamp = st.stamps[(long long)key * L + lane];
+        if (stamp >= 0) fmine = decay_factor(st, lane, stamp);
+    }
+    float f[TPN_MAX_LAYERS];
+#pragma unroll
+    for (int l = 0; l < TPN_MAX_LAYERS; ++l) f[l] = LAZY ? __shfl_sync(0xffffffffu, fmine, l) : 1.0f;
+    for (int c0 = lane; c0 < snap4; c0 += 128) {        // four row requests in flight per lane
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + 32 * k;
+            v[k] = c < snap4 ? ld4(rows + 4 * (long long)c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + 32 * k;
+            if (c < snap4) {
+                if (LAZY) {
+                    const int li = c / ds4;             // layer - 1
+                    scale4(v[k], li == 0 ? f[0] : (li == 1 ? f[1] : (li == 2 ? f[2] : f[3])));
+                }
+                st4(slot + 4 * (long long)c, v[k]);
+            }
+        }
     }
 }
 
@@ -1334,7 +1441,9 @@ int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const D
     const int slice_w_r = (((rs + spr_r - 1) / spr_r) + 3) & ~3;
     const int spr_g = (rs + kHub2GiantFloats - 1) / kHub2GiantFloats;     // giants (<= 32 floats)
     const int slice_w_g = (((rs + spr_g - 1) / spr_g) + 3) & ~3;
-    const unsigned grid = 148 * 2;                                        // 2 CTAs (88 KB of ring each) per SM
+    // 2 CTAs (88 KB of ring each) per SM.  One per SM — leaving half of every SM to the short-segment
+    // walker from the start — was measured slower (0.62 vs 0.58 ms per 100k-edge step).
+    const unsigned grid = 148 * 2;
     if (lazy)
         walk_hub2_kernel<true, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                              ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
@@ -1527,33 +1636,62 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
                                                              ws.ssrc, ws.sw, ws.sslot, ws.slen, err_flag_dev, log_w, L,
                                                              new_epoch, dargs, view, sw_args);
     } else {
-        prep_large_kernel<<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(msgs, E, t_last_f, neg_lambda,
-                                                                          st->num_nodes, ws.w, ws.key_a, ws.val_a,
-                                                                          err_flag_dev, log_w, L, new_epoch, dargs,
-                                                                          ws.ctr);
         int bits = 0;
         while ((1ll << bits) <= st->num_nodes) ++bits;    // keys are in [0, num_nodes] (num_nodes = dropped)
         const int passes = (bits + 7) / 8;
         const int nblk = (E + kRadixTile - 1) / kRadixTile;
-        uint32_t *kin = ws.key_a, *kout = ws.key_b, *vin = ws.val_a, *vout = ws.val_b;
-        for (int p = 0; p < passes; ++p) {
-            radix_hist_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, E, 8 * p, ws.hist, nblk);
-            const int prefixed = nblk > kRadixDirectBlocks ? 1 : 0;      // few tiles: the scatter sums the columns itself
-            if (prefixed) radix_prefix_kernel<<<kRadixBins / 8, 256, 0, stream>>>(ws.hist, nblk);
-            radix_scatter_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, vin, kout, vout, E, 8 * p, ws.hist, nblk,
-                                                                     prefixed);
-            uint32_t* tk = kin; kin = kout; kout = tk;
-            uint32_t* tv = vin; vin = vout; vout = tv;
+        struct { PrepArgs prep; PayloadArgs pay; } fa;
+        fa.prep.msgs = msgs;
+        fa.prep.E = E;
+        fa.prep.t_last_f = t_last_f;
+        fa.prep.neg_lambda = neg_lambda;
+        fa.prep.num_nodes = st->num_nodes;
+        fa.prep.w = ws.w;
+        fa.prep.key = ws.key_a;
+        fa.prep.val = ws.val_a;
+        fa.prep.err_flag = err_flag_dev;
+        fa.prep.decay_log = log_w;
+        fa.prep.L = L;
+        fa.prep.new_epoch = new_epoch;
+        fa.prep.decay = dargs;
+        fa.prep.ctr = ws.ctr;
+        fa.pay.order = nullptr;
+        fa.pay.skey = nullptr;
+        fa.pay.key_out = ws.key_a;
+        fa.pay.msgs = msgs;
+        fa.pay.w = ws.w;
+        fa.pay.E = E;
+        fa.pay.ssrc = ws.ssrc;
+        fa.pay.sw = ws.sw;
+        fa.pay.sslot = snapshot_path ? ws.sslot : nullptr;
+        fa.pay.slen = ws.slen;
+        fa.pay.hub_giant = ws.hub_giant;
+        fa.pay.hub_reg = ws.hub_reg;
+        fa.pay.small_heads = ws.small_heads;
+        fa.pay.ctr = ws.ctr;
+        fa.pay.svst = (lazy && !snapshot_path && L >= 2) ? ws.svst : nullptr;
+        fa.pay.stamps = st->stamps;
+        fa.pay.L = L;
+        fa.pay.E4 = E4;
+        fa.pay.num_nodes = st->num_nodes;
+        fa.pay.err_flag = err_flag_dev;
+        {
+            prep_large_kernel<<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(fa.prep);
+            uint32_t *kin = ws.key_a, *kout = ws.key_b, *vin = ws.val_a, *vout = ws.val_b;
+            for (int p = 0; p < passes; ++p) {
+                radix_hist_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, E, 8 * p, ws.hist, nblk);
+                const int prefixed = nblk > kRadixDirectBlocks ? 1 : 0;      // few tiles: the scatter sums the columns itself
+                if (prefixed) radix_prefix_kernel<<<kRadixBins / 8, 256, 0, stream>>>(ws.hist, nblk);
+                radix_scatter_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, vin, kout, vout, E, 8 * p, ws.hist, nblk,
+                                                                         prefixed);
+                uint32_t* tk = kin; kin = kout; kout = tk;
+                uint32_t* tv = vin; vin = vout; vout = tv;
+            }
+            fa.pay.order = vin;
+            fa.pay.skey = kin;          // odd number of passes: sorted keys live in key_b; payload copies them to key_a
+            payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(fa.pay);
+            if (snapshot_path) sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr);
         }
-        if (kin != ws.key_a) {       // odd number of passes: sorted keys live in key_b
-            cudaMemcpyAsync(ws.key_a, kin, sizeof(uint32_t) * E, cudaMemcpyDeviceToDevice, stream);
-        }
-        payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(vin, ws.key_a, msgs, ws.w, E, ws.ssrc, ws.sw,
-                                                            snapshot_path ? ws.sslot : nullptr, ws.slen, ws.hub_giant,
-                                                            ws.hub_reg, ws.small_heads, ws.ctr,
-                                                            (lazy && !snapshot_path && L >= 2) ? ws.svst : nullptr,
-                                                            st->stamps, L, E4, st->num_nodes, err_flag_dev);
-        if (snapshot_path) sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr);
         if (eager_sweep) {
             const long long want = (sweep_total4 + 255) / 256;
             const unsigned grid = (unsigned)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
