@@ -57,7 +57,7 @@
 extern "C" {
 #endif
 
-#define TPN_ABI_VERSION 4
+#define TPN_ABI_VERSION 5
 
 #define TPN_MAX_LAYERS 4
 
@@ -189,6 +189,22 @@ int tpn_pairwise(const tpn_state_t* st, const int64_t* a_ids_dev, const int64_t*
 int tpn_pairwise_neighbors(const tpn_state_t* st, const int64_t* nbr_dev, const int64_t* src_dev,
                            const int64_t* dst_dev, int64_t m, int num_neighbors, int apply_log_scale,
                            float* out_dev, void* stream);
+
+/*
+ * Forward of the pair-wise head `self.mlp` = Linear(F, 4F) -> ReLU -> Linear(4F, F)
+ * (TPNet.py:64-65, applied at :125/:129) for INFERENCE: y = W2 relu(W1 x + b1) + b2 in fp32
+ * (no TF32), one fused kernel, the hidden layer never leaves the SM.  Training keeps the head in
+ * PyTorch (autograd); callers use this only when no gradient is required.
+ *   x_dev   : float32[n][features] device, 16-byte aligned (the output of tpn_pairwise /
+ *             tpn_pairwise_neighbors viewed as [n, F])
+ *   w1_dev  : float32[hidden][features] (nn.Linear layout), b1_dev : float32[hidden]
+ *   w2_dev  : float32[features][hidden],                    b2_dev : float32[features]
+ *   y_dev   : float32[n][features] device, 16-byte aligned
+ * Built for the default 3-layer configuration, features = 64 and hidden = 256; any other shape
+ * returns TPN_ERR_UNSUPPORTED (the caller applies the head with its own GEMMs).
+ */
+int tpn_head_forward(const float* x_dev, int64_t n, int features, int hidden, const float* w1_dev,
+                     const float* b1_dev, const float* w2_dev, const float* b2_dev, float* y_dev, void* stream);
 
 /*
  * RandomProjectionModule.get_random_projections — TPNet.py:101-110.

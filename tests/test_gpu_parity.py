@@ -107,7 +107,10 @@ def test_pairwise_and_gather_match_reference_fixture(name, mode):
     with torch.no_grad():
         full = m.get_pair_wise_feature(a, b)
     assert full.shape == (len(a), m.pair_wise_feature_dim)
-    assert torch.allclose(full, m.mlp(torch.from_numpy(got).to(DEV)))
+    with torch.no_grad():
+        head = m.mlp(torch.from_numpy(got).to(DEV))
+    # the no-grad call runs the fused fp32 head (other summation order than cuBLAS): compare at the output's scale
+    assert float((full - head).abs().max()) <= 2e-5 * (float(head.abs().max()) + 1.0)
 
 
 def nbr_tol(o, nbr, src, dst, ref, not_scale):
@@ -402,6 +405,42 @@ def test_pairwise_large_call(N, dim, L, n, mode):
     dev_ids = [torch.from_numpy(x).to(DEV) for x in (a, b)]
     assert np.array_equal(m.pair_wise_gram(*dev_ids).cpu().numpy(), big)
     m.check_errors()
+
+
+@pytest.mark.parametrize('n', [1, 63, 64, 65, 1000, 100003])
+def test_fused_head_matches_torch_head(n):
+    """tpn_head_forward (no-grad path of get_pair_wise_feature) vs `self.mlp` in PyTorch: both are fp32
+    with different summation orders, so both are compared with the float64 head."""
+    torch.manual_seed(3)
+    kw = dict(node_num=50, edge_num=5000, dim_factor=10, num_layer=3, time_decay_weight=1e-6, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=-1)
+    m = RandomProjectionModule(device=DEV, decay_mode='eager', **kw).to(DEV)
+    assert m.pair_wise_feature_dim == 64
+    with torch.no_grad():
+        for p in m.mlp.parameters():
+            p.mul_(3.0)                                       # well away from the init scale
+    x = (torch.rand(n, 64, device=DEV) * 12.0).contiguous()   # log-scaled Gram entries live in [0, ~12]
+    x[:, ::7] = 0
+    with torch.no_grad():
+        fused = m._head(x)
+        ref32 = m.mlp(x)
+    ref64 = m.mlp.double()(x.double())
+    m.mlp.float()
+    scale = float(ref64.abs().max()) + 1.0
+    err_fused = float((fused.double() - ref64).abs().max())
+    err_torch = float((ref32.double() - ref64).abs().max())
+    assert err_fused <= 4 * err_torch + 1e-6 * scale, (err_fused, err_torch)
+    assert float((fused - ref32).abs().max()) <= 2e-5 * scale
+    # autograd on: the PyTorch head, gradients reach its parameters (TPNet trains it)
+    y = m._head(x)
+    assert y.requires_grad and torch.equal(y.detach(), ref32)
+    # the public calls use it: same values with the fused head switched off
+    ids = np.arange(1, 41, dtype=np.int64)
+    with torch.no_grad():
+        a = m.get_pair_wise_feature(ids, ids[::-1].copy())
+        m.fused_head = False
+        b = m.get_pair_wise_feature(ids, ids[::-1].copy())
+    assert float((a - b).abs().max()) <= 2e-5 * (float(b.abs().max()) + 1.0)
 
 
 def test_lazy_matches_eager_and_log_restart(monkeypatch):

@@ -20,7 +20,7 @@ TPN_ERR_UNSUPPORTED = -5
 TPN_ERR_INDEX = -6
 STAGE_RAW, STAGE_ID_WRAP, STAGE_ID = 0, 1, 2
 TPN_MAX_LAYERS = 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 #: every symbol include/tpnet_b200.h declares (tests assert the .so exports all of them)
 EXPORTED_SYMBOLS = (
@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     'tpn_update_workspace_bytes', 'tpn_update', 'tpn_pairwise', 'tpn_gather',
     'tpn_materialize', 'tpn_reset_epoch', 'tpn_clear_walk_layers',
     'tpn_stager_create', 'tpn_stager_destroy', 'tpn_stage',
-    'tpn_update_messages', 'tpn_gather_blocks', 'tpn_set_debug_flags', 'tpn_pairwise_neighbors',
+    'tpn_update_messages', 'tpn_gather_blocks', 'tpn_set_debug_flags', 'tpn_pairwise_neighbors', 'tpn_head_forward',
 )
 
 
@@ -84,6 +84,9 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.tpn_pairwise_neighbors.restype = c_int
     lib.tpn_pairwise_neighbors.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                            c_void_p, c_void_p]
+    lib.tpn_head_forward.restype = c_int
+    lib.tpn_head_forward.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]
     lib.tpn_gather.restype = c_int
     lib.tpn_gather.argtypes = [POINTER(TpnState), c_void_p, c_int64, c_void_p, c_void_p]
     for name in ('tpn_materialize', 'tpn_reset_epoch', 'tpn_clear_walk_layers'):

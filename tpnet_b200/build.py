@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-O3', '-std=c++17', '-lineinfo',
     '-Xcompiler', '-fPIC',
+    '-Xcompiler', '-fopenmp',         # host side: the staging pass of big batches (tpn_stage.cu)
     '-Xptxas', '-v',
     # IEEE arithmetic everywhere: no fast-math, denormals kept, precise div/sqrt.
     '--ftz=false', '--prec-div=true', '--prec-sqrt=true',
@@ -77,7 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}:\n{r.stdout}\n{r.stderr}')
         objs.append(obj)
-    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB_PATH, *objs]
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fopenmp', '-o', LIB_PATH, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')

@@ -6,6 +6,7 @@
 // ids on the way, which replaces the bounds check torch indexing performs), issues ONE
 // cudaMemcpyAsync per call on the caller's stream and records an event so that a slot is
 // never overwritten before its copy has left.  No Python-level stream/event objects.
+#include <omp.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -38,6 +39,21 @@ void release(tpn_stager* sg) {
     sg->dev = nullptr;
     sg->done = nullptr;
     sg->used = nullptr;
+}
+
+// host threads of the staging pass: TPN_STAGE_THREADS, else min(8, cores / 2)
+int stage_threads() {
+    static int n = 0;
+    if (n == 0) {
+        const char* env = getenv("TPN_STAGE_THREADS");
+        int v = env != nullptr ? atoi(env) : 0;
+        if (v < 1) {
+            v = omp_get_num_procs() / 2;
+            v = v > 8 ? 8 : v;
+        }
+        n = v < 1 ? 1 : (v > 64 ? 64 : v);
+    }
+    return n;
 }
 
 int allocate(tpn_stager* sg, size_t slot_bytes, int slots) {
@@ -119,15 +135,25 @@ extern "C" int tpn_stage(tpn_stager_t* sg, const void* const* host, const int64_
     }
     char* dst = sg->host[k];
     size_t off = 0;
+    // big batches (100k-edge calls move megabytes): the validate-and-copy pass is split over a few
+    // host threads (OpenMP's persistent pool); small ones stay on the calling thread
+    const int threads = total >= ((size_t)1 << 19) ? stage_threads() : 1;
     for (int i = 0; i < count; ++i) {
         const int64_t n = elems[i];
         if (kinds[i] == TPN_STAGE_RAW) {
-            memcpy(dst + off, host[i], (size_t)n * 8);
+            const char* src = reinterpret_cast<const char*>(host[i]);
+            const int64_t bytes = n * 8, chunk = (bytes / threads + 63) & ~(int64_t)63;
+#pragma omp parallel for num_threads(threads) schedule(static) if (threads > 1)
+            for (int t = 0; t < threads; ++t) {
+                const int64_t b0 = (int64_t)t * chunk, b1 = b0 + chunk < bytes ? b0 + chunk : bytes;
+                if (b0 < b1) memcpy(dst + off + b0, src + b0, (size_t)(b1 - b0));
+            }
         } else {
             const int64_t* src = reinterpret_cast<const int64_t*>(host[i]);
             int64_t* out64 = reinterpret_cast<int64_t*>(dst + off);
             const int64_t lo = kinds[i] == TPN_STAGE_ID_WRAP ? -num_nodes : 0;   // indexing wraps, scatter does not
             int64_t mn = 0, mx = 0;
+#pragma omp parallel for num_threads(threads) schedule(static) reduction(min : mn) reduction(max : mx) if (threads > 1)
             for (int64_t j = 0; j < n; ++j) {
                 const int64_t v = src[j];
                 mn = v < mn ? v : mn;

@@ -792,31 +792,31 @@ snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, int E, int ds4,
     const float* rows = st.data + (long long)key * st.node_stride + st.row_stride;    // row 1
     float* slot = snap + (long long)p * snap4 * 4;
     // pending decay of rows 1..L-1: lane l fetches the stamp of layer l + 1 and computes its factor
-    // (one f64 division per layer, not per lane and column step); rows never written hold zeros,
-    // so they are loaded unconditionally and any factor is right for them
+    // (one f64 division per layer, not per lane and column step); a negative factor marks a row
+    // that was never written (all zero): it is not read at all
     float fmine = 1.0f;
     if (LAZY && lane < L - 1) {
         const long long stamp = st.stamps[(long long)key * L + lane];
-        if (stamp >= 0) fmine = decay_factor(st, lane, stamp);
+        fmine = stamp >= 0 ? decay_factor(st, lane, stamp) : -1.0f;
     }
     float f[TPN_MAX_LAYERS];
 #pragma unroll
     for (int l = 0; l < TPN_MAX_LAYERS; ++l) f[l] = LAZY ? __shfl_sync(0xffffffffu, fmine, l) : 1.0f;
     for (int c0 = lane; c0 < snap4; c0 += 128) {        // four row requests in flight per lane
         float4 v[4];
+        float fk[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + 32 * k;
-            v[k] = c < snap4 ? ld4(rows + 4 * (long long)c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int li = c / ds4;                     // layer - 1
+            fk[k] = li == 0 ? f[0] : (li == 1 ? f[1] : (li == 2 ? f[2] : f[3]));
+            v[k] = (c < snap4 && fk[k] >= 0.f) ? ld4(rows + 4 * (long long)c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + 32 * k;
             if (c < snap4) {
-                if (LAZY) {
-                    const int li = c / ds4;             // layer - 1
-                    scale4(v[k], li == 0 ? f[0] : (li == 1 ? f[1] : (li == 2 ? f[2] : f[3])));
-                }
+                if (LAZY && fk[k] >= 0.f) scale4(v[k], fk[k]);
                 st4(slot + 4 * (long long)c, v[k]);
             }
         }

@@ -158,6 +158,7 @@ class RandomProjectionModule(nn.Module):
         self._ws_batch = 0
         self._err: Optional[torch.Tensor] = None
         self.validate_ids = True
+        self.fused_head = True          # no-grad calls: fused fp32 head kernel when the head has the default shape
         self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module.materialize())
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._after_external_write())
 
@@ -381,10 +382,38 @@ class RandomProjectionModule(nn.Module):
             self._h.launches += 1
         return out
 
+    def _head(self, gram: torch.Tensor) -> torch.Tensor:
+        """``self.mlp`` on ``[n, F]`` features (TPNet.py:125/:129).  With autograd on (training) it is
+        the PyTorch module; under ``torch.no_grad()`` the default-shape head (F = 64) runs as one
+        fused fp32 kernel (``tpn_head_forward``)."""
+        if torch.is_grad_enabled() or not self.fused_head or gram.shape[0] == 0:
+            return self.mlp(gram)
+        mlp = self.mlp
+        if not (isinstance(mlp, nn.Sequential) and len(mlp) == 3 and isinstance(mlp[0], nn.Linear)
+                and isinstance(mlp[1], nn.ReLU) and isinstance(mlp[2], nn.Linear)):
+            return self.mlp(gram)
+        l1, l2 = mlp[0], mlp[2]
+        f, hid = l1.in_features, l1.out_features
+        ok = (l2.in_features == hid and l2.out_features == f and gram.shape[1] == f and l1.bias is not None
+              and l2.bias is not None and gram.is_contiguous()
+              and all(t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.device == gram.device
+                      for t in (gram, l1.weight, l1.bias, l2.weight, l2.bias)))
+        if ok:
+            out = torch.empty_like(gram)
+            rc = _lib.load().tpn_head_forward(gram.data_ptr(), gram.shape[0], f, hid, l1.weight.data_ptr(),
+                                              l1.bias.data_ptr(), l2.weight.data_ptr(), l2.bias.data_ptr(),
+                                              out.data_ptr(), self._stream())
+            if rc == _lib.TPN_OK:
+                self._h.launches += 1
+                return out
+            if rc != _lib.TPN_ERR_UNSUPPORTED:
+                _lib.check(rc, 'tpn_head_forward')
+        return self.mlp(gram)
+
     def get_pair_wise_feature(self, src_node_ids: IdArray, dst_node_ids: IdArray) -> torch.Tensor:
         """TPNet.py:112-129.  Gradients flow to ``self.mlp`` only, as in the reference
         (the projections are ``requires_grad=False``)."""
-        return self.mlp(self.pair_wise_gram(src_node_ids, dst_node_ids))
+        return self._head(self.pair_wise_gram(src_node_ids, dst_node_ids))
 
     def neighbor_pair_wise_gram(self, neighbor_node_ids: IdArray, src_node_ids: IdArray,
                                 dst_node_ids: IdArray) -> torch.Tensor:
@@ -428,7 +457,7 @@ class RandomProjectionModule(nn.Module):
         ``[m*K*2, F]`` view (same values, same gradients to the head)."""
         g = self.neighbor_pair_wise_gram(neighbor_node_ids, src_node_ids, dst_node_ids)
         m, k = g.shape[0], g.shape[1]
-        return self.mlp(g.view(m * k * 2, self.pair_wise_feature_dim)).view(m, k, 2 * self.pair_wise_feature_dim)
+        return self._head(g.view(m * k * 2, self.pair_wise_feature_dim)).view(m, k, 2 * self.pair_wise_feature_dim)
 
     def reset_random_projections(self):
         """TPNet.py:131-139."""

@@ -304,7 +304,7 @@ class ShardedRandomProjection(RandomProjectionModule):
 
     def get_pair_wise_feature(self, src_node_ids, dst_node_ids):
         keep, feat = self.pair_wise_gram(src_node_ids, dst_node_ids)
-        return keep, self.mlp(feat)
+        return keep, self._head(feat)
 
     def gather_global(self) -> List[torch.Tensor]:
         """All-gathers the L+1 global [N, d] matrices (tests / small graphs only)."""
