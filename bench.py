@@ -10,7 +10,8 @@ Primary workload (all N): BASELINE.json configs[3], the one its metric ("... at 
 decay, batches of 100,000 edges, p=2 pair-encodes per edge (the decoder shape of
 models/modules.py:112: (src,dst) and (src,neg)).  It fits one GPU (34.6 GB state) and is
 HBM-bound, so the roofline fraction is a real DRAM figure.  N>1: the state is sharded by node
-id (tpnet_b200/sharded.py), strong scaling of the same graph and batch.
+id (tpnet_b200/sharded.py); weak scaling by default — every GPU brings 100,000 edges per step, the
+job's batch is 100,000 x N (`--scaling strong` splits one 100,000-edge batch instead).
 At N=1 the line also carries `also.reddit`: BASELINE.json configs[1] (Reddit-shaped, B=200,
 K=20, p=162 — one TPNet training batch, latency-bound, state L2-resident).
 
@@ -60,7 +61,9 @@ def parse_args():
     ap.add_argument('--cpu-sample-steps', type=int, default=None)
     ap.add_argument('--warm-batches', type=int, default=None, help='untimed batches that fill the state')
     ap.add_argument('--pl-nodes', type=int, default=None, help='override the power-law node count (debug)')
-    ap.add_argument('--pl-batch', type=int, default=PL_BATCH)
+    ap.add_argument('--pl-batch', type=int, default=PL_BATCH, help='power-law: edges per step and GPU')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='N > 1: weak = pl_batch edges per GPU and step (job batch pl_batch x N), strong = pl_batch in total')
     return ap.parse_args()
 
 
@@ -382,7 +385,10 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
     import torch.distributed as dist
     from tpnet_b200.sharded import ShardedRandomProjection
     shape = powerlaw_shape(args)
-    B = args.pl_batch
+    # weak scaling (default): every GPU brings its own 100,000 edges per step, so the batch of the whole job is
+    # pl_batch x N; strong: the same 100,000-edge batch split over the ranks
+    weak = args.scaling == 'weak'
+    B = args.pl_batch * (world if weak else 1)
     per_edge_B, per_pair_B = algorithmic_bytes(shape)
     warm_n = args.warm_batches if args.warm_batches is not None else PL_WARM
     n_phase = min(K, 8)
@@ -564,7 +570,8 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
     h2d = 3 * B * 8 + 2 * (2 * B * 8)
     return {
         'metric': METRIC, 'value': B * K / (dev_ms * 1e-3), 'unit': 'edges/s', 'n_gpus': world, 'steps': K,
-        'warmup': W, 'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'warmup': W, 'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'weak' if weak else 'strong',
+        'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': (f'power-law temporal graph, {shape.num_nodes} nodes / {shape.num_edges} edges '
                                 f'(BASELINE configs[3]), d={shape.dim}, L={shape.num_layer}, batch {B}, 2 pair-encodes '
@@ -625,7 +632,7 @@ def main():
             cfg = {'workload': f'{shape.name}-shaped synthetic graph, batch {BATCH}, K={NUM_NEIGHBORS}', 'batch': BATCH}
         print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'edges/s', 'n_gpus': args.gpus,
                           'steps': K, 'warmup': W, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
-                          'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+                          'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
                           'cpu_baseline': {'value': val, 'unit': 'edges/s', 'cores': threads, 'kind': 'port',
                                            'sample': sample},
                           'e2e': {'value': val, 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
