@@ -1177,13 +1177,14 @@ walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_
 // (the reference's accumulation order is observable), so a hub of m messages is a dependent
 // chain of m fp32 adds per column.  The chain must see nothing but the add: everything else is
 // moved off it.  Work item = (segment, column slice inside ONE source row), one CTA:
-//   8 producer warps : warp p owns ring stages b = p, p+8, ... of 32 messages.  Each lane fetches
-//       the (source id, snapshot slot, weight) of one message, lanes exchange row pointers by
-//       shuffle so that every 128-bit load instruction covers 2 (4 for giants) whole message
-//       slices, coalesced; all loads of the stage are in flight together, then the slices are
-//       scaled — fmul_rn(x, w), the reference's rounded product (TPNet.py:91-96), plus this
-//       call's decay for received rows of a sharded state — and stored to the stage, published
-//       with the stage's `full` mbarrier.  Eight stages in flight hide DRAM latency.
+//   7 producer warps : warp p owns ring stages b = p, p+7, ... of 32 messages (128 for giants).  Each
+//       lane fetches the (source id, snapshot slot, weight) of one message, lanes exchange row pointers
+//       by shuffle so that every 128-bit load instruction covers 2 (8 for giants) whole message
+//       slices, coalesced; then the slices are scaled — fmul_rn(x, w), the reference's rounded
+//       product (TPNet.py:91-96), plus this call's decay for received rows of a sharded state — and
+//       stored to the stage, published with the stage's `full` mbarrier.  (Measured: a warp keeps
+//       only 2-3 of these scattered LDG.128 in flight, so the number of producer WARPS sets the gather
+//       rate; see DESIGN.md section 4 "Hubs" for the variants that were measured and rejected.)
 //   1 consumer warp  : two adjacent columns per lane; per message one LDS.64 and two scalar
 //       FADDs, acc = fadd_rn(acc, product) in sorted-message order — bit-identical to the warp
 //       walker — then the stage goes back through its `empty` mbarrier.
