@@ -53,7 +53,9 @@ constexpr int kHubThreads = (kHubConsumers + 1) * 32;      // + 1 producer warp
 constexpr int kHubStages = 4;            // ring stages of 32 messages
 constexpr int kHubSlotFloats = kHubConsumers * 32;         // 128 floats (512 B) per message slot
 constexpr int kHubMetaChunk = 512;       // messages of metadata staged per bulk copy
-constexpr size_t kSnapMaxBytes = (size_t)3 << 29;          // 1.5 GiB: above this the per-layer path is used
+constexpr size_t kSnapMaxBytes = (size_t)8 << 30;          // 8 GiB: above this the per-layer path is used (its hub
+                                                           // walker is 10x slower on giant segments: 33 ms vs ~3 ms for
+                                                           // d=1024, L=3, 100k zipf(1.5) edges)
 // large batches, snapshot path: short segments -> persistent warp walker, long ones -> hub2
 constexpr int kSmallWalkThreads = 256;
 constexpr int kHub2Producers = 7;        // producer warps: each keeps one ring stage (32 messages) of loads in flight
