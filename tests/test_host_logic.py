@@ -51,6 +51,11 @@ def test_argument_validation_without_gpu():
     assert lib.tpn_pairwise(ctypes.byref(st), None, None, 4, 1, None, None) < 0
     assert lib.tpn_gather(ctypes.byref(st), None, 4, None, None) < 0
     assert lib.tpn_materialize(ctypes.byref(st), None) < 0
+    assert lib.tpn_pairwise_neighbors(ctypes.byref(st), None, None, None, 4, 5, 1, None, None) < 0
+    # the fused head exists for the default 64 -> 256 -> 64 shape only; other shapes are the caller's GEMMs
+    assert lib.tpn_head_forward(None, 10, 36, 144, None, None, None, None, None, None) == _lib.TPN_ERR_UNSUPPORTED
+    assert lib.tpn_head_forward(None, 10, 64, 256, None, None, None, None, None, None) < 0      # null pointers
+    assert lib.tpn_head_forward(None, 0, 64, 256, None, None, None, None, None, None) == 0      # nothing to do
 
 
 def test_constructor_matches_reference_contract():
@@ -123,6 +128,24 @@ def test_compute_without_cuda_fails_loudly():
         m.get_pair_wise_feature(ids, ids)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         m.get_random_projections(ids)
+
+
+def test_head_is_the_pytorch_module_whenever_autograd_or_shape_require_it():
+    """`_head` = `self.mlp` (TPNet.py:125/:129).  With autograd on (training) and for tensors / shapes the
+    fused kernel does not serve it must be the PyTorch module, gradients included."""
+    torch.manual_seed(0)
+    m = make()
+    x = torch.randn(7, m.pair_wise_feature_dim)
+    y = m._head(x)
+    assert y.requires_grad and torch.equal(y, m.mlp(x))
+    y.sum().backward()
+    assert m.mlp[0].weight.grad is not None and m.mlp[2].bias.grad is not None
+    with torch.no_grad():                       # CPU tensors, F = 36: not the kernel's case -> PyTorch head
+        assert torch.equal(m._head(x), m.mlp(x))
+        assert m._head(x[:0]).shape == (0, m.pair_wise_feature_dim)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m.get_neighbor_pair_wise_feature(np.ones((3, 4), dtype=np.int64), np.ones(3, dtype=np.int64),
+                                         np.ones(3, dtype=np.int64))
 
 
 def test_product_never_imports_the_oracle():

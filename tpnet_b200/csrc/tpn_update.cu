@@ -1039,12 +1039,6 @@ walk_hub_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, cons
 __device__ __forceinline__ float pick4(float f0, float f1, float f2, float f3, int i) {
     return i == 0 ? f0 : (i == 1 ? f1 : (i == 2 ? f2 : f3));
 }
-__device__ __forceinline__ const float* shfl_ptr(const float* p, int src_lane) {
-    unsigned long long v = reinterpret_cast<unsigned long long>(p);
-    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src_lane);
-    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src_lane);
-    return reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
-}
 
 // Short segments (< kHubMin messages).  Persistent warps stride over the compacted head list
 // (payload_kernel); one warp owns the whole L*row_stride span of a target (V float4 per lane;
@@ -1288,7 +1282,6 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                 const float dfac = (DIRECT && LAZY && dnow.has_decay && r >= 1)
                                        ? pick4(dnow.c[0], dnow.c[1], dnow.c[2], dnow.c[3], r - 1) : 1.0f;
                 const int mpi = 32 >> lpm_shift;              // messages per load instruction: 8 (giant) or 2
-                const int ipb = 32 / mpi;                     // load instructions per 32-message sub-block: 4 or 16
                 auto row_ptr = [&](uint32_t v, uint32_t x) -> const float* {
                     if (DIRECT && (x & kDirect) != 0)         // received row: rows 0..L-1 contiguous in the state
                         return st.data + (long long)v * st.node_stride + (long long)r * rs + c0;
@@ -1300,6 +1293,7 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                     const uint32_t use = g / (uint32_t)kHub2Stages;
                     const int stage = (int)(g - use * (uint32_t)kHub2Stages);
                     const int pass = b / kHub2Producers;
+                    (void)pass;                       // only the timeline build reads it
                     HUB2_STAMP(pass, 0);
                     // (1) metadata of this lane's message in each sub-block of the stage (all in flight together)
                     unsigned plo[4], phi[4];
@@ -1540,7 +1534,7 @@ int launch_walk_hub(const StateView& v, int layer, const Workspace& ws, int E4, 
     const uint32_t* xarr = ALL ? ws.sslot
                                : (lazy && layer >= 2 ? reinterpret_cast<const uint32_t*>(ws.svst) + (size_t)(layer - 2) * E4
                                                      : nullptr);
-    const int work_ctr = 2 + (ALL ? 0 : layer - 1);
+    const int work_ctr = kCtrWork0 + (ALL ? 0 : layer - 1);
     const unsigned grid = 148 * 2;
     if (lazy)
         walk_hub_kernel<true, ALL><<<grid, kHubThreads, smem, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, xarr, ws.slen,
