@@ -1,0 +1,69 @@
+"""Runs an UNMODIFIED reference script on the B200 drop-in:
+
+    python -m tpnet_b200.launch /path/to/TPNet train_link_prediction.py --dataset_name wikipedia \
+        --model_name TPNet --use_random_projection --gpu 0 ...
+
+What it does before handing control to the script (``runpy``, ``__name__ == '__main__'``):
+  * puts the reference checkout first on ``sys.path`` and makes it the working directory (the
+    scripts read ``./processed_data`` and write ``./logs``, ``./saved_models``);
+  * replaces ``models.TPNet.RandomProjectionModule`` by ``tpnet_b200.RandomProjectionModule``, so
+    ``from models.TPNet import TPNet, RandomProjectionModule`` (``train_link_prediction.py:36``,
+    ``evaluate_link_prediction.py:33``) binds the CUDA-backed class;
+  * Python >= 3.11 only: lets ``random.sample`` accept a set again (``utils/DataLoader.py:156``
+    relies on the pre-3.11 behaviour, which converted the set with ``tuple()``).
+Nothing of the reference is copied or edited.
+"""
+from __future__ import annotations
+
+import os
+import random
+import runpy
+import sys
+from typing import List
+
+
+def allow_sampling_from_sets() -> None:
+    """``random.sample(set, k)`` as CPython <= 3.10 did it: ``population = tuple(population)``."""
+    if getattr(random.sample, '_tpn_set_shim', False):
+        return
+    original = random.sample
+
+    def sample(population, k, *args, **kwargs):
+        if isinstance(population, (set, frozenset)):
+            population = tuple(population)
+        return original(population, k, *args, **kwargs)
+
+    sample._tpn_set_shim = True
+    random.sample = sample
+
+
+def install(reference_dir: str):
+    """Makes the reference importable and swaps in the drop-in class.  Returns ``models.TPNet``."""
+    reference_dir = os.path.abspath(reference_dir)
+    if not os.path.isfile(os.path.join(reference_dir, 'models', 'TPNet.py')):
+        raise FileNotFoundError(f'{reference_dir} is not a TPNet checkout (models/TPNet.py not found)')
+    if reference_dir not in sys.path:
+        sys.path.insert(0, reference_dir)
+    import models.TPNet as ref_tpnet                        # the reference's module, unmodified
+
+    import tpnet_b200
+    ref_tpnet.RandomProjectionModule = tpnet_b200.RandomProjectionModule
+    if sys.version_info >= (3, 11):
+        allow_sampling_from_sets()
+    return ref_tpnet
+
+
+def main(argv: List[str]) -> None:
+    if len(argv) < 2:
+        raise SystemExit('usage: python -m tpnet_b200.launch <TPNet checkout> <script.py> [script arguments ...]')
+    reference_dir, script = os.path.abspath(argv[0]), argv[1]
+    install(reference_dir)
+    os.chdir(reference_dir)
+    for d in ('logs', 'saved_models', 'saved_results'):     # the scripts expect these to exist or create them lazily
+        os.makedirs(os.path.join(reference_dir, d), exist_ok=True)
+    sys.argv = [script] + argv[2:]
+    runpy.run_path(os.path.join(reference_dir, script), run_name='__main__')
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:])

@@ -9,6 +9,7 @@ float64 seconds.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Iterator, Tuple
 
@@ -125,3 +126,44 @@ def tpnet_pair_lists(nbr: RecentNeighbors, src: np.ndarray, dst: np.ndarray):
     a = np.tile(neighbours.reshape(-1), 2)
     b = np.concatenate([np.repeat(s2, nbr.k), np.repeat(d2, nbr.k)])
     return a.astype(np.int64), b.astype(np.int64)
+
+
+def write_processed_dataset(shape: GraphShape, root: str, seed: int = 0, edge_feat_dim: int = 172,
+                            node_feat_dim: int = 172, dtype=np.float64) -> str:
+    """Writes the shape as a dataset the reference scripts load unchanged
+    (``utils/DataLoader.py:96-98``; format of ``preprocess_data/preprocess_data.py:84-117``):
+
+        <root>/processed_data/<name>/ml_<name>.csv       columns ,u,i,ts,label,idx  (ids and idx 1-based)
+        <root>/processed_data/<name>/ml_<name>.npy       [E+1, edge_feat_dim], row 0 zero, N(0,1) features
+        <root>/processed_data/<name>/ml_<name>_node.npy  [N+1, node_feat_dim] zeros
+
+    Every node id occurs at least once (the loader asserts a gap-free id range, DataLoader.py:136-138).
+    Day-quantised shapes (Flights) store the day index: the loader's ``convert_time`` turns it into seconds.
+    Returns the dataset directory."""
+    name = shape.name
+    E = shape.num_edges
+    need = max(shape.num_src, shape.num_dst) if shape.num_dst else (shape.num_src + 1) // 2
+    if E < need:
+        raise ValueError(f'{E} edges cannot touch every one of the {shape.num_nodes} nodes')
+    src, dst, t = next(iter(edge_stream(shape, E, 1, seed=seed)))
+    rng = np.random.default_rng(seed + 991)
+    if shape.num_dst:                                   # bipartite: sources 1..S, destinations S+1..S+D
+        src[rng.permutation(E)[:shape.num_src]] = np.arange(1, shape.num_src + 1)
+        dst[rng.permutation(E)[:shape.num_dst]] = shape.num_src + np.arange(1, shape.num_dst + 1)
+    else:                                               # one id space: cover it with both endpoint columns
+        half = (shape.num_src + 1) // 2
+        pos = rng.permutation(E)
+        src[pos[:half]] = np.arange(1, half + 1)
+        dst[pos[:shape.num_src - half]] = np.arange(half + 1, shape.num_src + 1)
+    ts = np.floor(t / 86400.0) if shape.day_quantised else t
+    out = os.path.join(root, 'processed_data', name)
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, f'ml_{name}.csv'), 'w') as fh:
+        fh.write(',u,i,ts,label,idx\n')
+        for j in range(E):
+            fh.write(f'{j},{int(src[j])},{int(dst[j])},{float(ts[j])!r},0.0,{j + 1}\n')
+    feats = np.zeros((E + 1, edge_feat_dim), dtype=dtype)
+    feats[1:] = rng.standard_normal((E, edge_feat_dim)).astype(dtype)
+    np.save(os.path.join(out, f'ml_{name}.npy'), feats)
+    np.save(os.path.join(out, f'ml_{name}_node.npy'), np.zeros((shape.num_nodes + 1, node_feat_dim), dtype=dtype))
+    return out
