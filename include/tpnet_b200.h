@@ -57,7 +57,7 @@
 extern "C" {
 #endif
 
-#define TPN_ABI_VERSION 5
+#define TPN_ABI_VERSION 6
 
 #define TPN_MAX_LAYERS 4
 
@@ -249,6 +249,28 @@ int tpn_stager_create(tpn_stager_t** out, size_t slot_bytes, int slots);
 void tpn_stager_destroy(tpn_stager_t* sg);
 int tpn_stage(tpn_stager_t* sg, const void* const* host, const int64_t* elems, const int* kinds, int count,
               int64_t num_nodes, void** dev_out, void* stream);
+
+/*
+ * Host-side routing plan of the node-sharded state (tpnet_b200/sharded.py; no reference counterpart —
+ * the reference is single-device).  Rows of node u live on rank u % world at local row u / world.
+ * For `count` work items (first[m], second[m]) — update messages (target, source) or pairs (a, b) —
+ * tpn_plan computes, for this planner's rank:
+ *   keep[0..n_keep)        : indices m of the items this rank owns (owner(first[m]) == rank), ascending
+ *   first_rows[i]          : local row of first[keep[i]]
+ *   second_rows[i]         : local row of second[keep[i]], or n_local + receive slot if it is remote;
+ *                            remote rows are de-duplicated and numbered by (owner rank, node id) ascending
+ *   recv_counts[q]         : remote rows received from rank q (they arrive in that order)
+ *   send_rows[0..n_send)   : local rows other ranks need, grouped by destination rank, ascending node id
+ *   send_counts[q]         : rows sent to rank q
+ * Output arrays hold `count` elements (send/recv_counts: `world`).  Host memory only, no CUDA calls.
+ * Returns TPN_ERR_INDEX if an id is outside [0, global_nodes).
+ */
+typedef struct tpn_planner tpn_planner_t;
+int tpn_planner_create(tpn_planner_t** out, int64_t global_nodes, int world, int rank);
+void tpn_planner_destroy(tpn_planner_t* p);
+int tpn_plan(tpn_planner_t* p, const int64_t* first, const int64_t* second, int64_t count, int64_t n_local,
+             int64_t* keep, int64_t* first_rows, int64_t* second_rows, int64_t* n_keep,
+             int64_t* send_rows, int64_t* n_send, int64_t* send_counts, int64_t* recv_counts);
 
 #ifdef __cplusplus
 }

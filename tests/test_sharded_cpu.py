@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle.walk_projection import WalkProjectionOracle, decay_factors, edge_weights
-from tpnet_b200.sharded import (exchange_blocks, make_plan, owner_of, rows_on_rank, update_messages)
+from tpnet_b200.sharded import (NativePlanner, exchange_blocks, make_plan, owner_of, rows_on_rank, update_messages)
 
 
 def _free_port():
@@ -43,6 +43,42 @@ def test_plan_is_consistent_across_ranks():
             assert p.num_recv == len(np.unique(oth[p.keep][remote]))
             assert np.all(p.second_rows[~remote] == oth[p.keep][~remote] // G)
             assert np.all(p.second_rows[remote] >= rows_on_rank(N, G, r))
+
+
+def _same_plan(a, b):
+    return (np.array_equal(a.keep, b.keep) and np.array_equal(a.first_rows, b.first_rows)
+            and np.array_equal(a.second_rows, b.second_rows) and np.array_equal(a.send_rows, b.send_rows)
+            and list(a.send_counts) == list(b.send_counts) and list(a.recv_counts) == list(b.recv_counts))
+
+
+@pytest.mark.parametrize('G', [2, 3, 4, 8])
+def test_native_planner_equals_the_numpy_plan(G):
+    """csrc/tpn_plan.cu (what ShardedRandomProjection uses) vs make_plan, field for field: random and zipf
+    batches, duplicates, self pairs, everything local / everything remote, empty input, reuse of one planner."""
+    rng = np.random.default_rng(G)
+    N = 5003
+    planners = [NativePlanner(N, G, r) for r in range(G)]
+    cases = []
+    for B in (1, 7, 400, 20000):
+        cases.append((rng.integers(0, N, B), rng.integers(0, N, B)))
+        cases.append(((rng.zipf(1.3, B) - 1) % N, (rng.zipf(1.3, B) - 1) % N))
+    a = rng.integers(0, N, 300)
+    cases.append((a, a.copy()))                                         # self pairs: nothing crosses
+    cases.append((np.full(500, G), np.arange(500) * G + 1 if G > 1 else np.arange(500)))   # one owner, all remote
+    cases.append((np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)))
+    for first, second in cases + cases[:3]:                             # again: the scratch state must be clean
+        first, second = first.astype(np.int64), second.astype(np.int64)
+        for r in range(G):
+            n_local = rows_on_rank(N, G, r)
+            want = make_plan(first, second, G, r, n_local)
+            got = planners[r].plan(first, second, n_local)
+            assert _same_plan(got, want), (G, r, len(first))
+    with pytest.raises(IndexError):
+        planners[0].plan(np.array([1, N], dtype=np.int64), np.array([2, 3], dtype=np.int64), rows_on_rank(N, G, 0))
+    # ... and the failed call left nothing behind
+    f, s2 = cases[1]
+    assert _same_plan(planners[0].plan(f.astype(np.int64), s2.astype(np.int64), rows_on_rank(N, G, 0)),
+                      make_plan(f.astype(np.int64), s2.astype(np.int64), G, 0, rows_on_rank(N, G, 0)))
 
 
 def _worker(rank, world, port, N, d, L, lam, batches, p0, result_dir):

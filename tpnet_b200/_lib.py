@@ -20,7 +20,7 @@ TPN_ERR_UNSUPPORTED = -5
 TPN_ERR_INDEX = -6
 STAGE_RAW, STAGE_ID_WRAP, STAGE_ID = 0, 1, 2
 TPN_MAX_LAYERS = 4
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 #: every symbol include/tpnet_b200.h declares (tests assert the .so exports all of them)
 EXPORTED_SYMBOLS = (
@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = (
     'tpn_materialize', 'tpn_reset_epoch', 'tpn_clear_walk_layers',
     'tpn_stager_create', 'tpn_stager_destroy', 'tpn_stage',
     'tpn_update_messages', 'tpn_gather_blocks', 'tpn_set_debug_flags', 'tpn_pairwise_neighbors', 'tpn_head_forward',
+    'tpn_planner_create', 'tpn_planner_destroy', 'tpn_plan',
 )
 
 
@@ -93,6 +94,13 @@ def _declare(lib: ctypes.CDLL) -> None:
         fn = getattr(lib, name)
         fn.restype = c_int
         fn.argtypes = [POINTER(TpnState), c_void_p]
+    lib.tpn_planner_create.restype = c_int
+    lib.tpn_planner_create.argtypes = [POINTER(c_void_p), c_int64, c_int, c_int]
+    lib.tpn_planner_destroy.restype = None
+    lib.tpn_planner_destroy.argtypes = [c_void_p]
+    lib.tpn_plan.restype = c_int
+    lib.tpn_plan.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                             POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, c_void_p]
     lib.tpn_stager_create.restype = c_int
     lib.tpn_stager_create.argtypes = [POINTER(c_void_p), c_size_t, c_int]
     lib.tpn_stager_destroy.restype = None

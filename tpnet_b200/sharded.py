@@ -100,6 +100,44 @@ def make_plan(first: np.ndarray, second: np.ndarray, world: int, rank: int, n_lo
                      recv_counts=[int(c) for c in recv_counts])
 
 
+class NativePlanner:
+    """`make_plan` computed by the library (csrc/tpn_plan.cu: two linear passes, no sort of the batch) —
+    same plan, field for field (tests/test_sharded_cpu.py), 10x faster on 100k-edge batches."""
+
+    def __init__(self, global_node_num: int, world: int, rank: int):
+        self._lib = _lib.load()
+        self.world, self.rank = int(world), int(rank)
+        self.handle = ctypes.c_void_p()
+        _lib.check(self._lib.tpn_planner_create(ctypes.byref(self.handle), int(global_node_num), self.world, self.rank),
+                   'tpn_planner_create')
+
+    def plan(self, first: np.ndarray, second: np.ndarray, n_local: int) -> ShardPlan:
+        first = np.ascontiguousarray(first, dtype=np.int64)
+        second = np.ascontiguousarray(second, dtype=np.int64)
+        m = int(first.shape[0])
+        if second.shape[0] != m:
+            raise ValueError('first and second must have the same length')
+        keep, rows1, rows2, send = (np.empty(max(m, 1), dtype=np.int64) for _ in range(4))
+        sc, rc_ = np.zeros(self.world, dtype=np.int64), np.zeros(self.world, dtype=np.int64)
+        nk, ns = ctypes.c_int64(0), ctypes.c_int64(0)
+        rc = self._lib.tpn_plan(self.handle, first.ctypes.data, second.ctypes.data, m, int(n_local), keep.ctypes.data,
+                                rows1.ctypes.data, rows2.ctypes.data, ctypes.byref(nk), send.ctypes.data,
+                                ctypes.byref(ns), sc.ctypes.data, rc_.ctypes.data)
+        if rc == _lib.TPN_ERR_INDEX:
+            raise IndexError('node id out of range in a sharded batch')
+        _lib.check(rc, 'tpn_plan')
+        return ShardPlan(keep=keep[:nk.value], first_rows=rows1[:nk.value], second_rows=rows2[:nk.value],
+                         send_rows=send[:ns.value], send_counts=[int(c) for c in sc], recv_counts=[int(c) for c in rc_])
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._lib.tpn_planner_destroy(self.handle)
+                self.handle = ctypes.c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
+
+
 def update_messages(src: np.ndarray, dst: np.ndarray, t: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """The 2B messages of one edge batch in the reference's accumulation order: all
     (target=src, source=dst) in batch order, then all (target=dst, source=src) — the two
@@ -156,6 +194,7 @@ class ShardedRandomProjection(RandomProjectionModule):
         self.exchanged_rows = 0          # rows received so far (bench accounting)
         self._send_buf: Optional[torch.Tensor] = None
         self._all_keep: Optional[np.ndarray] = None
+        self._planner: Optional[NativePlanner] = None
 
     # ------------------------------------------------------------------ helpers
     def init_p0_on_device(self, seed: int) -> None:
@@ -197,10 +236,17 @@ class ShardedRandomProjection(RandomProjectionModule):
         self.exchanged_rows += R
 
     # ------------------------------------------------------------------ API
+    def _make_plan(self, first: np.ndarray, second: np.ndarray) -> ShardPlan:
+        if self.world == 1:
+            return make_plan(first, second, 1, 0, self.n_local)
+        if self._planner is None:
+            self._planner = NativePlanner(self.global_node_num, self.world, self.rank)
+        return self._planner.plan(first, second, self.n_local)
+
     def plan_update(self, src: np.ndarray, dst: np.ndarray, t: np.ndarray):
         tgt, oth, tm = update_messages(np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64),
                                        np.asarray(t, dtype=np.float64))
-        plan = make_plan(tgt, oth, self.world, self.rank, self.n_local)
+        plan = self._make_plan(tgt, oth)
         return plan, np.ascontiguousarray(tm[plan.keep])
 
     def update(self, src_node_ids, dst_node_ids, node_interact_times, next_time=None, plan=None):
@@ -275,8 +321,7 @@ class ShardedRandomProjection(RandomProjectionModule):
                     self.random_projections[i].mul_(float(factors[i - 1]))
 
     def plan_pairs(self, a_ids: np.ndarray, b_ids: np.ndarray) -> ShardPlan:
-        return make_plan(np.asarray(a_ids, dtype=np.int64), np.asarray(b_ids, dtype=np.int64), self.world, self.rank,
-                         self.n_local)
+        return self._make_plan(np.asarray(a_ids, dtype=np.int64), np.asarray(b_ids, dtype=np.int64))
 
     def pair_wise_gram(self, src_node_ids, dst_node_ids, plan: Optional[ShardPlan] = None):
         """Features (input of self.mlp, TPNet.py:119-128) of the pairs whose first endpoint this
