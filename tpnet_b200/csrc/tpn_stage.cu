@@ -41,19 +41,23 @@ void release(tpn_stager* sg) {
     sg->used = nullptr;
 }
 
-// host threads of the staging pass: TPN_STAGE_THREADS, else min(8, cores / 2)
+// host threads of the staging pass: TPN_STAGE_THREADS, else min(8, cores / 2) — and never more than the
+// process allows itself (OMP_NUM_THREADS / omp_set_num_threads: torchrun gives every rank 1 thread, the
+// reference scripts ask for 3)
 int stage_threads() {
-    static int n = 0;
-    if (n == 0) {
+    static int base = 0;
+    if (base == 0) {
         const char* env = getenv("TPN_STAGE_THREADS");
         int v = env != nullptr ? atoi(env) : 0;
         if (v < 1) {
             v = omp_get_num_procs() / 2;
             v = v > 8 ? 8 : v;
         }
-        n = v < 1 ? 1 : (v > 64 ? 64 : v);
+        base = v < 1 ? 1 : (v > 64 ? 64 : v);
     }
-    return n;
+    if (getenv("TPN_STAGE_THREADS") != nullptr) return base;
+    const int allowed = omp_get_max_threads();
+    return allowed < base ? (allowed < 1 ? 1 : allowed) : base;
 }
 
 int allocate(tpn_stager* sg, size_t slot_bytes, int slots) {
