@@ -57,7 +57,7 @@
 extern "C" {
 #endif
 
-#define TPN_ABI_VERSION 6
+#define TPN_ABI_VERSION 7
 
 #define TPN_MAX_LAYERS 4
 
@@ -249,6 +249,22 @@ int tpn_stager_create(tpn_stager_t** out, size_t slot_bytes, int slots);
 void tpn_stager_destroy(tpn_stager_t* sg);
 int tpn_stage(tpn_stager_t* sg, const void* const* host, const int64_t* elems, const int* kinds, int count,
               int64_t num_nodes, void** dev_out, void* stream);
+
+/*
+ * The reference's `recent` historical-neighbour sampler — NeighborSampler.get_historical_neighbors,
+ * utils/utils.py:160-224 with sample_neighbor_strategy == 'recent' (SURVEY.md 8(f) N2).
+ * Adjacency as one CSR on the device: entries of node u are [offsets[u], offsets[u+1]), stably sorted by
+ * time (both directions of every edge, utils/utils.py:248-251).  For query i: the num_neighbors most recent
+ * entries of q_nodes[i] with time STRICTLY before q_times[i] (np.searchsorted 'left', :151), written to the
+ * back of row i of the outputs; the front is zero-padded (:211-218).
+ *   offsets_dev int64[num_nodes+1]; nbr_dev, eid_dev int64[2E]; times_dev float64[2E]
+ *   q_nodes_dev int64[n], q_times_dev float64[n]
+ *   out_nbr_dev, out_eid_dev int64[n][num_neighbors]; out_times_dev float64[n][num_neighbors]
+ */
+int tpn_sampler_recent(const int64_t* offsets_dev, const int64_t* nbr_dev, const int64_t* eid_dev,
+                       const double* times_dev, int64_t num_nodes, const int64_t* q_nodes_dev,
+                       const double* q_times_dev, int64_t n, int num_neighbors, int64_t* out_nbr_dev,
+                       int64_t* out_eid_dev, double* out_times_dev, void* stream);
 
 /*
  * Host-side routing plan of the node-sharded state (tpnet_b200/sharded.py; no reference counterpart —

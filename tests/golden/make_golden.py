@@ -246,5 +246,38 @@ def main():
     print('matrix_kat: reference and oracle match the exhaustive walk enumeration')
 
 
+def sampler_fixture():
+    """`recent` NeighborSampler (utils/utils.py:70-224) vs oracle/neighbor_sampler.py."""
+    from utils.DataLoader import Data                     # the reference's containers
+    from utils.utils import get_neighbor_sampler
+
+    from oracle.neighbor_sampler import RecentNeighborOracle
+    rng = np.random.default_rng(77)
+    N, E = 37, 400
+    src = 1 + (rng.zipf(1.4, E) - 1) % (N - 1)
+    dst = 1 + (rng.zipf(1.4, E) - 1) % (N - 1)
+    src[5], dst[5] = 9, 9                                  # a self loop
+    src[7], dst[7] = src[6], dst[6]                        # a repeated edge
+    t = np.sort(np.floor(rng.random(E) * 60.0))            # many equal timestamps
+    eid = np.arange(1, E + 1)
+    data = Data(src_node_ids=src.astype(np.longlong), dst_node_ids=dst.astype(np.longlong),
+                node_interact_times=t.astype(np.float64), edge_ids=eid.astype(np.longlong), labels=np.zeros(E))
+    ref = get_neighbor_sampler(data=data, sample_neighbor_strategy='recent', seed=0)
+    orc = RecentNeighborOracle(src, dst, eid, t, N)
+    out = {'src': src.astype(np.int64), 'dst': dst.astype(np.int64), 'eid': eid.astype(np.int64), 't': t, 'num_nodes': np.int64(N)}
+    for k, K in enumerate((1, 5, 20)):
+        qn = rng.integers(0, N, 300).astype(np.int64)      # includes node 0 (padding: no history)
+        qt = np.where(rng.random(300) < 0.5, np.floor(rng.random(300) * 62.0), rng.random(300) * 62.0)
+        a = ref.get_historical_neighbors(qn, qt, num_neighbors=K)
+        b = orc.get_historical_neighbors(qn, qt, num_neighbors=K)
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and np.array_equal(x, y), f'sampler oracle != reference (K={K})'
+        out[f'q{k}_nodes'], out[f'q{k}_times'], out[f'q{k}_K'] = qn, qt, np.int64(K)
+        out[f'q{k}_nbr'], out[f'q{k}_eid'], out[f'q{k}_t'] = (np.asarray(v) for v in a)
+    np.savez_compressed(os.path.join(HERE, 'sampler_tiny.npz'), **out)
+    print('sampler_tiny: oracle equals the reference NeighborSampler (recent) for K = 1, 5, 20')
+
+
 if __name__ == '__main__':
     main()
+    sampler_fixture()

@@ -200,3 +200,67 @@ def test_add_at_equals_loop():
         b.update(s, d, ts)
     for i in range(4):
         assert np.array_equal(a.P[i], b.P[i])
+
+
+# --------------------------------------------------------------------------- `recent` neighbour sampler
+def _sampler_case():
+    import os
+    from golden_util import GOLDEN_DIR
+    return np.load(os.path.join(GOLDEN_DIR, 'sampler_tiny.npz'))
+
+
+def test_sampler_oracle_matches_reference_fixture():
+    """oracle/neighbor_sampler.py vs the outputs of the reference's NeighborSampler ('recent', utils/utils.py:160-224)
+    stored by tests/golden/make_golden.py: equal timestamps, a self loop, a repeated edge, node 0, K = 1, 5, 20."""
+    from oracle.neighbor_sampler import RecentNeighborOracle
+    z = _sampler_case()
+    o = RecentNeighborOracle(z['src'], z['dst'], z['eid'], z['t'], int(z['num_nodes']))
+    for k in range(3):
+        got = o.get_historical_neighbors(z[f'q{k}_nodes'], z[f'q{k}_times'], int(z[f'q{k}_K']))
+        for x, name in zip(got, ('nbr', 'eid', 't')):
+            assert np.array_equal(x, z[f'q{k}_{name}']) and x.dtype == z[f'q{k}_{name}'].dtype
+        assert not got[0][z[f'q{k}_nodes'] == 0].any()                  # the padding node has no history
+
+
+def _kernel_arithmetic(offsets, nbr, eid, times, num_nodes, q_nodes, q_times, K):
+    """The index arithmetic of csrc/tpn_sampler.cu (one query per warp), line for line, on the host."""
+    n = len(q_nodes)
+    out_n, out_e, out_t = np.zeros((n, K), np.int64), np.zeros((n, K), np.int64), np.zeros((n, K), np.float64)
+    for q in range(n):
+        node, t = int(q_nodes[q]), float(q_times[q])
+        begin = end = 0
+        if 0 <= node < num_nodes:
+            begin, end = int(offsets[node]), int(offsets[node + 1])
+        a, b = begin, end
+        while a < b:
+            mid = a + ((b - a) >> 1)
+            if times[mid] < t:
+                a = mid + 1
+            else:
+                b = mid
+        take = min(a - begin, K)
+        first, pad = a - take, K - take
+        for j in range(K):
+            if j >= pad:
+                s = first + (j - pad)
+                out_n[q, j], out_e[q, j], out_t[q, j] = nbr[s], eid[s], times[s]
+    return out_n, out_e, out_t
+
+
+def test_sampler_host_logic_and_kernel_arithmetic():
+    """The product's CSR builder (host logic, tpnet_b200/neighbor_sampler.py) equals the oracle's adjacency, and
+    the kernel's search / padding arithmetic over it reproduces the reference outputs."""
+    from oracle.neighbor_sampler import RecentNeighborOracle
+    from tpnet_b200.neighbor_sampler import RecentNeighborSampler, build_recent_csr
+    z = _sampler_case()
+    N = int(z['num_nodes'])
+    off, nbr, eid, tt = build_recent_csr(z['src'], z['dst'], z['eid'], z['t'], N)
+    o = RecentNeighborOracle(z['src'], z['dst'], z['eid'], z['t'], N)
+    assert np.array_equal(off, o.offsets) and np.array_equal(nbr, o.nbr) and np.array_equal(eid, o.eid)
+    assert np.array_equal(tt, o.times) and off[0] == 0 and off[1] == 0 and off[-1] == 2 * len(z['src'])
+    for k in range(3):
+        got = _kernel_arithmetic(off, nbr, eid, tt, N, z[f'q{k}_nodes'], z[f'q{k}_times'], int(z[f'q{k}_K']))
+        for x, name in zip(got, ('nbr', 'eid', 't')):
+            assert np.array_equal(x, z[f'q{k}_{name}'])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        RecentNeighborSampler(z['src'], z['dst'], z['eid'], z['t'], device='cpu')

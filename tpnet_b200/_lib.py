@@ -20,7 +20,7 @@ TPN_ERR_UNSUPPORTED = -5
 TPN_ERR_INDEX = -6
 STAGE_RAW, STAGE_ID_WRAP, STAGE_ID = 0, 1, 2
 TPN_MAX_LAYERS = 4
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 #: every symbol include/tpnet_b200.h declares (tests assert the .so exports all of them)
 EXPORTED_SYMBOLS = (
@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     'tpn_materialize', 'tpn_reset_epoch', 'tpn_clear_walk_layers',
     'tpn_stager_create', 'tpn_stager_destroy', 'tpn_stage',
     'tpn_update_messages', 'tpn_gather_blocks', 'tpn_set_debug_flags', 'tpn_pairwise_neighbors', 'tpn_head_forward',
-    'tpn_planner_create', 'tpn_planner_destroy', 'tpn_plan',
+    'tpn_planner_create', 'tpn_planner_destroy', 'tpn_plan', 'tpn_sampler_recent',
 )
 
 
@@ -94,6 +94,9 @@ def _declare(lib: ctypes.CDLL) -> None:
         fn = getattr(lib, name)
         fn.restype = c_int
         fn.argtypes = [POINTER(TpnState), c_void_p]
+    lib.tpn_sampler_recent.restype = c_int
+    lib.tpn_sampler_recent.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.tpn_planner_create.restype = c_int
     lib.tpn_planner_create.argtypes = [POINTER(c_void_p), c_int64, c_int, c_int]
     lib.tpn_planner_destroy.restype = None

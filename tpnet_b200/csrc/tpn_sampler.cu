@@ -1,0 +1,79 @@
+// tpn_sampler — the reference's `recent` historical-neighbour sampler on the GPU
+// (utils/utils.py:160-224, NeighborSampler.get_historical_neighbors with
+// sample_neighbor_strategy == 'recent').
+//
+// The reference walks a Python loop over the batch: per (node, time) a np.searchsorted on the node's
+// time-sorted adjacency and three slice copies — 5.5 ms per 400-row batch, the end-to-end bottleneck
+// once the projections are fast.  Here the adjacency is one CSR on the device (built once per sampler
+// by the host class: per node, entries stably sorted by timestamp) and a query is one warp:
+//   i    = first entry of the node with time >= t            (searchsorted 'left': strictly before t)
+//   take = min(i - begin, K) most recent entries before t, written to the BACK of a zero row
+// Outputs (neighbour ids, edge ids, times; [n, K]) stay on the device, so the structured pair-wise call
+// (tpn_pairwise_neighbors) can consume the ids without a host round trip.
+#include "tpn_common.cuh"
+
+namespace tpn {
+namespace {
+
+__global__ void __launch_bounds__(256)
+sampler_recent_kernel(const long long* __restrict__ offsets, const long long* __restrict__ nbr,
+                      const long long* __restrict__ eid, const double* __restrict__ times, long long num_nodes,
+                      const long long* __restrict__ q_nodes, const double* __restrict__ q_times, long long n, int K,
+                      long long* __restrict__ out_nbr, long long* __restrict__ out_eid, double* __restrict__ out_t) {
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= n) return;
+    const long long node = q_nodes[q];
+    const double t = q_times[q];
+    long long begin = 0, end = 0;
+    if (node >= 0 && node < num_nodes) {
+        begin = offsets[node];
+        end = offsets[node + 1];
+    }
+    long long a = begin, b = end;                   // every lane runs the same search (broadcast loads)
+    while (a < b) {
+        const long long mid = a + ((b - a) >> 1);
+        if (times[mid] < t) a = mid + 1; else b = mid;
+    }
+    const long long cnt = a - begin;
+    const int take = (int)(cnt < (long long)K ? cnt : (long long)K);
+    const long long first = a - take;               // entries first .. a-1 are the `take` most recent before t
+    const int pad = K - take;
+    for (int j = lane; j < K; j += 32) {
+        long long vn = 0, ve = 0;
+        double vt = 0.0;
+        if (j >= pad) {
+            const long long s = first + (j - pad);
+            vn = nbr[s];
+            ve = eid[s];
+            vt = times[s];
+        }
+        out_nbr[q * K + j] = vn;
+        out_eid[q * K + j] = ve;
+        out_t[q * K + j] = vt;
+    }
+}
+
+}  // namespace
+}  // namespace tpn
+
+extern "C" int tpn_sampler_recent(const int64_t* offsets_dev, const int64_t* nbr_dev, const int64_t* eid_dev,
+                                  const double* times_dev, int64_t num_nodes, const int64_t* q_nodes_dev,
+                                  const double* q_times_dev, int64_t n, int num_neighbors, int64_t* out_nbr_dev,
+                                  int64_t* out_eid_dev, double* out_times_dev, void* stream_v) {
+    using namespace tpn;
+    if (n < 0 || num_neighbors < 1 || num_nodes < 1 || n > ((int64_t)1 << 40)) return TPN_ERR_INVALID_ARGUMENT;
+    if (n == 0) return TPN_OK;
+    if (offsets_dev == nullptr || nbr_dev == nullptr || eid_dev == nullptr || times_dev == nullptr ||
+        q_nodes_dev == nullptr || q_times_dev == nullptr || out_nbr_dev == nullptr || out_eid_dev == nullptr ||
+        out_times_dev == nullptr)
+        return TPN_ERR_INVALID_ARGUMENT;
+    const long long blocks = (n * 32 + 255) / 256;
+    if (blocks > 0x7fffffffll) return TPN_ERR_INVALID_ARGUMENT;
+    sampler_recent_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+        reinterpret_cast<const long long*>(offsets_dev), reinterpret_cast<const long long*>(nbr_dev),
+        reinterpret_cast<const long long*>(eid_dev), times_dev, num_nodes,
+        reinterpret_cast<const long long*>(q_nodes_dev), q_times_dev, n, num_neighbors,
+        reinterpret_cast<long long*>(out_nbr_dev), reinterpret_cast<long long*>(out_eid_dev), out_times_dev);
+    return check_launch();
+}
