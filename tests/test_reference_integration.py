@@ -100,3 +100,28 @@ def test_launcher_runs_a_reference_style_script(in_tmp):
                        capture_output=True, text=True, cwd=repo, timeout=300)
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip().splitlines()[-1] == "tpnet_b200.random_projection ['--dataset_name', 'wikipedia'] checkout 2"
+
+
+def test_launcher_gpu_sampler_option(in_tmp):
+    """`--tpn-gpu-sampler`: consumed by the launcher; `utils.utils.get_neighbor_sampler` keeps the reference's
+    sampler for every strategy but 'recent'."""
+    fake = in_tmp / 'checkout2'
+    (fake / 'models').mkdir(parents=True)
+    (fake / 'utils').mkdir()
+    (fake / 'models' / '__init__.py').write_text('')
+    (fake / 'utils' / '__init__.py').write_text('')
+    (fake / 'models' / 'TPNet.py').write_text('class RandomProjectionModule:\n    pass\n')
+    (fake / 'utils' / 'utils.py').write_text(
+        'def get_neighbor_sampler(data, sample_neighbor_strategy="uniform", time_scaling_factor=0.0, seed=None):\n'
+        '    return ("reference sampler", sample_neighbor_strategy, seed)\n')
+    (fake / 'probe.py').write_text(
+        'import sys\n'
+        'from utils.utils import get_neighbor_sampler\n'
+        'print(get_neighbor_sampler(data=None, sample_neighbor_strategy="uniform", seed=3), '
+        'getattr(get_neighbor_sampler, "_tpn_gpu_sampler", False), sys.argv[1:])\n')
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(tpnet_b200.__file__)))
+    for extra, patched in (([], False), (['--tpn-gpu-sampler'], True)):
+        r = subprocess.run([sys.executable, '-m', 'tpnet_b200.launch', str(fake), 'probe.py', '--gpu', '1'] + extra,
+                           capture_output=True, text=True, cwd=repo, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.strip().splitlines()[-1] == f"('reference sampler', 'uniform', 3) {patched} ['--gpu', '1']"

@@ -62,6 +62,10 @@ class RecentNeighborSampler:
             self._eid = torch.zeros(1, dtype=torch.int64, device=dev)
             self._times = torch.zeros(1, dtype=torch.float64, device=dev)
         self.sample_neighbor_strategy = 'recent'
+        self.seed = None                                    # attributes / methods the reference's callers touch
+
+    def reset_random_state(self) -> None:
+        """`recent` sampling is deterministic: nothing to reset (utils/utils.py:316-321 exists for the random strategies)."""
 
     def _to_device(self, a: ArrayOrTensor, dtype: torch.dtype) -> torch.Tensor:
         if isinstance(a, torch.Tensor):
