@@ -45,6 +45,7 @@ WARM_BATCHES = 400          # untimed: populates P_1..P_L and the neighbour tabl
 PL_BATCH = 100_000          # power-law batch (configs[3])
 PL_WARM = 12
 METRIC = 'temporal edges/sec (update+pairwise encode)'
+REF_THREADS = 3             # the reference pins torch to 3 intra-op threads (train_link_prediction.py:124)
 
 
 def parse_args():
@@ -59,6 +60,7 @@ def parse_args():
     ap.add_argument('--no-graphs', action='store_true', help='power-law, 1 GPU: launch the steps eagerly instead of as CUDA graphs')
     ap.add_argument('--no-also', action='store_true', help='N=1: skip the secondary Reddit-shaped measurement')
     ap.add_argument('--cpu-sample-steps', type=int, default=None)
+    ap.add_argument('--cpu-threads', type=int, default=None, help='--impl reference: host threads (default: all cores)')
     ap.add_argument('--warm-batches', type=int, default=None, help='untimed batches that fill the state')
     ap.add_argument('--pl-nodes', type=int, default=None, help='override the power-law node count (debug)')
     ap.add_argument('--pl-batch', type=int, default=PL_BATCH, help='power-law: edges per step and GPU')
@@ -328,9 +330,13 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
         threads = os.cpu_count() or 1
         n_cpu = args.cpu_sample_steps or 30
         sec = cpu_port_tpnet(shape, warm_batches, steps, 2, n_cpu, threads)
+        sec3 = cpu_port_tpnet(shape, warm_batches, steps, 2, n_cpu, REF_THREADS)
         out['cpu_baseline'] = {'value': BATCH / sec, 'unit': 'edges/s', 'cores': threads, 'kind': 'port',
                                'sample': f'{n_cpu} steps of the same workload on the host (torch-CPU port of the '
-                                         f'reference, self.mlp included, {sec * 1e3:.1f} ms/step)'}
+                                         f'reference, self.mlp included, {sec * 1e3:.1f} ms/step)',
+                               'at_reference_threads': {'value': BATCH / sec3, 'cores': REF_THREADS,
+                                                        'note': 'torch.set_num_threads(3), the reference\'s own setting '
+                                                                '(train_link_prediction.py:124)'}}
     del graphs, pair_graphs, m, flush
     torch.cuda.empty_cache()
     return out
@@ -606,7 +612,7 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    threads = os.cpu_count() or 1
+    threads = args.cpu_threads or os.cpu_count() or 1
 
     # ---------------- reference arm: CPU port on the host cores, rank 0 only
     if args.impl == 'reference':
@@ -658,11 +664,15 @@ def main():
             if world == 1:
                 n_cpu = args.cpu_sample_steps or 3
                 sec, n_small = cpu_port_powerlaw(powerlaw_shape(args), args.pl_batch, 1, n_cpu, threads, scale_down=10)
+                sec3, _ = cpu_port_powerlaw(powerlaw_shape(args), args.pl_batch, 1, 1, REF_THREADS, scale_down=10)
                 line['cpu_baseline'] = {'value': args.pl_batch / sec, 'unit': 'edges/s', 'cores': threads,
                                         'kind': 'port',
                                         'sample': f'{n_cpu} batches on a {n_small}-node replica (10x fewer nodes than '
                                                   f'the GPU run; torch-CPU port of the reference, self.mlp included, '
-                                                  f'{sec:.2f} s/step)'}
+                                                  f'{sec:.2f} s/step)',
+                                        'at_reference_threads': {'value': args.pl_batch / sec3, 'cores': REF_THREADS,
+                                                                 'note': 'torch.set_num_threads(3), the reference\'s own '
+                                                                         'setting (train_link_prediction.py:124); 1 batch'}}
                 if not args.no_also:
                     line['also'] = {'reddit': run_tpnet_shape(args, SHAPES['reddit'], device, 300, 10, with_cpu=True)}
             else:
