@@ -61,9 +61,15 @@ constexpr int kSmallWalkThreads = 256;
 constexpr int kHub2Producers = 7;        // producer warps: each keeps one ring stage (32 messages) of loads in flight
 constexpr int kHub2Threads = (1 + kHub2Producers) * 32;    // + the consumer warp (warp 0)
 constexpr int kHub2SlotFloats = 64;      // floats of one message held by a ring slot (consumer: 2 columns per lane)
-constexpr int kHub2GiantFloats = 16;     // slice width of giant segments: an SM sustains ~10 B/clk of row gathers
+#ifndef TPN_HUB2_GIANT_FLOATS
+#define TPN_HUB2_GIANT_FLOATS 16         // A/B builds: -DTPN_HUB2_GIANT_FLOATS=32 (128-byte slices: full cache lines,
+#endif                                   // half the work items; scripts/micro/gather_paths.cu says same message rate)
+constexpr int kHub2GiantFloats = TPN_HUB2_GIANT_FLOATS;     // slice width of giant segments: an SM sustains ~10 B/clk of row gathers
                                          // (outstanding-miss capacity), so 64 B per message keeps its data path
                                          // near the add chain's 4-6 cycles per message
+static_assert(kHub2GiantFloats == 16 || kHub2GiantFloats == 32, "giant slices are 64 or 128 bytes");
+constexpr int kGiantLs = kHub2GiantFloats == 16 ? 2 : 3;   // log2(lanes per giant message): 4 or 8 lanes of 16 bytes
+constexpr int kGiantSpm = 16 >> kGiantLs;                  // 32-message sub-blocks per ring stage: 4 or 2
 constexpr int kHub2Stages = kHub2Producers + 4;            // ring stages of 32 messages (8 KB each)
 // ctr[] slots (zeroed by prep_large_kernel)
 constexpr int kCtrGiant = 0, kCtrHub = 1, kCtrWork0 = 2, kCtrSmall = 6, kCtrHub2Work = 7, kCtrHub2Giant = 8;
@@ -1267,7 +1273,7 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
         const uint32_t key = skey[head];
         // a ring stage (8 KB) holds 32 messages of <= 64 floats, or — giants — 128 messages of <= 16 floats:
         // four times fewer full/empty handshakes on the critical chain
-        const int spm = giant ? 4 : 1;                  // 32-message sub-blocks per stage
+        const int spm = giant ? kGiantSpm : 1;          // 32-message sub-blocks per stage
         const int slot = giant ? kHub2GiantFloats : kHub2SlotFloats;      // floats between messages of a stage
         const int mps = 32 * spm;                       // messages per stage
         const int nblk = (len + mps - 1) / mps;
@@ -1276,7 +1282,7 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                 // ------------------------------------------------ producers
                 const int pw = warp - 1;
                 const int nvec = width >> 2;            // 16-byte pieces per message (<= 4 giant, <= 16 otherwise)
-                const int lpm_shift = giant ? 2 : 4;    // lanes per message: 4 or 16
+                const int lpm_shift = giant ? kGiantLs : 4;    // lanes per message: 4 (8) or 16
                 const int grp = lane >> lpm_shift, sub = lane & ((1 << lpm_shift) - 1);
                 // received source rows (sharded state): this call's decay of source row r (P_0 never decays)
                 const float dfac = (DIRECT && LAZY && dnow.has_decay && r >= 1)
@@ -1325,11 +1331,11 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                     float4 xv[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
-                        const int sb = giant ? (q >> 2) : 0;
-                        const int i = giant ? (q & 3) : q;
+                        const int sb = giant ? (q >> kGiantLs) : 0;
+                        const int i = giant ? (q & ((1 << kGiantLs) - 1)) : q;
                         const int m = mpi * i + grp;                       // message inside the sub-block
-                        const unsigned lo = __shfl_sync(0xffffffffu, giant ? plo[q >> 2] : plo[0], m);
-                        const unsigned hi = __shfl_sync(0xffffffffu, giant ? phi[q >> 2] : phi[0], m);
+                        const unsigned lo = __shfl_sync(0xffffffffu, giant ? plo[q >> kGiantLs] : plo[0], m);
+                        const unsigned hi = __shfl_sync(0xffffffffu, giant ? phi[q >> kGiantLs] : phi[0], m);
                         const float* pj = reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
                         xv[q] = (sb * 32 + m < nm && sub < nvec) ? ld4(pj + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
@@ -1344,11 +1350,11 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
 #endif
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
-                        const int sb = giant ? (q >> 2) : 0;
-                        const int i = giant ? (q & 3) : q;
+                        const int sb = giant ? (q >> kGiantLs) : 0;
+                        const int i = giant ? (q & ((1 << kGiantLs) - 1)) : q;
                         const int m = mpi * i + grp;
-                        const float w = __shfl_sync(0xffffffffu, giant ? wl[q >> 2] : wl[0], m);
-                        if (DIRECT) scale4(xv[q], __shfl_sync(0xffffffffu, giant ? fl[q >> 2] : fl[0], m));   // x * 1.0f is exact
+                        const float w = __shfl_sync(0xffffffffu, giant ? wl[q >> kGiantLs] : wl[0], m);
+                        if (DIRECT) scale4(xv[q], __shfl_sync(0xffffffffu, giant ? fl[q >> kGiantLs] : fl[0], m));   // x * 1.0f is exact
                         scale4(xv[q], w);
                         if (sub < nvec) st4(dst + (size_t)(sb * 32 + mpi * i) * slot, xv[q]);
                     }
