@@ -81,6 +81,32 @@ def test_native_planner_equals_the_numpy_plan(G):
                       make_plan(f.astype(np.int64), s2.astype(np.int64), G, 0, rows_on_rank(N, G, 0)))
 
 
+def test_sharded_module_plans_with_the_native_builder():
+    """ShardedRandomProjection.plan_update / plan_pairs (the calls bench.py and the public API make) on a stand-in
+    object: world > 1 goes through the library's planner and yields the numpy plan; world == 1 stays in numpy."""
+    from types import SimpleNamespace
+    from tpnet_b200.sharded import ShardedRandomProjection as S
+    rng = np.random.default_rng(9)
+    N, B = 1001, 3000
+    src, dst = rng.integers(1, N, B), rng.integers(1, N, B)
+    t = np.sort(rng.random(B))
+    for world in (1, 2, 4):
+        for rank in range(world):
+            me = SimpleNamespace(world=world, rank=rank, n_local=rows_on_rank(N, world, rank), global_node_num=N,
+                                 _planner=None)
+            me._make_plan = lambda a, b, me=me: S._make_plan(me, a, b)
+            plan, tmsg = S.plan_update(me, src, dst, t)
+            tgt, oth, tm = update_messages(src, dst, t)
+            want = make_plan(tgt, oth, world, rank, me.n_local)
+            assert _same_plan(plan, want) and np.array_equal(tmsg, tm[want.keep])
+            assert (me._planner is None) == (world == 1)
+            pp = S.plan_pairs(me, src, dst)
+            assert _same_plan(pp, make_plan(src, dst, world, rank, me.n_local))
+            for arr in (plan.keep, plan.first_rows, plan.second_rows, plan.send_rows):
+                assert arr.dtype == np.int64 and arr.ndim == 1
+                torch.from_numpy(np.ascontiguousarray(arr))          # what bench.py / the stager do with them
+
+
 def _worker(rank, world, port, N, d, L, lam, batches, p0, result_dir):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
