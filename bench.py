@@ -361,14 +361,16 @@ def powerlaw_steps(shape, B, n, seed=1234):
     return out
 
 
-def cpu_port_powerlaw(shape, B, n_warm, n_timed, threads, scale_down):
-    """CPU port on a down-scaled replica (the reference's eager decay is N-proportional)."""
+def cpu_port_powerlaw(shape, B, n_warm, n_timed, threads, scale_down, device='cpu'):
+    """The reference's op sequence on a down-scaled replica (its eager decay is N-proportional).  device='cpu': the
+    CPU baseline.  A CUDA device: the same stock ATen ops on the GPU (what the unmodified reference does with
+    --gpu 0: pageable H2D of the ids per call, scatter_add_ with float atomics, batched GEMM), wall clock."""
     import dataclasses
     from oracle.cpu_port import CpuWalkProjection
     torch.set_num_threads(threads)
     small = dataclasses.replace(shape, num_src=max(shape.num_src // scale_down, 1000))
     ref = CpuWalkProjection(small.node_num, shape.dim, shape.num_layer, shape.time_decay_weight, 0.0,
-                            not_scale=False, with_mlp=True, seed=0)
+                            not_scale=False, with_mlp=True, seed=0, device=device)
     steps = powerlaw_steps(small, B, n_warm + n_timed)
 
     def one(st):
@@ -381,9 +383,11 @@ def cpu_port_powerlaw(shape, B, n_warm, n_timed, threads, scale_down):
 
     for st in steps[:n_warm]:
         one(st)
+    if device != 'cpu':
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for st in steps[n_warm:]:
-        one(st)
+        one(st)                      # ends in float(...): the device is idle again when it returns
     return (time.perf_counter() - t0) / n_timed, small.node_num
 
 
@@ -673,6 +677,17 @@ def main():
                                         'at_reference_threads': {'value': args.pl_batch / sec3, 'cores': REF_THREADS,
                                                                  'note': 'torch.set_num_threads(3), the reference\'s own '
                                                                          'setting (train_link_prediction.py:124); 1 batch'}}
+                try:                 # reported comparison point only; must never cost the line above
+                    sec_g, n_g = cpu_port_powerlaw(powerlaw_shape(args), args.pl_batch, 2, 5, threads, scale_down=10,
+                                                   device=str(device))
+                    line['aten_gpu_baseline'] = {
+                        'value': args.pl_batch / sec_g, 'unit': 'edges/s', 'ms_per_step': sec_g * 1e3,
+                        'what': f'the reference\'s own op sequence (stock ATen kernels: index, mul, scatter_add_ with float '
+                                f'atomics, batched GEMM, log, Linear head) on the same GPU, numpy inputs, wall clock, 5 '
+                                f'batches on a {n_g}-node replica (10x fewer nodes: eager whole-state decay)'}
+                except Exception as e:      # noqa: BLE001
+                    line['aten_gpu_baseline'] = {'error': repr(e)[:300]}
+                    torch.cuda.empty_cache()
                 if not args.no_also:
                     line['also'] = {'reddit': run_tpnet_shape(args, SHAPES['reddit'], device, 300, 10, with_cpu=True)}
             else:
