@@ -677,17 +677,6 @@ def main():
                                         'at_reference_threads': {'value': args.pl_batch / sec3, 'cores': REF_THREADS,
                                                                  'note': 'torch.set_num_threads(3), the reference\'s own '
                                                                          'setting (train_link_prediction.py:124); 1 batch'}}
-                try:                 # reported comparison point only; must never cost the line above
-                    sec_g, n_g = cpu_port_powerlaw(powerlaw_shape(args), args.pl_batch, 2, 5, threads, scale_down=10,
-                                                   device=str(device))
-                    line['aten_gpu_baseline'] = {
-                        'value': args.pl_batch / sec_g, 'unit': 'edges/s', 'ms_per_step': sec_g * 1e3,
-                        'what': f'the reference\'s own op sequence (stock ATen kernels: index, mul, scatter_add_ with float '
-                                f'atomics, batched GEMM, log, Linear head) on the same GPU, numpy inputs, wall clock, 5 '
-                                f'batches on a {n_g}-node replica (10x fewer nodes: eager whole-state decay)'}
-                except Exception as e:      # noqa: BLE001
-                    line['aten_gpu_baseline'] = {'error': repr(e)[:300]}
-                    torch.cuda.empty_cache()
                 if not args.no_also:
                     line['also'] = {'reddit': run_tpnet_shape(args, SHAPES['reddit'], device, 300, 10, with_cpu=True)}
             else:
