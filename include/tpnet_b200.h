@@ -10,8 +10,10 @@
  *
  * Conventions
  *   - extern "C", POD arguments only; every pointer named `*_dev`/documented as
- *     device memory is a CUDA device pointer on the current device, everything
- *     else is host memory.
+ *     device memory is a CUDA device pointer, everything else is host memory.  All device
+ *     pointers of one call live on ONE device; the call runs there whatever the caller's
+ *     current device is (it is looked up from the state / first device pointer and the
+ *     caller's current device is restored on return), and `stream` must belong to it.
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
  *     never synchronises, never allocates; scratch memory is supplied by the
  *     caller (size from tpn_update_workspace_bytes).
@@ -57,7 +59,7 @@
 extern "C" {
 #endif
 
-#define TPN_ABI_VERSION 7
+#define TPN_ABI_VERSION 8
 
 #define TPN_MAX_LAYERS 4
 
@@ -88,6 +90,11 @@ typedef struct tpn_state {
     double   cum_floor;     /* host mirror: smallest cumulative product in the log (1.0 at epoch 0);
                                maintained by tpn_update / tpn_reset_epoch / tpn_clear_walk_layers.
                                tpn_update returns TPN_ERR_LOG_FULL before it could underflow.   */
+    int32_t* err_flag;      /* device int32 or NULL: set to 1 by tpn_pairwise / tpn_pairwise_neighbors /
+                               tpn_gather / tpn_gather_blocks when a DEVICE-RESIDENT id is outside
+                               [-num_nodes, num_nodes) — the reference's IndexError (TPNet.py:109), which a
+                               kernel cannot raise; negative ids wrap as tensor indexing does; the access is
+                               clamped only to stay in bounds.  The host polls the flag.                */
 } tpn_state_t;
 
 int tpn_version(void);

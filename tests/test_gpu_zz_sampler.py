@@ -56,7 +56,12 @@ def test_sampler_vs_oracle_large(K):
     # nothing to do / ids outside the graph have no history
     e = s.get_historical_neighbors(qn[:0], qt[:0], K)
     assert e[0].shape == (0, K)
-    far = s.get_historical_neighbors(np.array([s.num_nodes + 5, -3], dtype=np.int64), np.array([1e9, 1e9]), K)
+    # host ids outside the graph: IndexError, as the reference's per-node list lookup (utils/utils.py:177) raises;
+    # device-resident ids cannot raise from a kernel: such queries have no history (all-zero rows)
+    with pytest.raises(IndexError):
+        s.get_historical_neighbors(np.array([s.num_nodes + 5, 1], dtype=np.int64), np.array([1e9, 1e9]), K)
+    far = s.get_historical_neighbors(torch.tensor([s.num_nodes + 5, -3], dtype=torch.int64, device=DEV),
+                                     torch.tensor([1e9, 1e9], dtype=torch.float64, device=DEV), K)
     assert not far[0].any() and not far[1].any() and not far[2].any()
     with pytest.raises(NotImplementedError):
         get_neighbor_sampler(Data, 'uniform', device=DEV)

@@ -20,7 +20,7 @@ TPN_ERR_UNSUPPORTED = -5
 TPN_ERR_INDEX = -6
 STAGE_RAW, STAGE_ID_WRAP, STAGE_ID = 0, 1, 2
 TPN_MAX_LAYERS = 4
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 #: every symbol include/tpnet_b200.h declares (tests assert the .so exports all of them)
 EXPORTED_SYMBOLS = (
@@ -47,6 +47,7 @@ class TpnState(ctypes.Structure):
         ('log_capacity', c_int64),
         ('epoch', c_int64),
         ('cum_floor', c_double),
+        ('err_flag', c_void_p),
     ]
 
 

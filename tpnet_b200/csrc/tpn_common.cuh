@@ -19,6 +19,7 @@ struct StateView {
     int* stamps;             // nullptr => eager
     const double* decay_log; // [cap][L] cumulative products of the per-update fp32 factors (row 0 = 1.0)
     long long epoch;         // epoch readers bring rows up to
+    int* err;                // optional device int32 error flag (tpn_state_t::err_flag)
 };
 
 inline StateView make_view(const tpn_state_t* st) {
@@ -32,8 +33,25 @@ inline StateView make_view(const tpn_state_t* st) {
     v.stamps = st->stamps;
     v.decay_log = st->decay_log;
     v.epoch = st->epoch;
+    v.err = st->err_flag;
     return v;
 }
+
+// Every entry point runs on the device that OWNS its buffers, whatever the caller's current device is
+// (the reference scripts only build the string 'cuda:G' and never call torch.cuda.set_device).
+// Restores the caller's device on exit.  `dev` also indexes the per-device "kernel attributes set" tables.
+constexpr int kMaxDevices = 64;
+struct DeviceScope {
+    int prev = -1, dev = -1;
+    bool switched = false;
+    explicit DeviceScope(const void* device_ptr);
+    ~DeviceScope();
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+    int slot() const { return dev >= 0 && dev < kMaxDevices ? dev : 0; }
+};
+// SM count of the current device (cached per device; 148 on B200)
+int device_sm_count();
 
 inline int validate_state(const tpn_state_t* st) {
     if (st == nullptr || st->data == nullptr) return TPN_ERR_INVALID_ARGUMENT;
@@ -51,6 +69,19 @@ inline int validate_state(const tpn_state_t* st) {
 
 void set_cuda_error(cudaError_t e);
 int check_launch();
+
+// Device-resident node id -> row.  Indexing calls (pair-wise, gather: TPNet.py:109 indexes tensors, where
+// negative ids wrap) pass wrap = true.  An id outside the range is the reference's IndexError: it cannot be
+// raised from a kernel, so the flag is set (RandomProjectionModule.check_errors raises) and the id is
+// clamped only to keep the access in bounds.
+__device__ __forceinline__ long long resolve_id(const StateView& st, long long id, bool wrap) {
+    if (wrap && id < 0) id += st.num_nodes;
+    if (id < 0 || id >= st.num_nodes) {
+        if (st.err != nullptr) *st.err = 1;
+        id = id < 0 ? 0 : st.num_nodes - 1;
+    }
+    return id;
+}
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }

@@ -197,7 +197,9 @@ extern "C" int tpn_head_forward(const float* x_dev, int64_t n, int features, int
     if (x_dev == nullptr || w1_dev == nullptr || b1_dev == nullptr || w2_dev == nullptr || b2_dev == nullptr ||
         y_dev == nullptr || ((reinterpret_cast<uintptr_t>(x_dev) | reinterpret_cast<uintptr_t>(y_dev)) & 15) != 0)
         return TPN_ERR_INVALID_ARGUMENT;
-    static bool configured = false;
+    DeviceScope scope(x_dev);
+    static bool configured_tab[kMaxDevices];
+    bool& configured = configured_tab[scope.slot()];
     const int smem = (int)sizeof(HeadSmem);
     if (!configured) {
         const cudaError_t e = cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -207,8 +209,7 @@ extern "C" int tpn_head_forward(const float* x_dev, int64_t n, int features, int
         }
         configured = true;
     }
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = device_sm_count();
     const long long ntiles = (n + kHeadTile - 1) / kHeadTile;
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
     head_forward_kernel<<<grid, kHeadThreads, smem, reinterpret_cast<cudaStream_t>(stream_v)>>>(

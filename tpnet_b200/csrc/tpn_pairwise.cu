@@ -24,6 +24,9 @@
 namespace tpn {
 namespace {
 
+thread_local int g_dev_slot = 0;      // device of the call in progress (set by the entry point)
+
+
 template <int LAYERS, int G, bool LAZY>
 __global__ void __launch_bounds__(kPairThreads)
 pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long long* __restrict__ b_ids,
@@ -48,8 +51,8 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
     long long ida = a_ids[pc], idb = b_ids[pc];
     fill_entry_table<R>(tab[warp], lane);
     // ids are validated on the host for numpy inputs; clamp so a bad device id can never fault
-    ida = ida < 0 ? 0 : (ida >= st.num_nodes ? st.num_nodes - 1 : ida);
-    idb = idb < 0 ? 0 : (idb >= st.num_nodes ? st.num_nodes - 1 : idb);
+    ida = resolve_id(st, ida, true);
+    idb = resolve_id(st, idb, true);
     const int rs4 = (int)(st.row_stride >> 2);
     const float4* pa = reinterpret_cast<const float4*>(st.data + ida * st.node_stride);
     const float4* pb = reinterpret_cast<const float4*>(st.data + idb * st.node_stride);
@@ -139,8 +142,8 @@ pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const lon
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fill_entry_table<R>(tab[warp], lane);
-    ida = ida < 0 ? 0 : (ida >= st.num_nodes ? st.num_nodes - 1 : ida);
-    idb = idb < 0 ? 0 : (idb >= st.num_nodes ? st.num_nodes - 1 : idb);
+    ida = resolve_id(st, ida, true);
+    idb = resolve_id(st, idb, true);
 
     const int rs4 = (int)(st.row_stride >> 2);
     const uint32_t block_bytes = (uint32_t)(H * st.row_stride * 4);       // rows P_0..P_L of one node
@@ -228,7 +231,8 @@ bool launch_tma(const StateView& v, const long long* a, const long long* b, long
     if (smem > 110 * 1024 || 4 * R * R * sizeof(float) > 8 * block_bytes || (block_bytes & 15) != 0 ||
         (v.node_stride & 3) != 0)
         return false;
-    static bool configured[2] = {false, false};
+    static bool configured_tab[kMaxDevices][2];          // per device: the opt-in is a per-device attribute
+    bool* configured = configured_tab[g_dev_slot];
     const bool lazy = v.stamps != nullptr;
     auto kernel = lazy ? pairwise_tma_kernel<LAYERS, true> : pairwise_tma_kernel<LAYERS, false>;
     if (!configured[lazy ? 1 : 0]) {
@@ -280,6 +284,8 @@ extern "C" int tpn_pairwise(const tpn_state_t* st, const int64_t* a_ids_dev, con
     if (a_ids_dev == nullptr || b_ids_dev == nullptr || out_dev == nullptr ||
         (reinterpret_cast<uintptr_t>(out_dev) & 15) != 0)
         return TPN_ERR_INVALID_ARGUMENT;
+    DeviceScope scope(st->data);
+    g_dev_slot = scope.slot();
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     const StateView v = make_view(st);
     const long long* a = reinterpret_cast<const long long*>(a_ids_dev);

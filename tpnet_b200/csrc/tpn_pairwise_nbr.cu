@@ -23,6 +23,9 @@
 namespace tpn {
 namespace {
 
+thread_local int g_dev_slot = 0;      // device of the call in progress (set by the entry point)
+
+
 constexpr int kNbrMaxWarps = 5;     // K = 20 (the reference default) = 5 quads: one pass, 3 CTAs per SM
 constexpr int kNbrG = 8;            // lanes per neighbour
 constexpr int kNbrPPW = 4;          // neighbours per warp pass
@@ -110,7 +113,7 @@ pairwise_nbr_kernel(StateView st, const long long* __restrict__ nbr, const long 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    auto clamp_id = [&](long long id) { return id < 0 ? 0 : (id >= st.num_nodes ? st.num_nodes - 1 : id); };
+    auto clamp_id = [&](long long id) { return resolve_id(st, id, true); };
     const long long ids = clamp_id(src[n]), idd = clamp_id(dst[n]);
     if (threadIdx.x == 0) {
         mbar_expect_tx(&mbar[0], 2 * block_bytes);
@@ -279,7 +282,8 @@ int launch_nbr(const StateView& v, const long long* nbr, const long long* src, c
     const size_t smem = 2 * block_bytes + nw * wb;
     const bool lazy = v.stamps != nullptr;
     auto kernel = lazy ? pairwise_nbr_kernel<LAYERS, true> : pairwise_nbr_kernel<LAYERS, false>;
-    static bool configured[2] = {false, false};
+    static bool configured_tab[kMaxDevices][2];          // per device
+    bool* configured = configured_tab[g_dev_slot];
     if (!configured[lazy ? 1 : 0]) {
         const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) {
@@ -306,6 +310,8 @@ extern "C" int tpn_pairwise_neighbors(const tpn_state_t* st, const int64_t* nbr_
     if (nbr_dev == nullptr || src_dev == nullptr || dst_dev == nullptr || out_dev == nullptr ||
         (reinterpret_cast<uintptr_t>(out_dev) & 15) != 0)
         return TPN_ERR_INVALID_ARGUMENT;
+    DeviceScope scope(st->data);
+    g_dev_slot = scope.slot();
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     const StateView v = make_view(st);
     const long long* nb = reinterpret_cast<const long long*>(nbr_dev);

@@ -70,6 +70,7 @@ extern "C" int tpn_sampler_recent(const int64_t* offsets_dev, const int64_t* nbr
         return TPN_ERR_INVALID_ARGUMENT;
     const long long blocks = (n * 32 + 255) / 256;
     if (blocks > 0x7fffffffll) return TPN_ERR_INVALID_ARGUMENT;
+    DeviceScope scope(offsets_dev);
     sampler_recent_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
         reinterpret_cast<const long long*>(offsets_dev), reinterpret_cast<const long long*>(nbr_dev),
         reinterpret_cast<const long long*>(eid_dev), times_dev, num_nodes,

@@ -109,6 +109,7 @@ extern "C" int tpn_stage(tpn_stager_t* sg, const void* const* host, const int64_
     if (sg == nullptr || host == nullptr || elems == nullptr || kinds == nullptr || dev_out == nullptr ||
         count < 1 || count > 8)
         return TPN_ERR_INVALID_ARGUMENT;
+    tpn::DeviceScope scope(sg->dev[0]);               // the ring lives on the device it was created on
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     size_t total = 0;
     for (int i = 0; i < count; ++i) {

@@ -22,6 +22,51 @@ int check_launch() {
     return TPN_OK;
 }
 
+DeviceScope::DeviceScope(const void* device_ptr) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        prev = -1;
+    }
+    dev = prev;
+    if (device_ptr != nullptr) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, device_ptr) == cudaSuccess &&
+            (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged))
+            dev = attr.device;
+        else
+            (void)cudaGetLastError();
+    }
+    if (dev != prev && dev >= 0) {
+        if (cudaSetDevice(dev) == cudaSuccess) switched = true;
+        else {
+            (void)cudaGetLastError();
+            dev = prev;
+        }
+    }
+}
+
+DeviceScope::~DeviceScope() {
+    if (switched && prev >= 0) (void)cudaSetDevice(prev);
+}
+
+int device_sm_count() {
+    static int table[kMaxDevices];          // 0 = not queried yet
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        (void)cudaGetLastError();
+        return 148;
+    }
+    if (table[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            n = 148;
+        }
+        table[dev] = n;
+    }
+    return table[dev];
+}
+
 namespace {
 
 // One warp per requested id; lanes stride over the float4 columns of each layer row.
@@ -34,7 +79,7 @@ gather_kernel(StateView st, const long long* __restrict__ ids, long long n, floa
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
     long long id = ids[i];
-    id = id < 0 ? 0 : (id >= st.num_nodes ? st.num_nodes - 1 : id);
+    id = resolve_id(st, id, true);
     const float* base = st.data + id * st.node_stride;
     const int d = st.dim;
     for (int l = 0; l <= st.num_layer; ++l) {
@@ -70,7 +115,7 @@ gather_blocks_kernel(StateView st, const long long* __restrict__ ids, long long 
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
     long long id = ids[i];
-    id = id < 0 ? 0 : (id >= st.num_nodes ? st.num_nodes - 1 : id);
+    id = resolve_id(st, id, true);
     const float* base = st.data + id * st.node_stride;
     float* o = out + i * st.node_stride;
     const int block4 = (int)(st.node_stride >> 2);
@@ -132,7 +177,7 @@ __global__ void __launch_bounds__(256) fill_int_kernel(int* __restrict__ p, long
 inline unsigned capped_grid(long long work_items, int per_block) {
     long long g = (work_items + per_block - 1) / per_block;
     if (g < 1) g = 1;
-    const long long cap = 148ll * 32;
+    const long long cap = (long long)device_sm_count() * 32;
     return (unsigned)(g > cap ? cap : g);
 }
 
@@ -177,6 +222,7 @@ extern "C" int tpn_gather(const tpn_state_t* st, const int64_t* ids_dev, int64_t
     if (n < 0) return TPN_ERR_INVALID_ARGUMENT;
     if (n == 0) return TPN_OK;
     if (ids_dev == nullptr || out_dev == nullptr) return TPN_ERR_INVALID_ARGUMENT;
+    DeviceScope scope(st->data);
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     const StateView v = make_view(st);
     const int ds4 = (int)(st->row_stride / 4);
@@ -196,6 +242,7 @@ extern "C" int tpn_gather_blocks(const tpn_state_t* st, const int64_t* ids_dev, 
     if (n == 0) return TPN_OK;
     if (ids_dev == nullptr || out_dev == nullptr || (reinterpret_cast<uintptr_t>(out_dev) & 15) != 0)
         return TPN_ERR_INVALID_ARGUMENT;
+    DeviceScope scope(st->data);
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     const StateView v = make_view(st);
     const int ds4 = (int)(st->row_stride / 4);
@@ -211,6 +258,7 @@ extern "C" int tpn_materialize(tpn_state_t* st, void* stream_v) {
     int rc = validate_state(st);
     if (rc != TPN_OK) return rc;
     if (st->stamps == nullptr || st->epoch == 0) return TPN_OK;
+    DeviceScope scope(st->data);
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     const StateView v = make_view(st);
     const long long rows = st->num_nodes * st->num_layer;
@@ -224,6 +272,7 @@ extern "C" int tpn_reset_epoch(tpn_state_t* st, void* stream_v) {
     int rc = validate_state(st);
     if (rc != TPN_OK) return rc;
     if (st->stamps == nullptr) return TPN_OK;
+    DeviceScope scope(st->data);
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     const long long rows = st->num_nodes * st->num_layer;
     restart_stamps_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(st->stamps, rows);
@@ -236,6 +285,7 @@ extern "C" int tpn_clear_walk_layers(tpn_state_t* st, void* stream_v) {
     using namespace tpn;
     int rc = validate_state(st);
     if (rc != TPN_OK) return rc;
+    DeviceScope scope(st->data);
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     const StateView v = make_view(st);
     const int ds4 = (int)(st->row_stride / 4);

@@ -35,6 +35,7 @@ namespace tpn {
 namespace {
 
 int g_debug_flags = 0;
+thread_local int g_dev_slot = 0;         // device of the call in progress (set by the entry point)
 
 constexpr int kSmallMaxMsgs = 4096;      // 2B <= 4096 -> single-CTA sort
 constexpr int kRankMaxMsgs = 1024;       // 2B <= 1024 -> rank sort (one barrier) instead of the bitonic network
@@ -53,6 +54,7 @@ constexpr int kHubThreads = (kHubConsumers + 1) * 32;      // + 1 producer warp
 constexpr int kHubStages = 4;            // ring stages of 32 messages
 constexpr int kHubSlotFloats = kHubConsumers * 32;         // 128 floats (512 B) per message slot
 constexpr int kHubMetaChunk = 512;       // messages of metadata staged per bulk copy
+constexpr int kChunkMin = 256;           // smallest chunk of the chunked accumulation order (tpn_state_t::giant_chunk)
 constexpr size_t kSnapMaxBytes = (size_t)8 << 30;          // 8 GiB: above this the per-layer path is used (its hub
                                                            // walker is 10x slower on giant segments: 33 ms vs ~3 ms for
                                                            // d=1024, L=3, 100k zipf(1.5) edges)
@@ -73,6 +75,8 @@ constexpr int kGiantSpm = 16 >> kGiantLs;                  // 32-message sub-blo
 constexpr int kHub2Stages = kHub2Producers + 4;            // ring stages of 32 messages (8 KB each)
 // ctr[] slots (zeroed by prep_large_kernel)
 constexpr int kCtrGiant = 0, kCtrHub = 1, kCtrWork0 = 2, kCtrSmall = 6, kCtrHub2Work = 7, kCtrHub2Giant = 8;
+constexpr int kCtrChunks = 9;            // chunked accumulation: partial-sum rows handed out so far
+constexpr uint32_t kNoPart = 0xffffffffu;   // hub_part[e]: the entry accumulates straight into its target row
 constexpr int kCtrSmClaim = 16;          // [256] first hub2 CTA of each SM claims the SM's giant-segment slot
 constexpr int kCtrSlots = kCtrSmClaim + 256;
 
@@ -127,6 +131,10 @@ struct Workspace {
     uint32_t* ctr;         // [kCtrSlots] 0: #giant, 1: #regular, 2..5: work counters of the per-layer hub launches,
                            //     6: #short segments, 7/8: work counters of the hub2 launch, 16..: SM claims
     uint32_t* small_heads; // [E] sorted positions of the heads of short segments (scheduling order only)
+    uint32_t* hub_len;     // [hub_cap] messages of the e-th entry of hub_reg (a whole segment, or one chunk of a giant)
+    uint32_t* hub_part;    // [hub_cap] kNoPart, or the partial-sum row the entry accumulates into (chunked giants)
+    uint32_t* giant_cbase; // [E / kGiantMin + 2] first partial-sum row of the i-th giant (chunked accumulation)
+    float* partial;        // [E / kChunkMin + E / kGiantMin + 2][L*row_stride] partial sums of giant chunks
     int* svst;             // [L-1][E] pre-batch stamp of the source row of each sorted message (lazy, per-layer path)
     bool has_snap;
     size_t bytes;
@@ -158,7 +166,14 @@ Workspace carve(void* base, int64_t batch, int num_layer, int64_t row_stride) {
     ws.has_snap = snap_bytes(E, num_layer, row_stride) <= kSnapMaxBytes;
     ws.snap = reinterpret_cast<float*>(take((ws.has_snap ? snap_bytes(E, num_layer, row_stride) : 0) + 16));
     ws.hub_giant = reinterpret_cast<uint32_t*>(take(4 * (E / kGiantMin + 2)));
-    ws.hub_reg = reinterpret_cast<uint32_t*>(take(4 * (E / kHubMin + 2)));
+    // hub_reg also holds the chunks of giants in chunked mode: <= E / kChunkMin + one ragged chunk per giant
+    const size_t hub_cap = E / kHubMin + E / kChunkMin + E / kGiantMin + 4;
+    const size_t part_rows = E / kChunkMin + E / kGiantMin + 2;
+    ws.hub_reg = reinterpret_cast<uint32_t*>(take(4 * hub_cap));
+    ws.hub_len = reinterpret_cast<uint32_t*>(take(4 * hub_cap));
+    ws.hub_part = reinterpret_cast<uint32_t*>(take(4 * hub_cap));
+    ws.giant_cbase = reinterpret_cast<uint32_t*>(take(4 * (E / kGiantMin + 2)));
+    ws.partial = reinterpret_cast<float*>(take(ws.has_snap ? 4 * part_rows * (size_t)num_layer * (size_t)row_stride : 16));
     ws.ctr = reinterpret_cast<uint32_t*>(take(4 * kCtrSlots));
     ws.small_heads = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.svst = reinterpret_cast<int*>(take(4 * (E + 4) * (size_t)(num_layer > 1 ? num_layer - 1 : 1) + 16));
@@ -552,6 +567,10 @@ struct PayloadArgs {
     int L, E4;
     long long num_nodes;
     int* err_flag;
+    uint32_t* hub_len;
+    uint32_t* hub_part;
+    uint32_t* giant_cbase;
+    int chunk;                 // > 0: chunked accumulation order for giant segments (tpn_state_t::giant_chunk)
 };
 
 // sorted position p (whole warps call it together: p may be >= E)
@@ -612,9 +631,32 @@ __device__ __forceinline__ void payload_body(const PayloadArgs& a, int p) {
             // long segments go to the CTA-pipelined walkers; integer atomics only (the list order
             // decides scheduling, never results)
             if ((long long)mykey < num_nodes) {
-                if (len >= (uint32_t)kGiantMin) hub_giant[atomicAdd(&ctr[kCtrGiant], 1u)] = (uint32_t)p;
-                else if (len >= (uint32_t)kHubMin) hub_reg[atomicAdd(&ctr[kCtrHub], 1u)] = (uint32_t)p;
-                else small_head = true;
+                if (len >= (uint32_t)kGiantMin) {
+                    const uint32_t gi = atomicAdd(&ctr[kCtrGiant], 1u);
+                    hub_giant[gi] = (uint32_t)p;
+                    if (a.chunk > 0) {
+                        // chunked order: the giant's messages are cut into chunks of `chunk` messages, each an
+                        // ordinary hub entry that sums its messages in order into its own partial row (from +0);
+                        // combine_giants_kernel then adds the partial rows to the target in chunk order.
+                        // Slot numbers only decide where a partial row lives, never a result.
+                        const uint32_t nch = (len + (uint32_t)a.chunk - 1u) / (uint32_t)a.chunk;
+                        const uint32_t cb = atomicAdd(&ctr[kCtrChunks], nch);
+                        const uint32_t eb = atomicAdd(&ctr[kCtrHub], nch);
+                        a.giant_cbase[gi] = cb;
+                        for (uint32_t c = 0; c < nch; ++c) {
+                            hub_reg[eb + c] = (uint32_t)p + c * (uint32_t)a.chunk;
+                            a.hub_len[eb + c] = min((uint32_t)a.chunk, len - c * (uint32_t)a.chunk);
+                            a.hub_part[eb + c] = cb + c;
+                        }
+                    }
+                } else if (len >= (uint32_t)kHubMin) {
+                    const uint32_t e = atomicAdd(&ctr[kCtrHub], 1u);
+                    hub_reg[e] = (uint32_t)p;
+                    a.hub_len[e] = len;
+                    a.hub_part[e] = kNoPart;
+                } else {
+                    small_head = true;
+                }
             }
         }
         slen[p] = len;
@@ -1214,7 +1256,9 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                  const float* __restrict__ sw, const uint32_t* __restrict__ sslot,
                  const uint32_t* __restrict__ slen, const float* __restrict__ snap,
                  const uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ hub_reg,
-                 uint32_t* __restrict__ ctr, int spr_g, int slice_w_g, int spr_r, int slice_w_r, DecayArgs dnow) {
+                 uint32_t* __restrict__ ctr, int spr_g, int slice_w_g, int spr_r, int slice_w_r, DecayArgs dnow,
+                 const uint32_t* __restrict__ hub_len, const uint32_t* __restrict__ hub_part,
+                 float* __restrict__ partial, int chunked) {
     extern __shared__ __align__(128) unsigned char hub2_raw[];
     float* const ring = reinterpret_cast<float*>(hub2_raw);                       // [stages][32][kHub2SlotFloats]
     uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)kHub2Stages * 32 * kHub2SlotFloats);
@@ -1239,7 +1283,8 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
     __syncthreads();
     const uint32_t n_giant = ctr[kCtrGiant], n_reg = ctr[kCtrHub];
     const uint32_t slices_g = (uint32_t)(L * spr_g), slices_r = (uint32_t)(L * spr_r);
-    const uint32_t total_g = n_giant * slices_g, total_r = n_reg * slices_r;
+    // chunked accumulation: giants were expanded into chunk entries of the regular list (payload_kernel)
+    const uint32_t total_g = chunked ? 0u : n_giant * slices_g, total_r = n_reg * slices_r;
     uint32_t blk_base = 0;      // ring blocks produced / consumed so far by this CTA (same count in every warp)
     for (;;) {
         if (threadIdx.x == 0) {
@@ -1269,7 +1314,8 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
         const int c0 = (slice - r * spr) * slice_w;     // first column of the slice inside the row
         const int width = min(rs, c0 + slice_w) - c0;   // floats, multiple of 4
         const int head = (int)(giant ? hub_giant[hub] : hub_reg[hub]);
-        const int len = (int)slen[head];
+        const int len = (int)(giant ? slen[head] : hub_len[hub]);
+        const uint32_t part = giant ? kNoPart : hub_part[hub];     // != kNoPart: a chunk of a giant -> its partial row
         const uint32_t key = skey[head];
         // a ring stage (8 KB) holds 32 messages of <= 64 floats, or — giants — 128 messages of <= 16 floats:
         // four times fewer full/empty handshakes on the critical chain
@@ -1369,9 +1415,11 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                 // latency of the add chain it is bound by
                 const int col = giant ? lane : 2 * lane;
                 const bool active = col < width;
-                float* tptr = st.data + (long long)key * st.node_stride + (long long)(r + 1) * rs + c0 + col;
+                float* tptr = part == kNoPart
+                                  ? st.data + (long long)key * st.node_stride + (long long)(r + 1) * rs + c0 + col
+                                  : partial + ((long long)part * L + r) * rs + c0 + col;
                 float2 acc = make_float2(0.f, 0.f);
-                if (active) {
+                if (active && part == kNoPart) {
                     if (giant) acc.x = *tptr;
                     else acc = *reinterpret_cast<const float2*>(tptr);      // zeros if never written
                     if (LAZY) {
@@ -1425,9 +1473,48 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
     }
 }
 
+// Chunked accumulation order, second half: target row of giant g  <-  ((row * pending decay) + partial_0) + partial_1 ...
+// in chunk order (partial_c = the chunk's messages summed in order from +0 by walk_hub2_kernel).  One CTA per giant,
+// one column per thread; the chain is the number of chunks, not the number of messages.
+template <bool LAZY>
+__global__ void __launch_bounds__(256)
+combine_giants_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ slen,
+                      const uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ giant_cbase,
+                      const uint32_t* __restrict__ ctr, const float* __restrict__ partial, int chunk) {
+    const int L = st.num_layer;
+    const int rs = (int)st.row_stride;
+    const int span = L * rs;
+    const uint32_t n_giant = ctr[kCtrGiant];
+    for (uint32_t g = blockIdx.x; g < n_giant; g += gridDim.x) {
+        const uint32_t head = hub_giant[g];
+        const uint32_t key = skey[head];
+        const uint32_t nch = (slen[head] + (uint32_t)chunk - 1u) / (uint32_t)chunk;
+        const float* pbase = partial + (long long)giant_cbase[g] * span;
+        float* trow = st.data + (long long)key * st.node_stride + rs;          // rows 1..L
+        for (int col = threadIdx.x; col < span; col += blockDim.x) {
+            const int r = col / rs;
+            float acc = trow[col];                                               // zeros if never written
+            if (LAZY) {
+                const int ts = st.stamps[(long long)key * L + r];
+                if (ts >= 0) acc = __fmul_rn(acc, decay_factor(st, r, ts));
+            }
+            uint32_t c = 0;
+            for (; c + 4 <= nch; c += 4) {                                       // four loads in flight, adds in order
+                const float p0 = pbase[(long long)(c + 0) * span + col], p1 = pbase[(long long)(c + 1) * span + col];
+                const float p2 = pbase[(long long)(c + 2) * span + col], p3 = pbase[(long long)(c + 3) * span + col];
+                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, p0), p1), p2), p3);
+            }
+            for (; c < nch; ++c) acc = __fadd_rn(acc, pbase[(long long)c * span + col]);
+            trow[col] = acc;
+        }
+    }
+}
+
 template <bool DIRECT>
-int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const DecayArgs& dnow, cudaStream_t stream) {
-    static bool configured = false;
+int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const DecayArgs& dnow, int chunk,
+                     cudaStream_t stream) {
+    static bool configured_tab[kMaxDevices];          // per device: the shared-memory opt-in is a device attribute
+    bool& configured = configured_tab[g_dev_slot];
     const int smem = (int)hub2_smem_bytes();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(walk_hub2_kernel<false, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1446,15 +1533,27 @@ int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const D
     const int slice_w_g = (((rs + spr_g - 1) / spr_g) + 3) & ~3;
     // 2 CTAs (88 KB of ring each) per SM.  One per SM — leaving half of every SM to the short-segment
     // walker from the start — was measured slower (0.62 vs 0.58 ms per 100k-edge step).
-    const unsigned grid = 148 * 2;
+    const unsigned grid = (unsigned)device_sm_count() * 2;
+    const int chunked = chunk > 0 ? 1 : 0;
     if (lazy)
         walk_hub2_kernel<true, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                              ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
-                                                                             spr_g, slice_w_g, spr_r, slice_w_r, dnow);
+                                                                             spr_g, slice_w_g, spr_r, slice_w_r, dnow,
+                                                                             ws.hub_len, ws.hub_part, ws.partial, chunked);
     else
         walk_hub2_kernel<false, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                               ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
-                                                                              spr_g, slice_w_g, spr_r, slice_w_r, dnow);
+                                                                              spr_g, slice_w_g, spr_r, slice_w_r, dnow,
+                                                                              ws.hub_len, ws.hub_part, ws.partial, chunked);
+    if (chunked) {
+        const unsigned cgrid = (unsigned)device_sm_count();
+        if (lazy)
+            combine_giants_kernel<true><<<cgrid, 256, 0, stream>>>(v, ws.key_a, ws.slen, ws.hub_giant, ws.giant_cbase,
+                                                                   ws.ctr, ws.partial, chunk);
+        else
+            combine_giants_kernel<false><<<cgrid, 256, 0, stream>>>(v, ws.key_a, ws.slen, ws.hub_giant, ws.giant_cbase,
+                                                                    ws.ctr, ws.partial, chunk);
+    }
     return TPN_OK;
 }
 
@@ -1462,7 +1561,7 @@ template <int V, bool DIRECT>
 void launch_walk_small_v(const StateView& v, const Workspace& ws, int E, int ds4, int tiles, bool lazy,
                          const DecayArgs& dnow, cudaStream_t stream) {
     long long want = ((long long)E + kSmallWalkThreads / 32 - 1) / (kSmallWalkThreads / 32);
-    const long long cap = 148 * 2 * 2;                // two resident CTAs per SM, two waves
+    const long long cap = (long long)device_sm_count() * 2 * 2;      // two resident CTAs per SM, two waves
     dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)tiles);
     if (lazy)
         walk_small_kernel<V, true, DIRECT><<<grid, kSmallWalkThreads, 0, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
@@ -1520,7 +1619,8 @@ SideStream* side_stream() {
 template <bool ALL>
 int launch_walk_hub(const StateView& v, int layer, const Workspace& ws, int E4, bool lazy, const DecayArgs& dnow,
                     cudaStream_t stream) {
-    static bool configured = false;
+    static bool configured_tab[kMaxDevices];
+    bool& configured = configured_tab[g_dev_slot];
     const int smem = (int)sizeof(HubSmem);
     if (!configured) {
         cudaError_t e = cudaSuccess;
@@ -1541,7 +1641,7 @@ int launch_walk_hub(const StateView& v, int layer, const Workspace& ws, int E4, 
                                : (lazy && layer >= 2 ? reinterpret_cast<const uint32_t*>(ws.svst) + (size_t)(layer - 2) * E4
                                                      : nullptr);
     const int work_ctr = kCtrWork0 + (ALL ? 0 : layer - 1);
-    const unsigned grid = 148 * 2;
+    const unsigned grid = (unsigned)device_sm_count() * 2;
     if (lazy)
         walk_hub_kernel<true, ALL><<<grid, kHubThreads, smem, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, xarr, ws.slen,
                                                                         ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
@@ -1599,14 +1699,15 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
         dargs.has_decay = all_one ? 0 : 1;      // x * 1.0f == x exactly: nothing to do
     }
     long long new_epoch = st->epoch;
+    double new_floor = st->cum_floor;
     if (lazy && dargs.has_decay) {
         if (st->epoch + 1 >= st->log_capacity) return TPN_ERR_LOG_FULL;
         // the log holds f64 cumulative products: restart it (materialise) long before they underflow
         double cmin = 1.0;
         for (int l = 0; l < L; ++l) cmin = dargs.c[l] < cmin ? (double)dargs.c[l] : cmin;
-        if (st->epoch == 0) st->cum_floor = 1.0;
-        if (st->epoch > 0 && !(st->cum_floor * cmin >= 1e-200)) return TPN_ERR_LOG_FULL;
-        st->cum_floor *= cmin;      // tiny (or 0) only right after a restart: the next epoch restarts again
+        new_floor = (st->epoch == 0 ? 1.0 : st->cum_floor);
+        if (st->epoch > 0 && !(new_floor * cmin >= 1e-200)) return TPN_ERR_LOG_FULL;
+        new_floor *= cmin;          // tiny (or 0) only right after a restart: the next epoch restarts again
         new_epoch = st->epoch + 1;
     }
 
@@ -1621,10 +1722,16 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
     const bool hubs = E > kSmallMaxMsgs;            // the single-CTA sort path keeps everything in the warp walker
     const int E4 = (E + 3) & ~3;                    // layer stride of svst (keeps bulk copies 16-byte aligned)
     const bool eager_sweep = !lazy && dargs.has_decay;
+    // chunked accumulation order of giant segments (snapshot path only; 0 = the reference's sequential order)
+    int chunk = st->giant_chunk > 0 ? (int)st->giant_chunk : 0;
+    if (chunk > 0 && chunk < kChunkMin) chunk = kChunkMin;
+    if (chunk > kGiantMin) chunk = kGiantMin;
+    chunk &= ~31;
     const long long sweep_total4 = st->num_nodes * (long long)L * ds4;
 
-    st->epoch = new_epoch;
-    const StateView view = make_view(st);
+    // the kernels read the NEW epoch; the caller's struct is only advanced once every launch went through
+    StateView view = make_view(st);
+    view.epoch = new_epoch;
 
     if (E <= kSmallMaxMsgs) {
         SweepArgs sw_args;
@@ -1633,7 +1740,8 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
         unsigned grid = 1;
         if (eager_sweep) {
             const long long want = (sweep_total4 + kPrepThreads - 1) / kPrepThreads;
-            grid += (unsigned)(want < 148 * 4 ? (want < 1 ? 1 : want) : 148 * 4);
+            const long long cap = (long long)device_sm_count() * 4;
+            grid += (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
         }
         prep_small_kernel<<<grid, kPrepThreads, 0, stream>>>(msgs, E, t_last_f, neg_lambda, st->num_nodes, ws.key_a,
                                                              ws.ssrc, ws.sw, ws.sslot, ws.slen, err_flag_dev, log_w, L,
@@ -1678,6 +1786,10 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
         fa.pay.E4 = E4;
         fa.pay.num_nodes = st->num_nodes;
         fa.pay.err_flag = err_flag_dev;
+        fa.pay.hub_len = ws.hub_len;
+        fa.pay.hub_part = ws.hub_part;
+        fa.pay.giant_cbase = ws.giant_cbase;
+        fa.pay.chunk = (snapshot_path && hubs) ? chunk : 0;
         {
             prep_large_kernel<<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(fa.prep);
             uint32_t *kin = ws.key_a, *kout = ws.key_b, *vin = ws.val_a, *vout = ws.val_b;
@@ -1693,11 +1805,12 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
             fa.pay.order = vin;
             fa.pay.skey = kin;          // odd number of passes: sorted keys live in key_b; payload copies them to key_a
             payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(fa.pay);
-            if (snapshot_path) sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr);
+            if (snapshot_path && chunk == 0) sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr);
         }
         if (eager_sweep) {
             const long long want = (sweep_total4 + 255) / 256;
-            const unsigned grid = (unsigned)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
+            const long long cap = (long long)device_sm_count() * 16;
+            const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
             sweep_decay_kernel<<<grid, 256, 0, stream>>>(view, dargs, sweep_total4, ds4);
         }
     }
@@ -1721,8 +1834,8 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
                 else
                     (void)cudaGetLastError();
             }
-            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, hub_stream)
-                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, hub_stream);
+            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, chunk, hub_stream)
+                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, chunk, hub_stream);
             if (hrc != TPN_OK) return hrc;
             if (direct) launch_walk_small<true>(view, ws, E, ds4, lazy, dargs, stream);
             else launch_walk_small<false>(view, ws, E, ds4, lazy, dargs, stream);
@@ -1762,7 +1875,12 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
                 stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, layer, ws.key_a, E);
         }
     }
-    return check_launch();
+    const int lrc = check_launch();
+    if (lrc == TPN_OK) {
+        st->epoch = new_epoch;
+        st->cum_floor = new_floor;
+    }
+    return lrc;
 }
 
 }  // namespace
@@ -1792,6 +1910,8 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
     if (batch < 1 || batch > ((int64_t)1 << 26) || src_dev == nullptr || dst_dev == nullptr || t_dev == nullptr ||
         ws_dev == nullptr || st->num_nodes >= (int64_t)0xffffffffll)
         return TPN_ERR_INVALID_ARGUMENT;
+    DeviceScope scope(st->data);
+    g_dev_slot = scope.slot();
     MsgSource msgs;
     msgs.a = reinterpret_cast<const long long*>(src_dev);
     msgs.b = reinterpret_cast<const long long*>(dst_dev);
@@ -1813,6 +1933,8 @@ extern "C" int tpn_update_messages(tpn_state_t* st, const int64_t* tgt_dev, cons
         t_dev == nullptr || ws_dev == nullptr || st->num_nodes >= (int64_t)0x7fffffffll || num_local_rows < 0 ||
         num_local_rows > st->num_nodes)
         return TPN_ERR_INVALID_ARGUMENT;
+    DeviceScope scope(st->data);
+    g_dev_slot = scope.slot();
     MsgSource msgs;
     msgs.a = reinterpret_cast<const long long*>(tgt_dev);
     msgs.b = reinterpret_cast<const long long*>(src_dev);

@@ -14,6 +14,10 @@ What it does before handing control to the script (``runpy``, ``__name__ == '__m
   * with ``--tpn-gpu-sampler`` (an option of the launcher, removed before the script sees its arguments):
     ``utils.utils.get_neighbor_sampler`` returns ``tpnet_b200.neighbor_sampler.RecentNeighborSampler`` for
     the `recent` strategy (the one TPNet uses; any other strategy still gets the reference's sampler).
+  * with ``--tpn-stock`` (also consumed here): NOTHING is swapped — the reference's own class runs, with only the
+    Python >= 3.11 ``random.sample`` shim applied.  This is the comparison arm of ``scripts/apauc_parity.py``.
+  * ``--gpu G``: ``torch.cuda.set_device(G)`` before the script starts (the scripts only build the string
+    ``cuda:G``; the library launches on the current device).
 Nothing of the reference is copied or edited.
 """
 from __future__ import annotations
@@ -83,11 +87,23 @@ def main(argv: List[str]) -> None:
     if len(argv) < 2:
         raise SystemExit('usage: python -m tpnet_b200.launch <TPNet checkout> <script.py> [script arguments ...]')
     reference_dir, script = os.path.abspath(argv[0]), argv[1]
-    rest = [a for a in argv[2:] if a != '--tpn-gpu-sampler']
+    own = ('--tpn-gpu-sampler', '--tpn-stock')
+    rest = [a for a in argv[2:] if a not in own]
     gpu = 0
     if '--gpu' in rest and rest.index('--gpu') + 1 < len(rest):      # the scripts' own device option (load_configs.py)
         gpu = int(rest[rest.index('--gpu') + 1])
-    install(reference_dir, gpu_sampler=len(rest) != len(argv) - 2, device=f'cuda:{gpu}')
+    if gpu >= 0:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.set_device(gpu)                      # the library launches on the CURRENT device
+    if '--tpn-stock' in argv[2:]:
+        # comparison arm: the reference's own RandomProjectionModule, untouched
+        if reference_dir not in sys.path:
+            sys.path.insert(0, reference_dir)
+        if sys.version_info >= (3, 11):
+            allow_sampling_from_sets()
+    else:
+        install(reference_dir, gpu_sampler='--tpn-gpu-sampler' in argv[2:], device=f'cuda:{gpu}')
     os.chdir(reference_dir)
     for d in ('logs', 'saved_models', 'saved_results'):     # the scripts expect these to exist or create them lazily
         os.makedirs(os.path.join(reference_dir, d), exist_ok=True)

@@ -81,6 +81,10 @@ class RecentNeighborSampler:
         n = int(len(node_ids))
         if len(node_interact_times) != n:
             raise ValueError('node ids and times must have the same length')
+        if not isinstance(node_ids, torch.Tensor) and n:
+            ids = np.asarray(node_ids)
+            if ids.min() < 0 or ids.max() >= self.num_nodes:     # the reference indexes a per-node list (utils.py:177)
+                raise IndexError(f'node id out of range for a sampler over {self.num_nodes} nodes')
         qn = self._to_device(node_ids, torch.int64).reshape(-1)
         qt = self._to_device(node_interact_times, torch.float64).reshape(-1)
         out_n = torch.empty(n, num_neighbors, dtype=torch.int64, device=self.device)

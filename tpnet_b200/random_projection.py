@@ -52,10 +52,11 @@ class _Stager:
     the per-call id / timestamp arrays into pinned memory (validating ids on the way) and issues
     one async H2D copy on the current stream."""
 
-    def __init__(self, slot_bytes: int = 1 << 20, slots: int = 8):
+    def __init__(self, dev_index: int, slot_bytes: int = 1 << 20, slots: int = 8):
         self._lib = _lib.load()
         self.handle = ctypes.c_void_p()
-        _lib.check(self._lib.tpn_stager_create(ctypes.byref(self.handle), slot_bytes, slots), 'tpn_stager_create')
+        with torch.cuda.device(dev_index):       # the ring's device slots live on the module's device
+            _lib.check(self._lib.tpn_stager_create(ctypes.byref(self.handle), slot_bytes, slots), 'tpn_stager_create')
         self.host = (ctypes.c_void_p * 8)()
         self.elems = (ctypes.c_int64 * 8)()
         self.kinds = (ctypes.c_int * 8)()
@@ -85,7 +86,8 @@ class _Stager:
 
 class _Host:
     """Mutable host-side bookkeeping kept off the nn.Module (its __setattr__ is slow)."""
-    __slots__ = ('now', 'begin', 'epoch', 'launches', 'stager', 'st', 'st_ref', 'dev_index', 'keepalive')
+    __slots__ = ('now', 'begin', 'epoch', 'launches', 'stager', 'st', 'st_ref', 'dev_index', 'keepalive',
+                 'device_ids_seen')
 
     def __init__(self, t0: float):
         self.now = t0
@@ -97,6 +99,7 @@ class _Host:
         self.st_ref = None
         self.dev_index = -1
         self.keepalive = None
+        self.device_ids_seen = False     # a device-resident id array was used since the last check_errors()
 
 
 class RandomProjectionModule(nn.Module):
@@ -271,6 +274,9 @@ class RandomProjectionModule(nn.Module):
                 st.stamps = None
                 st.decay_log = None
                 st.log_capacity = 0
+            if self._err is None:
+                self._err = torch.zeros(1, dtype=torch.int32, device=self._state.device)
+            st.err_flag = self._err.data_ptr()
             h.st = st
             h.st_ref = ctypes.byref(st)
         st.epoch = h.epoch
@@ -288,6 +294,7 @@ class RandomProjectionModule(nn.Module):
                     raise TypeError(f'device-resident {kind} arrays must be contiguous {want} tensors on {dev}')
                 out.append(a.data_ptr())
             self._h.keepalive = arrays
+            self._h.device_ids_seen = True
             return out
         host, ck = [], []
         id_kind = _lib.STAGE_ID_WRAP if wrap_negative else _lib.STAGE_ID
@@ -303,7 +310,8 @@ class RandomProjectionModule(nn.Module):
             ck.append(id_kind if kind == 'id' else _lib.STAGE_RAW)
         h = self._h
         if h.stager is None:
-            h.stager = _Stager()
+            self._stream()                              # resolves dev_index
+            h.stager = _Stager(h.dev_index)
         return h.stager.upload(host, ck, self.node_num, self._stream())
 
     # ------------------------------------------------------------------ reference API
@@ -335,8 +343,6 @@ class RandomProjectionModule(nn.Module):
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
             self._ws_batch = n
-        if self._err is None:
-            self._err = torch.zeros(1, dtype=torch.int32, device=dev)
         args = (ptrs[0], ptrs[1], ptrs[2], n, float(next_time), float(np.float32(-lam)), factors,
                 self._ws.data_ptr(), self._ws.numel(), self._err.data_ptr(), self._stream())
         rc = lib.tpn_update(st, *args)
@@ -460,8 +466,11 @@ class RandomProjectionModule(nn.Module):
         return self._head(g.view(m * k * 2, self.pair_wise_feature_dim)).view(m, k, 2 * self.pair_wise_feature_dim)
 
     def reset_random_projections(self):
-        """TPNet.py:131-139."""
+        """TPNet.py:131-139.  (Called once per epoch by train_link_prediction.py:248: also the point where
+        an out-of-range id of a device-resident batch — which a kernel can only flag — is raised.)"""
         self._require_cuda()
+        if self._h.device_ids_seen:
+            self.check_errors()
         lib = _lib.load()
         _lib.check(lib.tpn_clear_walk_layers(self._c_state(), self._stream()), 'tpn_clear_walk_layers')
         self._h.epoch = 0
@@ -509,7 +518,10 @@ class RandomProjectionModule(nn.Module):
         self._h.epoch = 0
 
     def check_errors(self) -> None:
-        """Synchronises and raises IndexError if a device-resident id was out of range."""
+        """Synchronises and raises IndexError if a device-resident id was out of range in any call since the
+        last check (update drops such edges; pair-wise / gather calls clamp the access).  Host (numpy) ids are
+        validated before anything is launched and raise at once, like the reference."""
+        self._h.device_ids_seen = False
         code = int(self._err.item()) if self._err is not None else 0
         if code != 0:
             self._err.zero_()
