@@ -8,21 +8,28 @@ encode) on synthetic graphs of the BASELINE.json shapes.
 Primary workload (all N): BASELINE.json configs[3], the one its metric ("... at 1/2/4/8 B200;
 % HBM roofline") is quoted on — a power-law temporal graph with 10M nodes, d=210, L=3, lazy
 decay, batches of 100,000 edges, p=2 pair-encodes per edge (the decoder shape of
-models/modules.py:112: (src,dst) and (src,neg)).  It fits one GPU (34.6 GB state) and is
-HBM-bound, so the roofline fraction is a real DRAM figure.  N>1: the state is sharded by node
-id (tpnet_b200/sharded.py); weak scaling by default — every GPU brings 100,000 edges per step, the
-job's batch is 100,000 x N (`--scaling strong` splits one 100,000-edge batch instead).
-At N=1 the line also carries `also.reddit`: BASELINE.json configs[1] (Reddit-shaped, B=200,
-K=20, p=162 — one TPNet training batch, latency-bound, state L2-resident).
+models/modules.py:112: (src,dst) and (src,neg)), `self.mlp` included.  It fits one GPU (34.6 GB
+state).  The roofline fraction uses SURVEY.md 8(d)'s ALGORITHMIC bytes (no credit for duplicate
+rows); with zipf endpoints most duplicate rows are L2 hits, so the measured DRAM traffic
+(`roofline.traffic`, ncu) is far below that figure — see DESIGN.md section 6.
+N>1: the state is sharded by node id (tpnet_b200/sharded.py): routing, NVLink pulls of remote rows and
+rank barriers all run on the device, the whole step is one CUDA graph per rank; weak scaling by default —
+every GPU brings 100,000 edges per step, the job's batch is 100,000 x N (`--scaling strong` splits one
+100,000-edge batch instead).  The N>1 line ends with a `parity` block: a down-scaled replica updated
+sharded and on one GPU, compared bit for bit.
+At N=1 the line also carries `also.{reddit,wikipedia,flights}`: BASELINE.json configs[1], [0], [2]
+(TPNet-batch shapes, B=200, K=20, p=162 — latency-bound, state L2-resident).
 
-One JSON line on stdout (driver contract).  `value`: inputs resident in HBM, CUDA-event time.
-`e2e`: the public numpy API with pinned H2D of the step's inputs, `self.mlp`, and a scalar
-result read back per step.  `--impl reference`: the torch-CPU port of the reference
-(oracle/cpu_port.py) on the host cores.
+One JSON line on stdout (driver contract).  `value`: inputs resident in HBM, CUDA-event time, the
+same work as the reference arm (pair-wise encode incl. `self.mlp` + update).  `e2e`: the public numpy API
+with pinned H2D of the step's inputs and a scalar result read back per step.  `--impl reference`: the
+UNMODIFIED reference class from oracle/_ref/TPNet (installed by oracle/make_ref.py) on the host cores;
+the torch-CPU port (oracle/cpu_port.py) only if that copy is missing.
 """
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
 import subprocess
@@ -46,6 +53,14 @@ PL_BATCH = 100_000          # power-law batch (configs[3])
 PL_WARM = 12
 METRIC = 'temporal edges/sec (update+pairwise encode)'
 REF_THREADS = 3             # the reference pins torch to 3 intra-op threads (train_link_prediction.py:124)
+NVLINK_GBS = 900.0          # per direction and GPU (NVLink 5)
+CHUNKED_NOTE = ('accumulation=chunked (opt-in, NOT the reference order): a row receiving >= 2048 messages in one update sums '
+                'them in chunks of 1024 in order, then the chunk sums in order; deterministic, bit-identical to the oracle\'s '
+                'restatement of that order; it removes the hub\'s sequential add chain.  It differs from the reference\'s '
+                'sequential fp32 order by up to ~3e-4 of a hub row\'s magnitude on this workload — which is the reference '
+                'order\'s own rounding error: against the exact (f64) result the sequential order is off by 2.4e-4, the '
+                'chunked one by 3e-6 (profiles/r02_accumulation_order_error.txt)')
+REF_DIR = os.path.join(ROOT, 'oracle', '_ref', 'TPNet')
 
 
 def parse_args():
@@ -56,9 +71,13 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='powerlaw', choices=['powerlaw', 'reddit', 'wikipedia', 'flights'])
     ap.add_argument('--decay-mode', default='auto', choices=['auto', 'eager', 'lazy'])
+    ap.add_argument('--accumulation', default='reference', choices=['chunked', 'reference'],
+                    help='power-law: order in which the messages of one row are added (tpn_state_t::giant_chunk)')
     ap.add_argument('--no-flush', action='store_true', help='small shapes: keep L2 warm between steps')
-    ap.add_argument('--no-graphs', action='store_true', help='power-law, 1 GPU: launch the steps eagerly instead of as CUDA graphs')
-    ap.add_argument('--no-also', action='store_true', help='N=1: skip the secondary Reddit-shaped measurement')
+    ap.add_argument('--no-graphs', action='store_true', help='power-law: launch the steps eagerly instead of as CUDA graphs')
+    ap.add_argument('--no-also', action='store_true', help='N=1: skip the secondary measurements')
+    ap.add_argument('--no-parity', action='store_true', help='N>1: skip the sharded-vs-single-GPU parity leg')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'nccl'], help='N>1: data plane of the sharded state')
     ap.add_argument('--cpu-sample-steps', type=int, default=None)
     ap.add_argument('--cpu-threads', type=int, default=None, help='--impl reference: host threads (default: all cores)')
     ap.add_argument('--warm-batches', type=int, default=None, help='untimed batches that fill the state')
@@ -133,7 +152,43 @@ class ClockSampler:
             self.proc.terminate()
 
 
-# ============================================================================= Reddit-shaped (TPNet batch) workload
+# ============================================================================= the reference arm (CPU)
+def load_reference_class():
+    """The UNMODIFIED reference class from oracle/_ref/TPNet (oracle/make_ref.py), or None."""
+    if not os.path.isfile(os.path.join(REF_DIR, 'models', 'TPNet.py')):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    from models.TPNet import RandomProjectionModule as Ref          # the reference's own module
+    return Ref
+
+
+class CpuArm:
+    """update / pair_wise of the reference on the host cores: the real class when it is installed
+    (kind 'reference'), else the torch-CPU port of its op sequence (kind 'port')."""
+
+    def __init__(self, shape, node_num, t0, with_mlp=True, device='cpu'):
+        Ref = load_reference_class() if device == 'cpu' else None
+        torch.manual_seed(0)
+        if Ref is not None:
+            self.kind = 'reference'
+            self.m = Ref(node_num=node_num, edge_num=shape.edge_num, dim_factor=shape.dim_factor,
+                         num_layer=shape.num_layer, time_decay_weight=shape.time_decay_weight, device='cpu',
+                         use_matrix=False, beginning_time=np.float64(t0), not_scale=False, enforce_dim=-1)
+            if not with_mlp:
+                self.m.mlp = torch.nn.Identity()
+            self.update = self.m.update
+            self.pair_wise = self.m.get_pair_wise_feature
+        else:
+            from oracle.cpu_port import CpuWalkProjection          # baseline leg only (see oracle/__init__.py)
+            self.kind = 'port'
+            self.m = CpuWalkProjection(node_num, shape.dim, shape.num_layer, shape.time_decay_weight, float(t0),
+                                       not_scale=False, with_mlp=with_mlp, seed=0, device=device)
+            self.update = self.m.update
+            self.pair_wise = self.m.pair_wise
+
+
+# ============================================================================= TPNet-batch workloads (configs[0..2])
 def make_steps(shape, n_steps, seed, warm=WARM_BATCHES):
     """Returns (warm_batches, steps).  Each step holds the numpy inputs of one batch."""
     rng = np.random.default_rng(seed + 17)
@@ -158,22 +213,20 @@ def pairs_per_step():
     return 8 * BATCH * NUM_NEIGHBORS + 2 * BATCH
 
 
-def cpu_port_tpnet(shape, warm_batches, steps, n_warm, n_timed, threads):
-    """Times the torch-CPU port of the reference on the host cores: same step shape."""
-    from oracle.cpu_port import CpuWalkProjection          # baseline leg only (see oracle/__init__.py)
+def cpu_tpnet(shape, warm_batches, steps, n_warm, n_timed, threads, with_mlp=True):
+    """Times the reference's CPU path on the host cores: same step shape.  Returns (seconds per step, kind)."""
     torch.set_num_threads(threads)
-    ref = CpuWalkProjection(shape.node_num, shape.dim, shape.num_layer, shape.time_decay_weight,
-                            float(warm_batches[0][2][0]), not_scale=False, with_mlp=True, seed=0)
+    arm = CpuArm(shape, shape.node_num, float(warm_batches[0][2][0]), with_mlp=with_mlp)
     for s, d, t in warm_batches[-40:]:                      # a short warm stream is enough to fill the rows
-        ref.update(s, d, t)
+        arm.update(s, d, t)
 
     def one(st):
         with torch.no_grad():
-            ref.pair_wise(*st['enc_pos'])
-            ref.pair_wise(*st['enc_neg'])
-            pos = ref.pair_wise(st['src'], st['dst'])
-            neg = ref.pair_wise(st['src'], st['neg'])
-            ref.update(st['src'], st['dst'], st['t'])
+            arm.pair_wise(*st['enc_pos'])
+            arm.pair_wise(*st['enc_neg'])
+            pos = arm.pair_wise(st['src'], st['dst'])
+            neg = arm.pair_wise(st['src'], st['neg'])
+            arm.update(st['src'], st['dst'], st['t'])
             res = pos.sum() - neg.sum()
         return float(res)
 
@@ -182,7 +235,7 @@ def cpu_port_tpnet(shape, warm_batches, steps, n_warm, n_timed, threads):
     t0 = time.perf_counter()
     for st in steps[n_warm:n_warm + n_timed]:
         one(st)
-    return (time.perf_counter() - t0) / n_timed
+    return (time.perf_counter() - t0) / n_timed, arm.kind
 
 
 def build_module(shape, device, decay_mode, t0):
@@ -204,13 +257,15 @@ def to_dev(st, device):
 
 
 def resident_step(m, ds):
-    """One step with device-resident inputs: kernels only (no head, no H2D).  The feature
-    tensors are dropped at once: inside a capture their memory returns to the graph pool."""
-    m.neighbor_pair_wise_gram(*ds['nbr_pos'])      # encoder: [2B, K, 2, F] = 4BK pair blocks (TPNet.py:313-324)
-    m.neighbor_pair_wise_gram(*ds['nbr_neg'])
-    m.pair_wise_gram(ds['src'], ds['dst'])
-    m.pair_wise_gram(ds['src'], ds['neg'])
-    m.update(ds['src'], ds['dst'], ds['t'], next_time=ds['t_last'])
+    """One step with device-resident inputs, the same work as the reference arm: encoder + decoder pair-wise
+    features incl. `self.mlp`, then the update.  The feature tensors are dropped at once: inside a capture their
+    memory returns to the graph pool."""
+    with torch.no_grad():
+        m.get_neighbor_pair_wise_feature(*ds['nbr_pos'])   # encoder: [2B, K, 2F] = 4BK pair blocks (TPNet.py:313-324)
+        m.get_neighbor_pair_wise_feature(*ds['nbr_neg'])
+        m.get_pair_wise_feature(ds['src'], ds['dst'])
+        m.get_pair_wise_feature(ds['src'], ds['neg'])
+        m.update(ds['src'], ds['dst'], ds['t'], next_time=ds['t_last'])
 
 
 def api_step(m, st):
@@ -225,7 +280,61 @@ def api_step(m, st):
     return float(res.item())                                   # D2H read of the step's result
 
 
-def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
+def time_sampler(shape, warm_batches, steps, device):
+    """one TPNet batch samples K recent neighbours for 2B (pos) + 2B (neg) nodes."""
+    from tpnet_b200.neighbor_sampler import RecentNeighborSampler
+    src = np.concatenate([b[0] for b in warm_batches])
+    dst = np.concatenate([b[1] for b in warm_batches])
+    t = np.concatenate([b[2] for b in warm_batches])
+    eid = np.arange(1, len(src) + 1)
+    gs = RecentNeighborSampler(src, dst, eid, t, device, num_nodes=shape.node_num)
+    st = steps[0]
+    q = np.concatenate([st['src'], st['dst'], st['src'], st['neg']])
+    qt = np.tile(st['t'], 4)
+    dq, dqt = torch.from_numpy(q).to(device), torch.from_numpy(qt).to(device)
+    for _ in range(5):
+        gs.get_historical_neighbors(dq, dqt, NUM_NEIGHBORS, as_tensors=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 200
+    a.record()
+    for _ in range(reps):
+        gs.get_historical_neighbors(dq, dqt, NUM_NEIGHBORS, as_tensors=True)
+    b.record()
+    torch.cuda.synchronize()
+    dev_us = a.elapsed_time(b) * 1e3 / reps
+    t0 = time.perf_counter()
+    for _ in range(50):
+        gs.get_historical_neighbors(q, qt, NUM_NEIGHBORS)              # numpy in, numpy out (the reference's interface)
+    api_us = (time.perf_counter() - t0) * 1e6 / 50
+    out = {'queries_per_batch': int(len(q)), 'num_neighbors': NUM_NEIGHBORS, 'edges_in_graph': int(len(src)),
+           'device_us_per_batch': dev_us, 'numpy_api_us_per_batch': api_us}
+    cpu_us, kind = None, None
+    try:
+        if load_reference_class() is not None:
+            from utils.DataLoader import Data                        # the reference's own sampler (utils/utils.py:160-224)
+            from utils.utils import get_neighbor_sampler
+            data = Data(src, dst, t, eid, np.zeros(len(src)))
+            q = np.minimum(q, int(max(src.max(), dst.max())))       # its adjacency list ends at the largest id seen
+            cs = get_neighbor_sampler(data=data, sample_neighbor_strategy='recent', seed=0)
+            kind = 'reference'
+        else:
+            from oracle.neighbor_sampler import RecentSamplerOracle
+            cs = RecentSamplerOracle(src, dst, eid, t)
+            kind = 'port'
+        cs.get_historical_neighbors(q, qt, NUM_NEIGHBORS)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            cs.get_historical_neighbors(q, qt, NUM_NEIGHBORS)
+        cpu_us = (time.perf_counter() - t0) * 1e6 / 10
+    except Exception as e:                                           # a baseline leg must never sink the bench line
+        kind = f'unavailable: {type(e).__name__}: {e}'
+    out['cpu_us_per_batch'] = cpu_us
+    out['cpu_kind'] = kind
+    return out
+
+
+def run_tpnet_shape(args, shape, device, K, W, with_cpu=True, sampler_leg=False):
     """Single-GPU TPNet-batch workload (Reddit / Wikipedia / Flights shapes)."""
     per_edge_B, per_pair_B = algorithmic_bytes(shape)
     pps = pairs_per_step()
@@ -242,6 +351,8 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
     side = torch.cuda.Stream(device)
     pool = torch.cuda.graph_pool_handle()       # graphs replay in capture order, so they can share memory
     with torch.cuda.stream(side):
+        resident_step(m, dsteps[0])             # allocations / attribute opt-ins happen outside the captures
+        side.synchronize()
         for ds in dsteps:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, stream=side):
@@ -299,12 +410,13 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
     peak, peak_src = peak_gbs()
     achieved = pairs_per_launch * per_pair_B / (pair_ms * 1e-3) / 1e9
     step_bytes = BATCH * per_edge_B + pps * per_pair_B
-    kernels_per_step = 4 + 3                                  # 4 pair-wise + prep(+sweep) + snapshot + walk
+    heads = 4 if shape.num_layer == 3 else 0                 # the fused head exists for F = 64 (L = 3); else cuBLAS via nn.Sequential
+    kernels_per_step = 4 + heads + 3                          # 4 pair-wise (+ 4 head) + prep(+sweep) + snapshot + walk
     out = {
         'value': BATCH * K / (dev_ms * 1e-3), 'unit': 'edges/s', 'steps': K, 'warmup': W, 'ms_per_step': dev_ms / K,
         'config': {'workload': (f'{shape.name}-shaped synthetic graph ({shape.num_nodes} nodes, {shape.num_edges} '
                                 f'edges), d={shape.dim}, L={shape.num_layer}, batch {BATCH}, K={NUM_NEIGHBORS}, '
-                                f'{pps // BATCH} pair-encodes per edge, random negatives'),
+                                f'{pps // BATCH} pair-encodes per edge incl. self.mlp, random negatives'),
                    'batch': BATCH, 'num_neighbors': NUM_NEIGHBORS, 'pairs_per_step': pps, 'dim': shape.dim,
                    'num_layer': shape.num_layer, 'node_num': shape.node_num, 'parallelism': 'single GPU',
                    'decay_mode': 'lazy' if m.lazy else 'eager',
@@ -316,7 +428,8 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
         'algorithmic_GBps_step': step_bytes * K / (dev_ms * 1e-3) / 1e9,
         'roofline': {'bound': 'hbm', 'kernel': 'tpn::pairwise_nbr_kernel (encoder launch: 2B rows x K neighbours = 4BK pair blocks)',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic_note('reddit_pairwise_dram_bytes_per_launch'), 'peak_source': peak_src,
+                     'traffic': traffic_note('reddit_pairwise_dram_bytes_per_launch') if shape.name == 'reddit' else None,
+                     'peak_source': peak_src,
                      'launch_us': pair_ms * 1e3, 'pairs_per_launch': pairs_per_launch,
                      'note': 'state (%.1f MB) is L2-resident: algorithmic bytes are served from L2 after first '
                              'touch, so this is a fraction of the HBM copy peak reached out of L2, not DRAM use' %
@@ -326,14 +439,19 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
                 'path': 'RandomProjectionModule.get_pair_wise_feature/update with numpy ids, self.mlp included'},
         'gpu_launches': kernels_per_step * K,
     }
+    if sampler_leg:
+        out['sampler'] = time_sampler(shape, warm_batches, steps, device)
     if with_cpu:
         threads = os.cpu_count() or 1
-        n_cpu = args.cpu_sample_steps or 30
-        sec = cpu_port_tpnet(shape, warm_batches, steps, 2, n_cpu, threads)
-        sec3 = cpu_port_tpnet(shape, warm_batches, steps, 2, n_cpu, REF_THREADS)
-        out['cpu_baseline'] = {'value': BATCH / sec, 'unit': 'edges/s', 'cores': threads, 'kind': 'port',
-                               'sample': f'{n_cpu} steps of the same workload on the host (torch-CPU port of the '
-                                         f'reference, self.mlp included, {sec * 1e3:.1f} ms/step)',
+        n_cpu = args.cpu_sample_steps or 20
+        sec, kind = cpu_tpnet(shape, warm_batches, steps, 2, n_cpu, threads)
+        sec3, _ = cpu_tpnet(shape, warm_batches, steps, 2, max(n_cpu // 2, 3), REF_THREADS)
+        sec_id, _ = cpu_tpnet(shape, warm_batches, steps, 2, max(n_cpu // 2, 3), threads, with_mlp=False)
+        out['cpu_baseline'] = {'value': BATCH / sec, 'unit': 'edges/s', 'cores': threads, 'kind': kind,
+                               'sample': f'{n_cpu} steps of the same workload on the host ({kind}, self.mlp included, '
+                                         f'{sec * 1e3:.1f} ms/step)',
+                               'mlp_identity': {'value': BATCH / sec_id, 'note': 'same, with mlp = nn.Identity() '
+                                                                                 '(BASELINE.md section 2)'},
                                'at_reference_threads': {'value': BATCH / sec3, 'cores': REF_THREADS,
                                                         'note': 'torch.set_num_threads(3), the reference\'s own setting '
                                                                 '(train_link_prediction.py:124)'}}
@@ -344,7 +462,6 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True):
 
 # ============================================================================= power-law (sharded) workload
 def powerlaw_shape(args):
-    import dataclasses
     shape = SHAPES['powerlaw']
     if args.pl_nodes:
         shape = dataclasses.replace(shape, num_src=int(args.pl_nodes))
@@ -361,24 +478,22 @@ def powerlaw_steps(shape, B, n, seed=1234):
     return out
 
 
-def cpu_port_powerlaw(shape, B, n_warm, n_timed, threads, scale_down, device='cpu'):
-    """The reference's op sequence on a down-scaled replica (its eager decay is N-proportional).  device='cpu': the
-    CPU baseline.  A CUDA device: the same stock ATen ops on the GPU (what the unmodified reference does with
-    --gpu 0: pageable H2D of the ids per call, scatter_add_ with float atomics, batched GEMM), wall clock."""
-    import dataclasses
-    from oracle.cpu_port import CpuWalkProjection
+def cpu_port_powerlaw(shape, B, n_warm, n_timed, threads, scale_down, device='cpu', with_mlp=True):
+    """The reference's CPU path on a down-scaled replica (its eager decay is N-proportional).  device='cpu': the
+    reference arm / CPU baseline (the real class when oracle/_ref is installed).  A CUDA device: the port's stock
+    ATen op sequence on the GPU (scripts/aten_gpu_baseline.py).  Returns (seconds per step, nodes, kind)."""
     torch.set_num_threads(threads)
     small = dataclasses.replace(shape, num_src=max(shape.num_src // scale_down, 1000))
-    ref = CpuWalkProjection(small.node_num, shape.dim, shape.num_layer, shape.time_decay_weight, 0.0,
-                            not_scale=False, with_mlp=True, seed=0, device=device)
+    arm = CpuArm(dataclasses.replace(small, num_edges=shape.num_edges), small.node_num, 0.0, with_mlp=with_mlp,
+                 device=device)
     steps = powerlaw_steps(small, B, n_warm + n_timed)
 
     def one(st):
         s, d, t, neg = st
         with torch.no_grad():
-            pos = ref.pair_wise(s, d)
-            ng = ref.pair_wise(s, neg)
-            ref.update(s, d, t)
+            pos = arm.pair_wise(s, d)
+            ng = arm.pair_wise(s, neg)
+            arm.update(s, d, t)
             return float(pos.sum() - ng.sum())
 
     for st in steps[:n_warm]:
@@ -388,12 +503,62 @@ def cpu_port_powerlaw(shape, B, n_warm, n_timed, threads, scale_down, device='cp
     t0 = time.perf_counter()
     for st in steps[n_warm:]:
         one(st)                      # ends in float(...): the device is idle again when it returns
-    return (time.perf_counter() - t0) / n_timed, small.node_num
+    return (time.perf_counter() - t0) / n_timed, small.node_num, arm.kind
 
 
-def run_powerlaw(args, rank, world, device, K, W, sampler):
+def sharded_parity(args, rank, world, device):
+    """N > 1: a down-scaled replica (100,001 nodes, same d / L / decay / accumulation, job batches of pl_batch x N
+    edges) updated sharded — this very data plane — and, on rank 0, by the plain single-GPU module; the gathered
+    sharded state must equal the single-GPU state BIT FOR BIT; routed pair-wise features within fp32 tolerance."""
+    import torch.distributed as dist
+    from tpnet_b200 import RandomProjectionModule
+    from tpnet_b200.sharded import ShardedRandomProjection
+    shape = dataclasses.replace(SHAPES['powerlaw'], num_src=100_000)
+    B = args.pl_batch * world
+    kw = dict(node_num=shape.node_num, edge_num=shape.edge_num, dim_factor=shape.dim_factor, num_layer=shape.num_layer,
+              time_decay_weight=shape.time_decay_weight, device=str(device), use_matrix=False,
+              beginning_time=np.float64(0.0), not_scale=False, enforce_dim=-1)
+    torch.manual_seed(5)
+    sh = ShardedRandomProjection(decay_mode='lazy', ext_rows=shape.node_num + 1024, p0='global', state_device=device,
+                                 exchange=args.exchange, accumulation=args.accumulation, **kw).to(device)
+    ref = None
+    if rank == 0:
+        torch.manual_seed(5)
+        ref = RandomProjectionModule(decay_mode='lazy', accumulation=args.accumulation, **kw).to(device)
+    steps = powerlaw_steps(shape, B, 3, seed=99)
+    pair_diff = 0.0
+    for s, d, t, neg in steps:
+        keep, feat = sh.pair_wise_gram(s, neg)
+        if ref is not None:
+            keep_t = keep if isinstance(keep, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(keep)).to(device)
+            want = ref.pair_wise_gram(s, neg)[keep_t]
+            pair_diff = max(pair_diff, float((feat - want).abs().max().item()) if feat.numel() else 0.0)
+        sh.update(s, d, t)
+        if ref is not None:
+            ref.update(s, d, t)
+    full = sh.gather_global()
+    sh.check_errors()
+    out = None
+    if rank == 0:
+        ref.materialize()
+        diff = max(float((full[i] - ref.random_projections[i].data).abs().max().item())
+                   for i in range(shape.num_layer + 1))
+        equal = all(torch.equal(full[i], ref.random_projections[i].data) for i in range(shape.num_layer + 1))
+        out = {'world': world, 'max_abs_diff': diff, 'bit_equal': bool(equal),
+               'checked_rows': int(shape.node_num * (shape.num_layer + 1)), 'batches': len(steps), 'batch': B,
+               'pairwise_max_abs_diff': pair_diff, 'exchange': sh.exchange,
+               'what': 'sharded state (gather_global) vs the single-GPU module on a 100,001-node replica, same '
+                       'd/L/decay/accumulation; pair-wise features of the routed call vs the single-GPU call'}
+    del sh, ref, full
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return out
+
+
+def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, with_e2e=True):
     import torch.distributed as dist
     from tpnet_b200.sharded import ShardedRandomProjection
+    accumulation = accumulation or args.accumulation
     shape = powerlaw_shape(args)
     # weak scaling (default): every GPU brings its own 100,000 edges per step, so the batch of the whole job is
     # pl_batch x N; strong: the same 100,000-edge batch split over the ranks
@@ -402,68 +567,79 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
     per_edge_B, per_pair_B = algorithmic_bytes(shape)
     warm_n = args.warm_batches if args.warm_batches is not None else PL_WARM
     n_phase = min(K, 8)
-    steps = powerlaw_steps(shape, B, warm_n + 2 * (K + W) + n_phase)
+    steps = powerlaw_steps(shape, B, warm_n + 2 * (K + W) + n_phase + 1)
     torch.manual_seed(0)
+    # remote rows cached per generation (two pair calls + the update of one batch): at most the owned pairs of
+    # both calls plus the owned dst-role messages; sized from the per-rank launch capacity (3.5 / world of a call)
+    cap_pairs = min(B, int(B * min(1.0, 3.5 / world)) + 1024)
+    ext_rows = 3 * cap_pairs + 4096 if world > 1 else 1024
     m = ShardedRandomProjection(node_num=shape.node_num, edge_num=shape.edge_num, dim_factor=shape.dim_factor,
                                 num_layer=shape.num_layer, time_decay_weight=shape.time_decay_weight,
                                 device=str(device), use_matrix=False, beginning_time=np.float64(0.0),
-                                not_scale=False, enforce_dim=-1, decay_mode='lazy', ext_rows=2 * B + 1024,
-                                p0='device', state_device=device)
+                                not_scale=False, enforce_dim=-1, decay_mode='lazy', ext_rows=ext_rows,
+                                p0='device', state_device=device, exchange=args.exchange, accumulation=accumulation)
     m = m.to(device)
     m.init_p0_on_device(seed=0)
+    peer = world > 1 and m.exchange == 'peer'
     for s, d, t, _ in steps[:warm_n]:
         m.update(s, d, t)
     torch.cuda.synchronize()
+    m.check_errors()
+
+    def g(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+    def stage(st):
+        """Resident inputs of one step: the (replicated) edge batch as device tensors."""
+        s, d, t, neg = st
+        return dict(src=g(s), dst=g(d), t=g(t), neg=g(neg), t_last=float(t[-1]), host=st)
 
     def dev_plan(plan):
-        g = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)     # noqa: E731
         plan.first_rows, plan.second_rows, plan.send_rows = g(plan.first_rows), g(plan.second_rows), g(plan.send_rows)
         return plan
 
-    def stage(st):
-        """Resident inputs of one step.  One GPU: the edge batch itself as device tensors (the
-        plain edge-batch path).  Sharded: the routing plans, a pure function of the batch."""
+    def stage_nccl(st):
         s, d, t, neg = st
-        if world == 1:
-            g = lambda a: torch.from_numpy(a).to(device)     # noqa: E731
-            return dict(src=g(s), dst=g(d), t=g(t), neg=g(neg), t_last=float(t[-1]))
         up, tmsg = m.plan_update(s, d, t)
         return dict(src=s, dst=d, t=t, up=(dev_plan(up), torch.from_numpy(tmsg).to(device)),
                     pos=dev_plan(m.plan_pairs(s, d)), neg=dev_plan(m.plan_pairs(s, neg)))
 
-    res = [stage(st) for st in steps[warm_n:warm_n + K + W]]
+    nccl = world > 1 and not peer
+    res = [(stage_nccl if nccl else stage)(st) for st in steps[warm_n:warm_n + K + W]]
 
     def resident_pairs(st, which):
-        if world == 1:
-            m.pair_wise_gram(st['src'], st['dst' if which == 'pos' else 'neg'])
-            return B
-        m.pair_wise_gram(None, None, plan=st[which])
-        return int(st[which].first_rows.shape[0])
+        with torch.no_grad():
+            if world == 1:
+                m.get_pair_wise_feature(st['src'], st['dst' if which == 'pos' else 'neg'])
+            elif peer:
+                m.routed_pair_wise_feature(st['src'], st['dst' if which == 'pos' else 'neg'])
+            else:
+                _, feat = m.pair_wise_gram(None, None, plan=st[which])
+                m._head(feat)
 
     def resident_update(st):
-        if world == 1:
+        if nccl:
+            m.update(st['src'], st['dst'], st['t'], plan=st['up'])
+        else:
             m.update(st['src'], st['dst'], st['t'], next_time=st['t_last'])
-            return 2 * B
-        m.update(st['src'], st['dst'], st['t'], plan=st['up'])
-        return int(st['up'][0].first_rows.shape[0])
 
     def resident(st):
         resident_pairs(st, 'pos')
         resident_pairs(st, 'neg')
         resident_update(st)
 
-    # One GPU: every step is captured once into a CUDA graph and replayed once, in order (the host-side
-    # launch latency of the ~20 small kernels of a step would otherwise show up as idle gaps).
-    # Sharded: the all_to_all exchange stays an eager NCCL call.
-    use_graphs = world == 1 and not args.no_graphs
+    # Every step is captured once into a CUDA graph and replayed once, in order (the host-side launch latency of
+    # the ~20-40 small kernels of a step would otherwise show up as idle gaps).  N > 1, peer data plane: routing,
+    # pulls and barriers are kernels too, so the whole sharded step is one graph per rank; the NCCL data plane stays eager.
+    use_graphs = not nccl and not args.no_graphs
     side = torch.cuda.Stream(device)
     pool = torch.cuda.graph_pool_handle() if use_graphs else None
 
     def capture(fn, *a):
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, pool=pool, stream=side):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, pool=pool, stream=side):
             fn(*a)
-        return g
+        return gr
 
     if use_graphs:
         with torch.cuda.stream(side):
@@ -472,6 +648,8 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
         run_step = lambda i: graphs[i].replay()              # noqa: E731
     else:
         run_step = lambda i: resident(res[i])                # noqa: E731
+    if world > 1:
+        dist.barrier()
     for i in range(W):
         run_step(i)
     torch.cuda.synchronize()
@@ -479,7 +657,6 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
         dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    rows0 = m.exchanged_rows
     wall0 = time.perf_counter()
     for k in range(K):
         ev[k][0].record()
@@ -490,24 +667,24 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
         dist.barrier()
     wall1 = time.perf_counter()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    recv_rows_per_step = (m.exchanged_rows - rows0) / K
     m.check_errors()
     del res
     if use_graphs:
         del graphs
 
     # per-phase device time (events around each call) for the roofline of the dominant kernel
-    t_pair, t_upd, n_pairs_local, n_msgs_local = [], [], 0, 0
+    t_pair, t_upd = [], []
     for st in steps[warm_n + K + W:warm_n + K + W + n_phase]:
-        r = stage(st)
+        r = (stage_nccl if nccl else stage)(st)
         if world > 1:
             dist.barrier()
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         if use_graphs:
-            n_pairs_local, n_msgs_local = B, 2 * B
             with torch.cuda.stream(side):
                 gp, gu = capture(resident_pairs, r, 'pos'), capture(resident_update, r)
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             a.record()
             gp.replay()
             b.record()
@@ -515,99 +692,173 @@ def run_powerlaw(args, rank, world, device, K, W, sampler):
             c.record()
         else:
             a.record()
-            n_pairs_local = resident_pairs(r, 'pos')
+            resident_pairs(r, 'pos')
             b.record()
-            n_msgs_local = resident_update(r)
+            resident_update(r)
             c.record()
         torch.cuda.synchronize()
         t_pair.append(a.elapsed_time(b))
         t_upd.append(b.elapsed_time(c))
     pair_ms, upd_ms = float(np.mean(t_pair)), float(np.mean(t_upd))
 
-    # end to end: numpy API, plans computed inside the timed region, head + scalar read-back
-    api = steps[warm_n + K + W + n_phase:][:K + W]
-
-    def api_one(st):
-        s, d, t, neg = st
+    # one instrumented eager step (N > 1, peer): how many remote rows were pulled, and how fast
+    exch = None
+    if peer:
+        st = stage(steps[warm_n + K + W + n_phase])
+        ctr = m._shard_tensors['counters']
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        dist.barrier()
         with torch.no_grad():
-            _, pos = m.get_pair_wise_feature(s, d)
-            _, ng = m.get_pair_wise_feature(s, neg)
-            m.update(s, d, t)
-            r = pos.sum() - ng.sum()
-        return float(r.item())
+            m.routed_pair_wise_feature(st['src'], st['dst'])
+            m.routed_pair_wise_feature(st['src'], st['neg'])
+        rows_pairs = int(ctr[0].item())
+        # the pull of the pos call alone, timed (fresh generation: force one by a no-op reload-free reset of the cache)
+        m._state_written()
+        torch.cuda.synchronize()
+        dist.barrier()
+        lib_ptrs = m._global_ids_to_device([st['src'], st['dst']], ['id', 'id'])
+        from tpnet_b200 import _lib as tl
+        lib = tl.load()
+        rb = m._route_buffers('pairs', B)
+        keep = torch.empty(B, dtype=torch.int64, device=device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=device)
+        lib.tpn_route_pairs(m._c_shard(), lib_ptrs[0], lib_ptrs[1], B, rb['first'].data_ptr(), rb['second'].data_ptr(),
+                            keep.data_ptr(), cnt.data_ptr(), rb['ws'].data_ptr(), rb['ws'].numel(), m._stream())
+        m._barrier()
+        m._dirty = False
+        evs[0].record()
+        lib.tpn_pull_rows(m._c_state(), m._c_shard(), m._stream())
+        evs[1].record()
+        torch.cuda.synchronize()
+        rows_pos = int(ctr[0].item())
+        pull_ms = evs[0].elapsed_time(evs[1])
+        block_bytes = (shape.num_layer + 1) * m.row_stride * 4
+        m._state_written()
+        dist.barrier()
+        tt = torch.tensor([rows_pairs, rows_pos, pull_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        rows_pairs, rows_pos, pull_ms = [float(x) for x in tt.tolist()]
+        exch = {'data_plane': 'device-side routing + NVLink pulls out of the owners\' HBM (IPC-mapped peer memory) + '
+                              'flag barriers; no NCCL in the step',
+                'rows_cached_per_rank_per_step': rows_pairs, 'bytes_per_rank_per_step': rows_pairs * block_bytes,
+                'pull_of_one_pair_call': {'rows': rows_pos, 'ms': pull_ms,
+                                          'achieved_GBps': rows_pos * block_bytes / (pull_ms * 1e-3) / 1e9,
+                                          'peak_GBps': NVLINK_GBS,
+                                          'note': 'upper bound on bytes: never-written rows are not fetched'},
+                'barriers_per_step': 2}
 
-    for st in api[:W]:
-        api_one(st)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0 = time.perf_counter()
-    n_api = len(api) - W
-    for st in api[W:]:
-        api_one(st)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e2e_ms = (time.perf_counter() - e0) * 1e3
+    # end to end: numpy API, routing inside the timed region, head + scalar read-back
+    e2e_ms, n_api = float('nan'), 0
+    if with_e2e:
+        api = steps[warm_n + K + W + n_phase + 1:][:K + W]
+
+        def api_one(st):
+            s, d, t, neg = st
+            with torch.no_grad():
+                if peer:
+                    pos = m.routed_pair_wise_feature(s, d).feat          # zero rows past the count
+                    ng = m.routed_pair_wise_feature(s, neg).feat
+                else:
+                    _, pos = m.get_pair_wise_feature(s, d)
+                    _, ng = m.get_pair_wise_feature(s, neg)
+                m.update(s, d, t)
+                r = pos.sum() - ng.sum()
+            return float(r.item())
+
+        for st in api[:W]:
+            api_one(st)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0 = time.perf_counter()
+        n_api = len(api) - W
+        for st in api[W:]:
+            api_one(st)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e2e_ms = (time.perf_counter() - e0) * 1e3
+        m.check_errors()
     wall_end = time.perf_counter()
 
-    tt = torch.tensor([dev_ms, e2e_ms, pair_ms, upd_ms, recv_rows_per_step], dtype=torch.float64, device=device)
+    tt = torch.tensor([dev_ms, e2e_ms if with_e2e else 0.0, pair_ms, upd_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, pair_ms, upd_ms, recv_rows_per_step = [float(x) for x in tt.tolist()]
+    dev_ms, e2e_ms, pair_ms, upd_ms = [float(x) for x in tt.tolist()]
+    barriers = m.barriers
+    row_stride = m.row_stride
+    del m
+    torch.cuda.empty_cache()
     if rank != 0:
         return None
 
     peak, peak_src = peak_gbs()
-    pair_gbs = n_pairs_local * per_pair_B / (pair_ms * 1e-3) / 1e9
-    upd_gbs = n_msgs_local * (per_edge_B / 2) / (upd_ms * 1e-3) / 1e9
+    # per rank: B/world * ... under weak scaling every rank owns ~pl_batch pairs per call and ~2*pl_batch messages
+    n_pairs_rank, n_msgs_rank = B // world, 2 * B // world
+    pair_gbs = n_pairs_rank * per_pair_B / (pair_ms * 1e-3) / 1e9
+    upd_gbs = n_msgs_rank * (per_edge_B / 2) / (upd_ms * 1e-3) / 1e9
     dominant_is_update = upd_ms >= 2 * pair_ms            # two pair-wise calls per step vs one update
     step_bytes = B * per_edge_B + 2 * B * per_pair_B
-    block_bytes = (shape.num_layer + 1) * m.row_stride * 4
+    block_bytes = (shape.num_layer + 1) * row_stride * 4
     state_gb = shape.node_num * block_bytes / 1e9
+    front = 'routing + NVLink pull + barriers + ' if world > 1 else ''
     roof = {'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
-            'phases': {'pairwise': {'what': 'exchange (N>1) + tpn::pairwise_tma_kernel, %d pairs on rank 0' % n_pairs_local,
-                                    'ms': pair_ms, 'achieved': pair_gbs, 'frac': pair_gbs / peak},
-                       'update': {'what': 'exchange (N>1) + radix sort + snapshot + tpn::walk_small_kernel || '
-                                          'tpn::walk_hub2_kernel, %d messages on rank 0'
-                                  % n_msgs_local, 'ms': upd_ms, 'achieved': upd_gbs, 'frac': upd_gbs / peak}}}
+            'phases': {'pairwise': {'what': front + 'tpn::pairwise_tma_kernel + tpn::head_forward_kernel, ~%d pairs per rank'
+                                            % n_pairs_rank, 'ms': pair_ms, 'achieved': pair_gbs, 'frac': pair_gbs / peak},
+                       'update': {'what': front + 'radix sort + snapshot + tpn::walk_small_kernel || tpn::walk_hub2_kernel'
+                                          ' (+ combine_giants), ~%d messages per rank' % n_msgs_rank,
+                                  'ms': upd_ms, 'achieved': upd_gbs, 'frac': upd_gbs / peak}}}
+    tkey = 'powerlaw_update_dram_bytes_per_call' if dominant_is_update else 'powerlaw_pairwise_dram_bytes_per_launch'
+    if accumulation == 'chunked' and dominant_is_update:
+        tkey = 'powerlaw_update_chunked_dram_bytes_per_call'
     if dominant_is_update:
         roof.update(kernel='update path (radix sort + snapshot + walk_small || walk_hub2)', achieved=upd_gbs,
-                    frac=upd_gbs / peak, traffic=traffic_note('powerlaw_update_dram_bytes_per_call'))
+                    frac=upd_gbs / peak)
     else:
-        roof.update(kernel='tpn::pairwise_tma_kernel', achieved=pair_gbs, frac=pair_gbs / peak,
-                    traffic=traffic_note('powerlaw_pairwise_dram_bytes_per_launch'))
+        roof.update(kernel='tpn::pairwise_tma_kernel (+ head)', achieved=pair_gbs, frac=pair_gbs / peak)
+    # ncu DRAM bytes are a property of the N=1 launch: not carried over to the sharded runs
+    roof['traffic'] = traffic_note(tkey) if world == 1 else None
     h2d = 3 * B * 8 + 2 * (2 * B * 8)
-    return {
+    upd_launches = 1 + 9 + 1 + 1 + 1 + 1 + 1 + 1                # prep, 3 x (hist, prefix, scatter), payload, sort_giants |
+    #                                                             combine, snapshot, hub2, small, stamps
+    per_step = 2 * 2 + upd_launches if world == 1 else (2 * (4 + 1 + 2) + 1 + 4 + 1 + 1 + upd_launches)
+    line = {
         'metric': METRIC, 'value': B * K / (dev_ms * 1e-3), 'unit': 'edges/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'weak' if weak else 'strong',
         'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': (f'power-law temporal graph, {shape.num_nodes} nodes / {shape.num_edges} edges '
                                 f'(BASELINE configs[3]), d={shape.dim}, L={shape.num_layer}, batch {B}, 2 pair-encodes '
-                                f'per edge (decoder shape), lazy decay'),
+                                f'per edge incl. self.mlp (decoder shape), lazy decay'),
                    'batch': B, 'pairs_per_step': 2 * B, 'dim': shape.dim, 'num_layer': shape.num_layer,
                    'node_num': shape.node_num, 'state_GB': state_gb,
+                   'accumulation': CHUNKED_NOTE if accumulation == 'chunked' else
+                   'reference: one message at a time per row, the order of CPU scatter_add_ (TPNet.py:93-96), bit for bit',
                    'parallelism': 'single GPU' if world == 1 else
-                   f'state sharded by node id over {world} GPUs, one all_to_all per call (NCCL)',
+                   (f'state sharded by node id over {world} GPUs; per call: device-side routing, remote rows pulled over '
+                    f'NVLink from peer memory, {2} flag barriers per step; the step is ONE CUDA graph per rank'
+                    if peer else f'state sharded by node id over {world} GPUs, host plan + one all_to_all per call (NCCL)'),
                    'l2': f'no flush needed: {state_gb:.1f} GB state >> 126 MB L2',
-                   'timing': ('CUDA events per step, one CUDA graph per step' if use_graphs else
-                              'CUDA events per step, max over ranks; routing plans are part of the resident inputs'),
+                   'timing': ('CUDA events per step, one CUDA graph per step' + (', max over ranks; routing is inside the step'
+                                                                                 if world > 1 else '')) if use_graphs else
+                             'CUDA events per step, max over ranks; host routing plans are resident inputs',
                    'algorithmic_bytes_per_step': step_bytes, 'wall_ms_per_step': (wall1 - wall0) * 1e3 / K},
         'pairs_per_s': 2 * B * K / (dev_ms * 1e-3),
         'algorithmic_GBps_step': step_bytes * K / (dev_ms * 1e-3) / 1e9,
         'roofline': roof,
-        'e2e': {'value': B * n_api / (e2e_ms * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / n_api,
-                'path': 'ShardedRandomProjection.get_pair_wise_feature/update with numpy ids (routing plan computed '
-                        'on the host inside the timed region), self.mlp included'},
-        # per step: 2 pair-wise + update (prep, 3 x (hist + prefix + scatter), payload, giant sort, snapshot,
-        # hub2, small, stamps)
-        'gpu_launches': K * (2 + 16 + (6 if world > 1 else 0)),
-        'exchange': None if world == 1 else {'rows_received_per_rank_per_step': recv_rows_per_step,
-                                             'bytes_per_rank_per_step': recv_rows_per_step * block_bytes},
+        'gpu_launches': K * per_step,
+        'exchange': exch,
         'clocks': sampler.window(wall0, wall_end) if sampler else None,
     }
+    if with_e2e:
+        line['e2e'] = {'value': B * n_api / (e2e_ms * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': h2d,
+                       'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / n_api,
+                       'path': ('ShardedRandomProjection.routed_pair_wise_feature/update with numpy ids: every rank stages '
+                                '1/N of each array, the slices are all-gathered over NVLink, routing on the device; '
+                                if peer else 'ShardedRandomProjection.get_pair_wise_feature/update with numpy ids; ')
+                               + 'self.mlp included, scalar result read back'}
+        line['barriers_total'] = barriers
+    return line
 
 
 # ============================================================================= main
@@ -618,7 +869,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     threads = args.cpu_threads or os.cpu_count() or 1
 
-    # ---------------- reference arm: CPU port on the host cores, rank 0 only
+    # ---------------- reference arm: the reference's CPU implementation on the host cores, rank 0 only
     if args.impl == 'reference':
         if rank != 0:
             return
@@ -626,25 +877,28 @@ def main():
             K = min(args.steps or 3, 6)
             W = min(args.warmup if args.warmup is not None else 1, 2)
             shape = powerlaw_shape(args)
-            sec, n_small = cpu_port_powerlaw(shape, args.pl_batch, W, K, threads, scale_down=10)
+            sec, n_small, kind = cpu_port_powerlaw(shape, args.pl_batch, W, K, threads, scale_down=10)
             val = args.pl_batch / sec
-            sample = (f'{K} batches of {args.pl_batch} edges + 2 pair-encodes per edge on a {n_small}-node replica '
-                      f'(10x fewer nodes: the reference\'s eager decay is N-proportional, so this flatters it)')
+            sample = (f'{K} batches of {args.pl_batch} edges + 2 pair-encodes per edge (self.mlp included) on a '
+                      f'{n_small}-node replica (10x fewer nodes: the reference\'s eager decay is N-proportional, so this '
+                      f'flatters it)')
             cfg = {'workload': f'power-law temporal graph (BASELINE configs[3]) d={shape.dim} L={shape.num_layer} '
                                f'batch {args.pl_batch}, CPU arm on a 10x down-scaled node set', 'batch': args.pl_batch}
         else:
             shape = SHAPES[args.workload]
             K, W = min(args.steps or 30, 60), max(args.warmup or 3, 1)
             warm_batches, steps = make_steps(shape, K + W, seed=0, warm=60)
-            sec = cpu_port_tpnet(shape, warm_batches, steps, W, K, threads)
+            sec, kind = cpu_tpnet(shape, warm_batches, steps, W, K, threads)
             val = BATCH / sec
-            sample = f'{K} steps of the same workload (torch-CPU port of the reference, self.mlp included)'
+            sample = f'{K} steps of the same workload (self.mlp included)'
             cfg = {'workload': f'{shape.name}-shaped synthetic graph, batch {BATCH}, K={NUM_NEIGHBORS}', 'batch': BATCH}
+        what = ('the unmodified reference class (oracle/_ref/TPNet, models/TPNet.py:9-157)' if kind == 'reference'
+                else 'torch-CPU port of the reference (oracle/cpu_port.py)')
         print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'edges/s', 'n_gpus': args.gpus,
                           'steps': K, 'warmup': W, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
                           'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
-                          'cpu_baseline': {'value': val, 'unit': 'edges/s', 'cores': threads, 'kind': 'port',
-                                           'sample': sample},
+                          'cpu_baseline': {'value': val, 'unit': 'edges/s', 'cores': threads, 'kind': kind,
+                                           'sample': sample + '; ' + what},
                           'e2e': {'value': val, 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
         return
 
@@ -664,21 +918,40 @@ def main():
     if args.workload == 'powerlaw':
         K, W = args.steps or 20, max(args.warmup if args.warmup is not None else 3, 3)
         line = run_powerlaw(args, rank, world, device, K, W, sampler)
+        if world > 1 and not args.no_parity:
+            parity = sharded_parity(args, rank, world, device)
+            if rank == 0:
+                line['parity'] = parity
         if rank == 0:
             if world == 1:
                 n_cpu = args.cpu_sample_steps or 3
-                sec, n_small = cpu_port_powerlaw(powerlaw_shape(args), args.pl_batch, 1, n_cpu, threads, scale_down=10)
-                sec3, _ = cpu_port_powerlaw(powerlaw_shape(args), args.pl_batch, 1, 1, REF_THREADS, scale_down=10)
+                shape = powerlaw_shape(args)
+                sec, n_small, kind = cpu_port_powerlaw(shape, args.pl_batch, 1, n_cpu, threads, scale_down=10)
+                sec3, _, _ = cpu_port_powerlaw(shape, args.pl_batch, 1, 1, REF_THREADS, scale_down=10)
+                sec_id, _, _ = cpu_port_powerlaw(shape, args.pl_batch, 1, 1, threads, scale_down=10, with_mlp=False)
                 line['cpu_baseline'] = {'value': args.pl_batch / sec, 'unit': 'edges/s', 'cores': threads,
-                                        'kind': 'port',
+                                        'kind': kind,
                                         'sample': f'{n_cpu} batches on a {n_small}-node replica (10x fewer nodes than '
-                                                  f'the GPU run; torch-CPU port of the reference, self.mlp included, '
-                                                  f'{sec:.2f} s/step)',
+                                                  f'the GPU run; {kind}, self.mlp included, {sec:.2f} s/step)',
+                                        'mlp_identity': {'value': args.pl_batch / sec_id,
+                                                         'note': 'same, with mlp = nn.Identity() (BASELINE.md section 2); 1 batch'},
                                         'at_reference_threads': {'value': args.pl_batch / sec3, 'cores': REF_THREADS,
                                                                  'note': 'torch.set_num_threads(3), the reference\'s own '
                                                                          'setting (train_link_prediction.py:124); 1 batch'}}
                 if not args.no_also:
-                    line['also'] = {'reddit': run_tpnet_shape(args, SHAPES['reddit'], device, 300, 10, with_cpu=True)}
+                    also = {}
+                    other = 'chunked' if args.accumulation == 'reference' else 'reference'
+                    alt = run_powerlaw(args, rank, world, device, min(K, 10), W, None, accumulation=other, with_e2e=False)
+                    also[other + '_order'] = {k: alt[k] for k in ('value', 'ms_per_step', 'roofline')}
+                    also[other + '_order']['note'] = CHUNKED_NOTE if other == 'chunked' else (
+                        'same workload with accumulation=reference (strictly sequential adds per row, bit-identical to '
+                        'CPU scatter_add_)')
+                    also['reddit'] = run_tpnet_shape(args, SHAPES['reddit'], device, 300, 10, with_cpu=True, sampler_leg=True)
+                    for name in ('wikipedia', 'flights'):
+                        a2 = argparse.Namespace(**vars(args))
+                        a2.cpu_sample_steps = args.cpu_sample_steps or 10
+                        also[name] = run_tpnet_shape(a2, SHAPES[name], device, 200, 10, with_cpu=True)
+                    line['also'] = also
             else:
                 line['cpu_baseline'] = None
     else:
@@ -686,7 +959,8 @@ def main():
             raise SystemExit('the TPNet-batch shapes are single-GPU workloads (state 13-32 MB): use --workload powerlaw')
         K, W = args.steps or 300, max(args.warmup if args.warmup is not None else 10, 3)
         t0 = time.perf_counter()
-        body = run_tpnet_shape(args, SHAPES[args.workload], device, K, W, with_cpu=True)
+        body = run_tpnet_shape(args, SHAPES[args.workload], device, K, W, with_cpu=True,
+                               sampler_leg=args.workload == 'reddit')
         line = {'metric': METRIC, 'n_gpus': 1, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic'}
         line.update(body)

@@ -59,7 +59,7 @@
 extern "C" {
 #endif
 
-#define TPN_ABI_VERSION 8
+#define TPN_ABI_VERSION 10
 
 #define TPN_MAX_LAYERS 4
 
@@ -95,6 +95,18 @@ typedef struct tpn_state {
                                [-num_nodes, num_nodes) — the reference's IndexError (TPNet.py:109), which a
                                kernel cannot raise; negative ids wrap as tensor indexing does; the access is
                                clamped only to stay in bounds.  The host polls the flag.                */
+    int32_t  giant_chunk;   /* accumulation order of one target row's messages in tpn_update[_messages]:
+                               0 (default) = the reference's order: one message at a time, sequentially
+                                 (what CPU scatter_add_ does, TPNet.py:93-96) — bit-identical to it;
+                               C > 0 (multiple of 32, 256..2048) = CHUNKED order for rows receiving >= 2048
+                                 messages in one call: the messages are cut, in order, into chunks of C;
+                                 every chunk is summed sequentially from +0; the chunk sums are then added
+                                 to the (decayed) row in chunk order.  Deterministic and independent of the
+                                 launch geometry; differs from the sequential order only by fp32 rounding
+                                 (|diff| <= ~1e-6 * sum|terms|, smaller than sequential-vs-exact), and lets
+                                 the add chain of a hub run in parallel.  Rows with < 2048 messages always
+                                 use the reference order.                                               */
+    int32_t  reserved0;
 } tpn_state_t;
 
 int tpn_version(void);
@@ -148,14 +160,18 @@ int tpn_set_debug_flags(int flags);
  * counterpart — the reference is single-device).  Message m adds source row src_dev[m] into
  * target row tgt_dev[m] with the weight of timestamp t_dev[m]; messages of one target are
  * accumulated in the order given.  Ids index rows of `st`: rows [0, num_local_rows) are this
- * shard's rows, rows [num_local_rows, num_nodes) hold blocks received from other ranks — they
- * must be current and are only ever read.  Precondition (true for edge batches, which carry
+ * shard's rows, rows [num_local_rows, num_nodes) hold copies of other ranks' blocks — they are only
+ * ever read and, in lazy mode, carry their own stamps like any row (a copy that was brought current
+ * by its sender is stamped with the current epoch).  Precondition (true for edge batches, which carry
  * both directions of every edge): every LOCAL source row is also a target of the same call;
  * in lazy mode a violation sets *err_flag_dev = 2 (eager mode handles it correctly).
+ * num_messages_dev: NULL, or a device int32 holding the real number of messages (<= num_messages, which is then
+ * only the capacity the grids are sized for) — the count the routing kernels (tpn_route_update) leave on the
+ * device, so that no launch waits for a device -> host copy.
  */
 int tpn_update_messages(tpn_state_t* st,
                         const int64_t* tgt_dev, const int64_t* src_dev, const double* t_dev, int64_t num_messages,
-                        int64_t num_local_rows,
+                        const int32_t* num_messages_dev, int64_t num_local_rows,
                         double t_last, float neg_lambda, const float* decay,
                         void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, void* stream);
 
@@ -171,9 +187,12 @@ int tpn_gather_blocks(const tpn_state_t* st, const int64_t* ids_dev, int64_t n, 
  *                          rows [a:P_0..P_L, b:P_0..P_L]                (TPNet.py:119-123)
  *   apply_log_scale      : 1 -> clamp at 0 then log(x + 1.0)   (TPNet.py:127-128)
  *                          0 -> raw inner products             (`not_scale`, :124-125)
+ *   n_dev                : NULL, or a device int32 with the real number of pairs (<= n; n is then the capacity
+ *                          the grid is sized for; rows of out_dev past the count are not written) — routed
+ *                          calls of a sharded state (tpn_route_pairs)
  */
 int tpn_pairwise(const tpn_state_t* st, const int64_t* a_ids_dev, const int64_t* b_ids_dev, int64_t n,
-                 int apply_log_scale, float* out_dev, void* stream);
+                 const int32_t* n_dev, int apply_log_scale, float* out_dev, void* stream);
 
 /*
  * The encoder's structured pair-wise call — the index construction and re-split around
@@ -209,8 +228,9 @@ int tpn_pairwise_neighbors(const tpn_state_t* st, const int64_t* nbr_dev, const 
  *   y_dev   : float32[n][features] device, 16-byte aligned
  * Built for the default 3-layer configuration, features = 64 and hidden = 256; any other shape
  * returns TPN_ERR_UNSUPPORTED (the caller applies the head with its own GEMMs).
+ * n_dev: NULL, or a device int32 with the real row count (<= n), as in tpn_pairwise.
  */
-int tpn_head_forward(const float* x_dev, int64_t n, int features, int hidden, const float* w1_dev,
+int tpn_head_forward(const float* x_dev, int64_t n, const int32_t* n_dev, int features, int hidden, const float* w1_dev,
                      const float* b1_dev, const float* w2_dev, const float* b2_dev, float* y_dev, void* stream);
 
 /*
@@ -294,6 +314,63 @@ void tpn_planner_destroy(tpn_planner_t* p);
 int tpn_plan(tpn_planner_t* p, const int64_t* first, const int64_t* second, int64_t count, int64_t n_local,
              int64_t* keep, int64_t* first_rows, int64_t* second_rows, int64_t* n_keep,
              int64_t* send_rows, int64_t* n_send, int64_t* send_counts, int64_t* recv_counts);
+
+/*
+ * ---------------------------------------------------------------------------------------------------------
+ * Node-sharded state over peer memory (no reference counterpart — the reference is
+ * single-device).  Rows of node u live on rank u % world at local row u / world; rows [0, num_local_rows) of a
+ * rank's state are its own, rows [num_local_rows, num_local_rows + ext_rows) cache row blocks of other ranks.
+ * The batch is replicated on every rank's device.  Per call every rank runs, on its own stream and with no host
+ * round trip:  tpn_route_* (which items are mine, which remote rows do I need)  ->  tpn_pull_rows (read them out
+ * of the owners' HBM over NVLink: peer pointers)  ->  [tpn_peer_barrier]  ->  tpn_update_messages / tpn_pairwise
+ * with the device-side count.  A cached remote row stays valid until the next write to the state: the caller
+ * starts a new generation (tpn_shard_new_generation) after every update.
+ * Barrier protocol (the caller's duty, tpnet_b200/sharded.py): one tpn_peer_barrier between the last write of a
+ * rank and the first pull of its rows by a peer, and one between the last pull of a call and the first write.
+ */
+#define TPN_SHARD_CTR_NEED 0    /* extension slots handed out in this generation                              */
+#define TPN_SHARD_CTR_PREV 1    /* ... before the latest tpn_route_* call (tpn_pull_rows pulls [PREV, NEED))   */
+#define TPN_SHARD_CTR_ERROR 2   /* sticky: 1 = id outside the graph, 2 = extension rows exhausted, 3 = a peer
+                                   never reached a barrier                                                     */
+#define TPN_SHARD_COUNTERS 8
+typedef struct tpn_shard {
+    int32_t  world, rank;
+    int64_t  global_nodes;              /* ids are 0 .. global_nodes-1                                          */
+    int64_t  num_local_rows;
+    int64_t  ext_rows;                  /* capacity of the remote-row cache                                     */
+    const float* const* peer_data;      /* DEVICE array [world]: state buffer of rank q, mapped into this process */
+    const int32_t* const* peer_stamps;  /* DEVICE array [world]: stamps of rank q (NULL in eager mode)          */
+    uint32_t* const* peer_flags;        /* DEVICE array [world]: barrier words of rank q, uint32[world] each    */
+    int32_t* mark;                      /* device int32[global_nodes], zero = not cached (tpn_shard_new_generation) */
+    int32_t* counters;                  /* device int32[TPN_SHARD_COUNTERS]                                     */
+    int64_t* need_nodes;                /* device int64[ext_rows]: global id cached in each extension row       */
+    uint32_t* barrier_seq;              /* device uint32[1]: barriers passed so far (same on every rank)        */
+} tpn_shard_t;
+
+size_t tpn_route_workspace_bytes(int64_t items);
+/* The 2*batch update messages of the replicated edge batch (the reference's order, TPNet.py:93-96): those whose
+ * target this rank owns, in order -> tgt_rows_out / src_rows_out (local row, or num_local_rows + cache slot) /
+ * t_out, their number -> *count_out_dev.  Outputs hold 2*batch elements. */
+int tpn_route_update(const tpn_shard_t* sh, const int64_t* src_dev, const int64_t* dst_dev, const double* t_dev,
+                     int64_t batch, int64_t* tgt_rows_out, int64_t* src_rows_out, double* t_out,
+                     int32_t* count_out_dev, void* ws_dev, size_t ws_bytes, void* stream);
+/* Pairs (a[i], b[i]) whose first endpoint this rank owns, in order; keep_out[j] = position i of the j-th kept pair
+ * (may be NULL).  Outputs hold n elements. */
+int tpn_route_pairs(const tpn_shard_t* sh, const int64_t* a_dev, const int64_t* b_dev, int64_t n,
+                    int64_t* a_rows_out, int64_t* b_rows_out, int64_t* keep_out, int32_t* count_out_dev,
+                    void* ws_dev, size_t ws_bytes, void* stream);
+/* Fills the cache slots handed out by the latest tpn_route_* call from the owners' memory (rows and, in lazy
+ * mode, their stamps — a cached row is read exactly like a local one). */
+int tpn_pull_rows(const tpn_state_t* st, const tpn_shard_t* sh, void* stream);
+int tpn_peer_barrier(const tpn_shard_t* sh, void* stream);
+int tpn_shard_new_generation(const tpn_shard_t* sh, void* stream);
+/* Peer-visible device memory: cudaMalloc'ed (zero-filled) on the current device, exported / opened with CUDA IPC.
+ * tpn_ipc_open maps another PROCESS's allocation and enables peer access from the current device. */
+int tpn_peer_alloc(void** out, size_t bytes);
+int tpn_peer_free(void* p);
+int tpn_ipc_export(const void* p, unsigned char* handle64);
+int tpn_ipc_open(const unsigned char* handle64, void** out);
+int tpn_ipc_close(void* p);
 
 #ifdef __cplusplus
 }

@@ -120,11 +120,19 @@ class WalkProjectionOracle:
             self.P[i] = np.array(layers[i - 1], dtype=F32, copy=True)
 
     # --------------------------------------------------------------- update
+    GIANT_MIN = 2048    # chunked order: rows with at least this many messages in one update
+
     def update(self, src: np.ndarray, dst: np.ndarray, times: np.ndarray,
-               weights: Optional[np.ndarray] = None) -> None:
+               weights: Optional[np.ndarray] = None, giant_chunk: int = 0) -> None:
         """TPNet.py:67-99.  ``weights`` lets the pinning script inject the
         reference's own torch-computed w_j so that everything else can be
-        compared bit-for-bit."""
+        compared bit-for-bit.
+
+        ``giant_chunk = C > 0`` restates the library's CHUNKED accumulation order
+        (include/tpnet_b200.h, ``tpn_state_t::giant_chunk``; not a reference behaviour): a row that
+        receives >= GIANT_MIN messages in this update has them cut, in the reference's order, into
+        chunks of C; each chunk is summed sequentially; the chunk sums are added to the decayed row in
+        chunk order.  Every other row keeps the reference's sequential order."""
         src = np.asarray(src, dtype=np.int64)
         dst = np.asarray(dst, dtype=np.int64)
         times = np.asarray(times, dtype=np.float64)
@@ -143,7 +151,10 @@ class WalkProjectionOracle:
             msg_to_src = below[dst] * w[:, None]                 # gathered BEFORE either scatter
             msg_to_dst = below[src] * w[:, None]
             tgt = self.P[i]
-            if src.shape[0] <= self.LOOP_MAX:
+            if giant_chunk > 0:
+                self._chunked_scatter(tgt, np.concatenate([src, dst]), np.concatenate([msg_to_src, msg_to_dst]),
+                                      int(giant_chunk))
+            elif src.shape[0] <= self.LOOP_MAX:
                 for j in range(src.shape[0]):                    # batch order per target row
                     tgt[src[j]] += msg_to_src[j]
                 for j in range(dst.shape[0]):
@@ -155,6 +166,23 @@ class WalkProjectionOracle:
                 np.add.at(tgt, src, msg_to_src)
                 np.add.at(tgt, dst, msg_to_dst)
         self.now_time = t_last
+
+    def _chunked_scatter(self, tgt: np.ndarray, rows: np.ndarray, msgs: np.ndarray, chunk: int) -> None:
+        """``rows``/``msgs``: the 2B messages of one layer in the reference's order (all src-role messages
+        in batch order, then all dst-role messages).  Non-giant rows: sequential adds (== the two add.at of
+        the reference order).  Giant rows: chunk sums, then the chunk sums in order."""
+        counts = np.bincount(rows, minlength=self.node_num)
+        giants = np.nonzero(counts >= self.GIANT_MIN)[0]
+        small = ~np.isin(rows, giants)
+        np.add.at(tgt, rows[small], msgs[small])
+        for g in giants:
+            m = msgs[rows == g]                                   # this row's messages, in order
+            acc = tgt[g].copy()
+            for c0 in range(0, m.shape[0], chunk):
+                # np.add.accumulate adds one element at a time in the array's dtype (sequential fp32 adds)
+                part = np.add.accumulate(m[c0:c0 + chunk], axis=0, dtype=F32)[-1]
+                acc = acc + part
+            tgt[g] = acc
 
     # ---------------------------------------------------------------- reads
     def get_random_projections(self, node_ids: np.ndarray) -> List[np.ndarray]:

@@ -40,22 +40,37 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.tpn_update_workspace_bytes(ctypes.byref(st), 100000) > lib.tpn_update_workspace_bytes(ctypes.byref(st), 200)
 
 
-def test_struct_layout_matches_header():
-    # int64-aligned POD: 8+8+4+4+8+8+8+8+8+8+8 bytes
-    assert ctypes.sizeof(_lib.TpnState) == 80
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors against the header itself: a C program (gcc) prints sizeof / offsetof of every field."""
+    import subprocess
+    fields = {'tpn_state_t': [f[0] for f in _lib.TpnState._fields_], 'tpn_shard_t': [f[0] for f in _lib.TpnShard._fields_]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tpnet_b200.h"', 'int main(void) {']
+    for name, fs in fields.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        lines += [f'  printf("{name}.{f} %zu\\n", offsetof({name}, {f}));' for f in fs]
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in (('tpn_state_t', _lib.TpnState), ('tpn_shard_t', _lib.TpnShard)):
+        assert int(out[name]) == ctypes.sizeof(cls), name
+        for f in fields[name]:
+            assert int(out[f'{name}.{f}']) == getattr(cls, f).offset, (name, f)
 
 
 def test_argument_validation_without_gpu():
     lib = _lib.load()
     st = _lib.TpnState()           # null data pointer
-    assert lib.tpn_pairwise(ctypes.byref(st), None, None, 4, 1, None, None) < 0
+    assert lib.tpn_pairwise(ctypes.byref(st), None, None, 4, None, 1, None, None) < 0
     assert lib.tpn_gather(ctypes.byref(st), None, 4, None, None) < 0
     assert lib.tpn_materialize(ctypes.byref(st), None) < 0
     assert lib.tpn_pairwise_neighbors(ctypes.byref(st), None, None, None, 4, 5, 1, None, None) < 0
     # the fused head exists for the default 64 -> 256 -> 64 shape only; other shapes are the caller's GEMMs
-    assert lib.tpn_head_forward(None, 10, 36, 144, None, None, None, None, None, None) == _lib.TPN_ERR_UNSUPPORTED
-    assert lib.tpn_head_forward(None, 10, 64, 256, None, None, None, None, None, None) < 0      # null pointers
-    assert lib.tpn_head_forward(None, 0, 64, 256, None, None, None, None, None, None) == 0      # nothing to do
+    assert lib.tpn_head_forward(None, 10, None, 36, 144, None, None, None, None, None, None) == _lib.TPN_ERR_UNSUPPORTED
+    assert lib.tpn_head_forward(None, 10, None, 64, 256, None, None, None, None, None, None) < 0      # null pointers
+    assert lib.tpn_head_forward(None, 0, None, 64, 256, None, None, None, None, None, None) == 0      # nothing to do
 
 
 def test_constructor_matches_reference_contract():

@@ -20,7 +20,7 @@ TPN_ERR_UNSUPPORTED = -5
 TPN_ERR_INDEX = -6
 STAGE_RAW, STAGE_ID_WRAP, STAGE_ID = 0, 1, 2
 TPN_MAX_LAYERS = 4
-ABI_VERSION = 8
+ABI_VERSION = 10
 
 #: every symbol include/tpnet_b200.h declares (tests assert the .so exports all of them)
 EXPORTED_SYMBOLS = (
@@ -30,7 +30,11 @@ EXPORTED_SYMBOLS = (
     'tpn_stager_create', 'tpn_stager_destroy', 'tpn_stage',
     'tpn_update_messages', 'tpn_gather_blocks', 'tpn_set_debug_flags', 'tpn_pairwise_neighbors', 'tpn_head_forward',
     'tpn_planner_create', 'tpn_planner_destroy', 'tpn_plan', 'tpn_sampler_recent',
+    'tpn_route_workspace_bytes', 'tpn_route_update', 'tpn_route_pairs', 'tpn_pull_rows', 'tpn_peer_barrier',
+    'tpn_shard_new_generation', 'tpn_peer_alloc', 'tpn_peer_free', 'tpn_ipc_export', 'tpn_ipc_open', 'tpn_ipc_close',
 )
+
+SHARD_CTR_NEED, SHARD_CTR_PREV, SHARD_CTR_ERROR, SHARD_COUNTERS = 0, 1, 2, 8
 
 
 class TpnState(ctypes.Structure):
@@ -48,6 +52,26 @@ class TpnState(ctypes.Structure):
         ('epoch', c_int64),
         ('cum_floor', c_double),
         ('err_flag', c_void_p),
+        ('giant_chunk', c_int32),
+        ('reserved0', c_int32),
+    ]
+
+
+class TpnShard(ctypes.Structure):
+    """Mirror of ``tpn_shard_t`` (include/tpnet_b200.h)."""
+    _fields_ = [
+        ('world', c_int32),
+        ('rank', c_int32),
+        ('global_nodes', c_int64),
+        ('num_local_rows', c_int64),
+        ('ext_rows', c_int64),
+        ('peer_data', c_void_p),
+        ('peer_stamps', c_void_p),
+        ('peer_flags', c_void_p),
+        ('mark', c_void_p),
+        ('counters', c_void_p),
+        ('need_nodes', c_void_p),
+        ('barrier_seq', c_void_p),
     ]
 
 
@@ -75,19 +99,19 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.tpn_update.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_double, c_float,
                                POINTER(c_float), c_void_p, c_size_t, c_void_p, c_void_p]
     lib.tpn_update_messages.restype = c_int
-    lib.tpn_update_messages.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,
-                                        c_float, POINTER(c_float), c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.tpn_update_messages.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                        c_double, c_float, POINTER(c_float), c_void_p, c_size_t, c_void_p, c_void_p]
     lib.tpn_set_debug_flags.restype = c_int
     lib.tpn_set_debug_flags.argtypes = [c_int]
     lib.tpn_gather_blocks.restype = c_int
     lib.tpn_gather_blocks.argtypes = [POINTER(TpnState), c_void_p, c_int64, c_void_p, c_void_p]
     lib.tpn_pairwise.restype = c_int
-    lib.tpn_pairwise.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]
+    lib.tpn_pairwise.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]
     lib.tpn_pairwise_neighbors.restype = c_int
     lib.tpn_pairwise_neighbors.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                            c_void_p, c_void_p]
     lib.tpn_head_forward.restype = c_int
-    lib.tpn_head_forward.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+    lib.tpn_head_forward.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p]
     lib.tpn_gather.restype = c_int
     lib.tpn_gather.argtypes = [POINTER(TpnState), c_void_p, c_int64, c_void_p, c_void_p]
@@ -105,6 +129,30 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.tpn_plan.restype = c_int
     lib.tpn_plan.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                              POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, c_void_p]
+    lib.tpn_route_workspace_bytes.restype = c_size_t
+    lib.tpn_route_workspace_bytes.argtypes = [c_int64]
+    lib.tpn_route_update.restype = c_int
+    lib.tpn_route_update.argtypes = [POINTER(TpnShard), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.tpn_route_pairs.restype = c_int
+    lib.tpn_route_pairs.argtypes = [POINTER(TpnShard), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.tpn_pull_rows.restype = c_int
+    lib.tpn_pull_rows.argtypes = [POINTER(TpnState), POINTER(TpnShard), c_void_p]
+    lib.tpn_peer_barrier.restype = c_int
+    lib.tpn_peer_barrier.argtypes = [POINTER(TpnShard), c_void_p]
+    lib.tpn_shard_new_generation.restype = c_int
+    lib.tpn_shard_new_generation.argtypes = [POINTER(TpnShard), c_void_p]
+    lib.tpn_peer_alloc.restype = c_int
+    lib.tpn_peer_alloc.argtypes = [POINTER(c_void_p), c_size_t]
+    lib.tpn_peer_free.restype = c_int
+    lib.tpn_peer_free.argtypes = [c_void_p]
+    lib.tpn_ipc_export.restype = c_int
+    lib.tpn_ipc_export.argtypes = [c_void_p, c_void_p]
+    lib.tpn_ipc_open.restype = c_int
+    lib.tpn_ipc_open.argtypes = [c_void_p, POINTER(c_void_p)]
+    lib.tpn_ipc_close.restype = c_int
+    lib.tpn_ipc_close.argtypes = [c_void_p]
     lib.tpn_stager_create.restype = c_int
     lib.tpn_stager_create.argtypes = [POINTER(c_void_p), c_size_t, c_int]
     lib.tpn_stager_destroy.restype = None

@@ -56,7 +56,8 @@ __device__ __forceinline__ void tile_fma(float2 (&acc)[8][4], const float (&a)[8
 __global__ void __launch_bounds__(kHeadThreads, 1)
 head_forward_kernel(const float* __restrict__ x, long long n, const float* __restrict__ w1,
                     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                    float* __restrict__ y) {
+                    float* __restrict__ y, const int* __restrict__ n_dev) {
+    if (n_dev != nullptr) n = min(n, (long long)max(*n_dev, 0));      // routed calls: the count lives on the device
     extern __shared__ __align__(16) unsigned char head_raw[];
     HeadSmem& sm = *reinterpret_cast<HeadSmem*>(head_raw);
     const int tid = threadIdx.x;
@@ -187,7 +188,7 @@ head_forward_kernel(const float* __restrict__ x, long long n, const float* __res
 }  // namespace
 }  // namespace tpn
 
-extern "C" int tpn_head_forward(const float* x_dev, int64_t n, int features, int hidden, const float* w1_dev,
+extern "C" int tpn_head_forward(const float* x_dev, int64_t n, const int32_t* n_dev, int features, int hidden, const float* w1_dev,
                                 const float* b1_dev, const float* w2_dev, const float* b2_dev, float* y_dev,
                                 void* stream_v) {
     using namespace tpn;
@@ -213,6 +214,6 @@ extern "C" int tpn_head_forward(const float* x_dev, int64_t n, int features, int
     const long long ntiles = (n + kHeadTile - 1) / kHeadTile;
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
     head_forward_kernel<<<grid, kHeadThreads, smem, reinterpret_cast<cudaStream_t>(stream_v)>>>(
-        x_dev, n, w1_dev, b1_dev, w2_dev, b2_dev, y_dev);
+        x_dev, n, w1_dev, b1_dev, w2_dev, b2_dev, y_dev, reinterpret_cast<const int*>(n_dev));
     return check_launch();
 }

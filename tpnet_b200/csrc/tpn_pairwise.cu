@@ -30,7 +30,11 @@ thread_local int g_dev_slot = 0;      // device of the call in progress (set by 
 template <int LAYERS, int G, bool LAZY>
 __global__ void __launch_bounds__(kPairThreads)
 pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long long* __restrict__ b_ids,
-                long long n, int apply_log_scale, float* __restrict__ out, int ds4) {
+                long long n, int apply_log_scale, float* __restrict__ out, int ds4, const int* __restrict__ n_dev) {
+    if (n_dev != nullptr) {                // routed calls: the count lives on the device
+        if (*n_dev > n && st.err != nullptr) *st.err = 4;       // more pairs than the call was sized for
+        n = min(n, (long long)max(*n_dev, 0));
+    }
     constexpr int H = LAYERS + 1;          // rows per endpoint
     constexpr int R = 2 * H;               // rows per pair
     constexpr int F = R * R;               // outputs per pair
@@ -115,7 +119,11 @@ pairwise_kernel(StateView st, const long long* __restrict__ a_ids, const long lo
 template <int LAYERS, bool LAZY>
 __global__ void __launch_bounds__(kPairThreads)
 pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const long long* __restrict__ b_ids,
-                    long long n, int apply_log_scale, float* __restrict__ out, int ds4) {
+                    long long n, int apply_log_scale, float* __restrict__ out, int ds4, const int* __restrict__ n_dev) {
+    if (n_dev != nullptr) {
+        if (*n_dev > n && st.err != nullptr) *st.err = 4;
+        n = min(n, (long long)max(*n_dev, 0));
+    }
     constexpr int G = 8;
     constexpr int H = LAYERS + 1;
     constexpr int R = 2 * H;
@@ -222,7 +230,7 @@ pairwise_tma_kernel(StateView st, const long long* __restrict__ a_ids, const lon
 }
 
 template <int LAYERS>
-bool launch_tma(const StateView& v, const long long* a, const long long* b, long long n, int scale, float* out,
+bool launch_tma(const StateView& v, const long long* a, const long long* b, long long n, const int* n_dev, int scale, float* out,
                 cudaStream_t s) {
     constexpr int R = 2 * (LAYERS + 1);
     const size_t block_bytes = (size_t)(LAYERS + 1) * v.row_stride * 4;
@@ -243,31 +251,31 @@ bool launch_tma(const StateView& v, const long long* a, const long long* b, long
         configured[lazy ? 1 : 0] = true;
     }
     const unsigned grid = (unsigned)((n + 15) / 16);
-    kernel<<<grid, kPairThreads, smem, s>>>(v, a, b, n, scale, out, (int)(v.row_stride / 4));
+    kernel<<<grid, kPairThreads, smem, s>>>(v, a, b, n, scale, out, (int)(v.row_stride / 4), n_dev);
     return true;
 }
 
 template <int LAYERS, int G>
-void launch_g(const StateView& v, const long long* a, const long long* b, long long n, int scale, float* out,
+void launch_g(const StateView& v, const long long* a, const long long* b, long long n, const int* n_dev, int scale, float* out,
               cudaStream_t s) {
     constexpr int pairs_per_block = kPairThreads / G;
     const unsigned grid = (unsigned)((n + pairs_per_block - 1) / pairs_per_block);
     const int ds4 = (int)(v.row_stride / 4);
     if (v.stamps != nullptr)
-        pairwise_kernel<LAYERS, G, true><<<grid, kPairThreads, 0, s>>>(v, a, b, n, scale, out, ds4);
+        pairwise_kernel<LAYERS, G, true><<<grid, kPairThreads, 0, s>>>(v, a, b, n, scale, out, ds4, n_dev);
     else
-        pairwise_kernel<LAYERS, G, false><<<grid, kPairThreads, 0, s>>>(v, a, b, n, scale, out, ds4);
+        pairwise_kernel<LAYERS, G, false><<<grid, kPairThreads, 0, s>>>(v, a, b, n, scale, out, ds4, n_dev);
 }
 
 template <int LAYERS>
-void launch(const StateView& v, const long long* a, const long long* b, long long n, int scale, float* out,
+void launch(const StateView& v, const long long* a, const long long* b, long long n, const int* n_dev, int scale, float* out,
             cudaStream_t s) {
     // few pairs (decoder calls): one warp per pair fills more SMs and needs fewer
     // dependent round trips per pair; many pairs: 8 lanes per pair wastes no lanes on d ~ 140
     if (n <= 4096) {
-        launch_g<LAYERS, 32>(v, a, b, n, scale, out, s);
-    } else if (!launch_tma<LAYERS>(v, a, b, n, scale, out, s)) {
-        launch_g<LAYERS, 8>(v, a, b, n, scale, out, s);          // rows too wide for the shared-memory staging
+        launch_g<LAYERS, 32>(v, a, b, n, n_dev, scale, out, s);
+    } else if (!launch_tma<LAYERS>(v, a, b, n, n_dev, scale, out, s)) {
+        launch_g<LAYERS, 8>(v, a, b, n, n_dev, scale, out, s);          // rows too wide for the shared-memory staging
     }
 }
 
@@ -275,7 +283,7 @@ void launch(const StateView& v, const long long* a, const long long* b, long lon
 }  // namespace tpn
 
 extern "C" int tpn_pairwise(const tpn_state_t* st, const int64_t* a_ids_dev, const int64_t* b_ids_dev, int64_t n,
-                            int apply_log_scale, float* out_dev, void* stream_v) {
+                            const int32_t* n_dev, int apply_log_scale, float* out_dev, void* stream_v) {
     using namespace tpn;
     int rc = validate_state(st);
     if (rc != TPN_OK) return rc;
@@ -290,11 +298,12 @@ extern "C" int tpn_pairwise(const tpn_state_t* st, const int64_t* a_ids_dev, con
     const StateView v = make_view(st);
     const long long* a = reinterpret_cast<const long long*>(a_ids_dev);
     const long long* b = reinterpret_cast<const long long*>(b_ids_dev);
+    const int* nd = reinterpret_cast<const int*>(n_dev);
     switch (st->num_layer) {
-        case 1: launch<1>(v, a, b, n, apply_log_scale, out_dev, stream); break;
-        case 2: launch<2>(v, a, b, n, apply_log_scale, out_dev, stream); break;
-        case 3: launch<3>(v, a, b, n, apply_log_scale, out_dev, stream); break;
-        case 4: launch<4>(v, a, b, n, apply_log_scale, out_dev, stream); break;
+        case 1: launch<1>(v, a, b, n, nd, apply_log_scale, out_dev, stream); break;
+        case 2: launch<2>(v, a, b, n, nd, apply_log_scale, out_dev, stream); break;
+        case 3: launch<3>(v, a, b, n, nd, apply_log_scale, out_dev, stream); break;
+        case 4: launch<4>(v, a, b, n, nd, apply_log_scale, out_dev, stream); break;
         default: return TPN_ERR_UNSUPPORTED;
     }
     return check_launch();

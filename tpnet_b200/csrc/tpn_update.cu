@@ -85,6 +85,19 @@ struct DecayArgs {
     int has_decay;
 };
 
+// Number of messages of a call: known on the host (dev == nullptr: `cap` is the count), or produced on the
+// device by the routing kernels of a sharded state (tpn_route.cu) and only bounded by `cap` on the host — grids
+// are then sized for `cap` and every kernel reads the real count, so no launch depends on a device -> host copy.
+struct Count {
+    int cap;
+    const int* dev;
+    __device__ __forceinline__ int get() const {
+        if (dev == nullptr) return cap;
+        const int v = *dev;
+        return v < 0 ? 0 : (v > cap ? cap : v);
+    }
+};
+
 // Snapshot-slot encoding (sslot): sorted position of the head of the source node's own segment, or
 // kDirect: the source is not a target of this call, so its rows are not written by it and are
 // read straight from the state (received rows of a sharded state; never happens in edge mode).
@@ -370,7 +383,7 @@ prep_small_kernel(MsgSource msgs, int E, float t_last_f, float neg_lambda, long 
 // ---------------------------------------------------------------- large path
 struct PrepArgs {
     MsgSource msgs;
-    int E;
+    Count count;
     float t_last_f, neg_lambda;
     long long num_nodes;
     float* w;
@@ -390,13 +403,16 @@ __device__ __forceinline__ void prep_body(const PrepArgs& a, int m) {
             a.decay_log[a.new_epoch * a.L + l] = a.decay_log[(a.new_epoch - 1) * a.L + l] * (double)a.decay.c[l];
     }
     if (m < kCtrSlots) a.ctr[m] = 0;                     // hub lists, work counters and SM claims of this call
-    if (m >= a.E) return;
+    // a device-side count above the capacity this call was sized for: the excess is dropped, and flagged
+    if (m == 0 && a.count.dev != nullptr && *a.count.dev > a.count.cap && a.err_flag != nullptr) *a.err_flag = 4;
+    const int E = a.count.get();
+    if (m >= E) return;
     long long tgt, oth;
     int widx;
     a.msgs.get(m, tgt, oth, widx);
     const bool ok = tgt >= 0 && tgt < a.num_nodes && oth >= 0 && oth < a.num_nodes;
     if (!ok && a.err_flag != nullptr) *a.err_flag = 1;
-    const int n_w = a.msgs.B > 0 ? (int)a.msgs.B : a.E;
+    const int n_w = a.msgs.B > 0 ? (int)a.msgs.B : E;
     if (m < n_w) a.w[m] = edge_weight(a.msgs.t[m], a.t_last_f, a.neg_lambda);
     a.key[m] = ok ? (uint32_t)tgt : (uint32_t)a.num_nodes;
     a.val[m] = (uint32_t)m;
@@ -422,8 +438,10 @@ __device__ __forceinline__ void hist_tile(uint32_t* bins, const uint32_t* __rest
 }
 
 __global__ void __launch_bounds__(kRadixThreads)
-radix_hist_kernel(const uint32_t* __restrict__ key, int E, int shift, uint32_t* __restrict__ hist, int nblk) {
+radix_hist_kernel(const uint32_t* __restrict__ key, Count count, int shift, uint32_t* __restrict__ hist) {
     __shared__ uint32_t bins[kRadixBins];
+    const int E = count.get();
+    if ((int)blockIdx.x * kRadixTile >= E) return;       // device-side count: tiles past the end do nothing
     hist_tile(bins, key, E, shift, hist, blockIdx.x);
 }
 
@@ -446,7 +464,8 @@ __device__ __forceinline__ void prefix_digit(uint32_t* __restrict__ hist, int nb
     if (lane == 0) hist[nblk * kRadixBins + dgt] = carry;
 }
 
-__global__ void __launch_bounds__(256) radix_prefix_kernel(uint32_t* __restrict__ hist, int nblk) {
+__global__ void __launch_bounds__(256) radix_prefix_kernel(uint32_t* __restrict__ hist, Count count) {
+    const int nblk = (count.get() + kRadixTile - 1) / kRadixTile;
     prefix_digit(hist, nblk, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
@@ -541,9 +560,12 @@ __device__ __forceinline__ void scatter_tile(ScatterSmem& sm, const uint32_t* __
 
 __global__ void __launch_bounds__(kRadixThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
-                     uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, int E, int shift,
-                     const uint32_t* __restrict__ offs, int nblk, int prefixed) {
+                     uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, Count count, int shift,
+                     const uint32_t* __restrict__ offs, int prefixed) {
     __shared__ ScatterSmem sm;
+    const int E = count.get();
+    if ((int)blockIdx.x * kRadixTile >= E) return;
+    const int nblk = (E + kRadixTile - 1) / kRadixTile;
     scatter_tile(sm, kin, vin, kout, vout, E, shift, offs, nblk, prefixed, blockIdx.x);
 }
 
@@ -553,7 +575,7 @@ struct PayloadArgs {
     uint32_t* key_out;         // != skey: the sorted targets are also copied here (odd number of passes)
     MsgSource msgs;
     const float* w;
-    int E;
+    Count count;
     uint32_t* ssrc;
     float* sw;
     uint32_t* sslot;
@@ -579,7 +601,7 @@ __device__ __forceinline__ void payload_body(const PayloadArgs& a, int p) {
     const uint32_t* __restrict__ skey = a.skey;
     const MsgSource& msgs = a.msgs;
     const float* __restrict__ w = a.w;
-    const int E = a.E;
+    const int E = a.count.get();
     uint32_t* __restrict__ ssrc = a.ssrc;
     float* __restrict__ sw = a.sw;
     uint32_t* __restrict__ sslot = a.sslot;
@@ -732,10 +754,10 @@ template <int V, int D, bool LAZY, bool ALL>
 __global__ void __launch_bounds__(kWalkThreads)
 walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ssrc,
             const float* __restrict__ sw, const uint32_t* __restrict__ sslot, const uint32_t* __restrict__ slen,
-            const float* __restrict__ snap, int E, int ds4, int write_stamp, int hub_min, DecayArgs dnow) {
+            const float* __restrict__ snap, Count count, int ds4, int write_stamp, int hub_min, DecayArgs dnow) {
     const int wid = (blockIdx.x * kWalkThreads + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (wid >= E) return;
+    if (wid >= count.get()) return;
     const uint32_t key = skey[wid];
     const uint32_t prev = wid > 0 ? skey[wid - 1] : 0xffffffffu;
     const int len = (int)slen[wid];
@@ -795,9 +817,14 @@ walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const ui
                         if (ALL) {
                             val = (c < ds4 || direct) ? ld4(sstate + 4 * (long long)c)
                                                       : ld4(ssnap + 4 * (long long)(c - ds4));
-                            // received rows are current as of the epoch before this call: apply
-                            // this call's decay (lazy mode; the eager sweep already covered them)
-                            if (LAZY && direct && c >= ds4 && dnow.has_decay) scale4(val, dnow.c[c / ds4 - 1]);
+                            // cached rows of other ranks carry their own stamps, like any row (lazy mode;
+                            // in eager mode the sweep already covered them): one multiply from the stamp
+                            // to this call's epoch, exactly what the snapshot does for local sources
+                            if (LAZY && direct && c >= ds4) {
+                                const int sli = c / ds4 - 1;
+                                const int sst = st.stamps[(long long)v * L + sli];
+                                if (sst >= 0) scale4(val, decay_factor(st, sli, sst));
+                            }
                         }
                         else if (vstamp[j] >= 0) val = ld4(sstate + 4 * (long long)c);
                     }
@@ -830,10 +857,10 @@ walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const ui
 // one warp per segment head; slot = sorted position of the head.
 template <bool LAZY>
 __global__ void __launch_bounds__(256)
-snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, int E, int ds4, float* __restrict__ snap) {
+snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, Count count, int ds4, float* __restrict__ snap) {
     const int p = (blockIdx.x * 256 + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (p >= E) return;
+    if (p >= count.get()) return;
     const uint32_t key = skey[p];
     if ((long long)key >= st.num_nodes) return;
     if (p > 0 && skey[p - 1] == key) return;
@@ -875,9 +902,9 @@ snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, int E, int ds4,
 
 // stamps of all layers (layer == 0) or one layer of every target <- current epoch
 __global__ void __launch_bounds__(256)
-stamp_targets_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, int E) {
+stamp_targets_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, Count count) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= E) return;
+    if (p >= count.get()) return;
     const uint32_t key = skey[p];
     if ((long long)key >= st.num_nodes) return;
     if (p > 0 && skey[p - 1] == key) return;
@@ -1172,6 +1199,19 @@ walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_
                     const bool direct = DIRECT && (slot & kDirect) != 0;
                     if (DIRECT) wj = fabsf(wj);
                     w[j] = wj;
+                    // cached rows of other ranks (sharded state) carry their own stamps: lane l computes the pending
+                    // factor of source row l + 1 (stamp -> this call's epoch, one multiply as in the snapshot)
+                    float fd1 = 1.0f, fd2 = 1.0f, fd3 = 1.0f;
+                    if (DIRECT && LAZY) {
+                        float fm = 1.0f;
+                        if (direct && jj < nmsg && lane < L - 1) {
+                            const int sst = st.stamps[(long long)v * L + lane];
+                            if (sst >= 0) fm = decay_factor(st, lane, sst);
+                        }
+                        fd1 = __shfl_sync(0xffffffffu, fm, 0);
+                        fd2 = __shfl_sync(0xffffffffu, fm, 1);
+                        fd3 = __shfl_sync(0xffffffffu, fm, 2);
+                    }
                     const float* sstate = st.data + (long long)v * st.node_stride;
                     const float* ssnap = snap + (long long)(slot & ~kDirect) * snap4 * 4;
 #pragma unroll
@@ -1180,9 +1220,8 @@ walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_
                         if (jj < nmsg && in[k]) {
                             val = (col[k] < ds4 || direct) ? ld4(sstate + 4 * (long long)col[k])
                                                            : ld4(ssnap + 4 * (long long)(col[k] - ds4));
-                            // received rows are current as of the epoch before this call
-                            if (DIRECT && LAZY && direct && col[k] >= ds4 && dnow.has_decay)
-                                scale4(val, pick4(dnow.c[0], dnow.c[1], dnow.c[2], dnow.c[3], tl[k] - 1));
+                            if (DIRECT && LAZY && direct && col[k] >= ds4)
+                                scale4(val, pick4(fd1, fd2, fd3, 1.0f, tl[k] - 1));      // x * 1.0f is exact
                         }
                         x[j][k] = val;
                     }
@@ -1330,9 +1369,6 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                 const int nvec = width >> 2;            // 16-byte pieces per message (<= 4 giant, <= 16 otherwise)
                 const int lpm_shift = giant ? kGiantLs : 4;    // lanes per message: 4 (8) or 16
                 const int grp = lane >> lpm_shift, sub = lane & ((1 << lpm_shift) - 1);
-                // received source rows (sharded state): this call's decay of source row r (P_0 never decays)
-                const float dfac = (DIRECT && LAZY && dnow.has_decay && r >= 1)
-                                       ? pick4(dnow.c[0], dnow.c[1], dnow.c[2], dnow.c[3], r - 1) : 1.0f;
                 const int mpi = 32 >> lpm_shift;              // messages per load instruction: 8 (giant) or 2
                 auto row_ptr = [&](uint32_t v, uint32_t x) -> const float* {
                     if (DIRECT && (x & kDirect) != 0)         // received row: rows 0..L-1 contiguous in the state
@@ -1360,8 +1396,12 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                             const uint32_t v = ssrc[head + j];
                             const uint32_t x = (r >= 1 || DIRECT) ? sslot[head + j] : 0u;
                             float w = sw[head + j];
-                            if (DIRECT) {                     // sign bit of the weight = "received row"
-                                fl[sb] = __float_as_int(w) < 0 ? dfac : 1.0f;
+                            if (DIRECT) {                     // sign bit of the weight = "cached row of another rank"
+                                if (LAZY && r >= 1 && __float_as_int(w) < 0) {
+                                    // it carries its own stamp: stamp -> this call's epoch in one multiply
+                                    const int sst = st.stamps[(long long)v * L + (r - 1)];
+                                    if (sst >= 0) fl[sb] = decay_factor(st, r - 1, sst);
+                                }
                                 w = fabsf(w);
                             }
                             wl[sb] = w;
@@ -1654,9 +1694,9 @@ int launch_walk_hub(const StateView& v, int layer, const Workspace& ws, int E4, 
 }
 
 template <int V, int D, bool ALL>
-void launch_walk(const StateView& v, int layer, const Workspace& ws, int E, int ds4, int tiles, bool lazy,
+void launch_walk(const StateView& v, int layer, const Workspace& ws, Count E, int ds4, int tiles, bool lazy,
                  bool hubs, const DecayArgs& dnow, cudaStream_t stream) {
-    dim3 grid((unsigned)(((long long)E * 32 + kWalkThreads - 1) / kWalkThreads), (unsigned)tiles);
+    dim3 grid((unsigned)(((long long)E.cap * 32 + kWalkThreads - 1) / kWalkThreads), (unsigned)tiles);
     const int write_stamp = (!ALL && tiles == 1 && !hubs) ? 1 : 0;
     const int hub_min = hubs ? kHubMin : 0x7fffffff;
     if (lazy)
@@ -1680,8 +1720,11 @@ extern "C" size_t tpn_update_workspace_bytes(const tpn_state_t* st, int64_t batc
 namespace tpn {
 namespace {
 
-int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch, double t_last, float neg_lambda,
-                const float* decay, void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, cudaStream_t stream) {
+int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* count_dev, int64_t ws_batch, double t_last,
+                float neg_lambda, const float* decay, void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev,
+                cudaStream_t stream) {
+    // E is the number of messages, or — count_dev != nullptr, routed calls of a sharded state — its upper bound
+    const Count cnt{E, reinterpret_cast<const int*>(count_dev)};
     Workspace ws = carve(ws_dev, ws_batch, st->num_layer, st->row_stride);
     if (ws.bytes > ws_bytes) return TPN_ERR_WORKSPACE_TOO_SMALL;
     const bool lazy = st->stamps != nullptr;
@@ -1718,8 +1761,9 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
     // also a target, so every source has a snapshot slot.  Message mode (sharded): sources that
     // are not targets of this call (received rows) are read straight from the state (kDirect).
     const bool force_per_layer = (g_debug_flags & TPN_DEBUG_PER_LAYER_WALK) != 0;      // test hook
-    const bool snapshot_path = ws.has_snap && !(force_per_layer && E > kSmallMaxMsgs);
-    const bool hubs = E > kSmallMaxMsgs;            // the single-CTA sort path keeps everything in the warp walker
+    const bool snapshot_path = ws.has_snap && !(force_per_layer && !(count_dev == nullptr && E <= kSmallMaxMsgs));
+    const bool small_path = count_dev == nullptr && E <= kSmallMaxMsgs;
+    const bool hubs = !small_path;                  // the single-CTA sort path keeps everything in the warp walker
     const int E4 = (E + 3) & ~3;                    // layer stride of svst (keeps bulk copies 16-byte aligned)
     const bool eager_sweep = !lazy && dargs.has_decay;
     // chunked accumulation order of giant segments (snapshot path only; 0 = the reference's sequential order)
@@ -1733,7 +1777,7 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
     StateView view = make_view(st);
     view.epoch = new_epoch;
 
-    if (E <= kSmallMaxMsgs) {
+    if (small_path) {
         SweepArgs sw_args;
         sw_args.total4 = eager_sweep ? sweep_total4 : 0;
         sw_args.ds4 = ds4;
@@ -1753,7 +1797,7 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
         const int nblk = (E + kRadixTile - 1) / kRadixTile;
         struct { PrepArgs prep; PayloadArgs pay; } fa;
         fa.prep.msgs = msgs;
-        fa.prep.E = E;
+        fa.prep.count = cnt;
         fa.prep.t_last_f = t_last_f;
         fa.prep.neg_lambda = neg_lambda;
         fa.prep.num_nodes = st->num_nodes;
@@ -1771,7 +1815,7 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
         fa.pay.key_out = ws.key_a;
         fa.pay.msgs = msgs;
         fa.pay.w = ws.w;
-        fa.pay.E = E;
+        fa.pay.count = cnt;
         fa.pay.ssrc = ws.ssrc;
         fa.pay.sw = ws.sw;
         fa.pay.sslot = snapshot_path ? ws.sslot : nullptr;
@@ -1791,13 +1835,15 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
         fa.pay.giant_cbase = ws.giant_cbase;
         fa.pay.chunk = (snapshot_path && hubs) ? chunk : 0;
         {
-            prep_large_kernel<<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(fa.prep);
+            // >= 2 blocks: the first kCtrSlots threads also zero the per-call counters
+            prep_large_kernel<<<(unsigned)((E + 255) / 256 < 2 ? 2 : (E + 255) / 256), 256, 0, stream>>>(fa.prep);
             uint32_t *kin = ws.key_a, *kout = ws.key_b, *vin = ws.val_a, *vout = ws.val_b;
             for (int p = 0; p < passes; ++p) {
-                radix_hist_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, E, 8 * p, ws.hist, nblk);
-                const int prefixed = nblk > kRadixDirectBlocks ? 1 : 0;      // few tiles: the scatter sums the columns itself
-                if (prefixed) radix_prefix_kernel<<<kRadixBins / 8, 256, 0, stream>>>(ws.hist, nblk);
-                radix_scatter_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, vin, kout, vout, E, 8 * p, ws.hist, nblk,
+                radix_hist_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, cnt, 8 * p, ws.hist);
+                // few tiles: the scatter sums the columns itself (a device-side count always takes the prefix kernel)
+                const int prefixed = (nblk > kRadixDirectBlocks || count_dev != nullptr) ? 1 : 0;
+                if (prefixed) radix_prefix_kernel<<<kRadixBins / 8, 256, 0, stream>>>(ws.hist, cnt);
+                radix_scatter_kernel<<<nblk, kRadixThreads, 0, stream>>>(kin, vin, kout, vout, cnt, 8 * p, ws.hist,
                                                                          prefixed);
                 uint32_t* tk = kin; kin = kout; kout = tk;
                 uint32_t* tv = vin; vin = vout; vout = tv;
@@ -1818,8 +1864,8 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
     if (snapshot_path) {
         if (L >= 2) {
             const unsigned grid = (unsigned)(((long long)E * 32 + 255) / 256);
-            if (lazy) snapshot_kernel<true><<<grid, 256, 0, stream>>>(view, ws.key_a, E, ds4, ws.snap);
-            else snapshot_kernel<false><<<grid, 256, 0, stream>>>(view, ws.key_a, E, ds4, ws.snap);
+            if (lazy) snapshot_kernel<true><<<grid, 256, 0, stream>>>(view, ws.key_a, cnt, ds4, ws.snap);
+            else snapshot_kernel<false><<<grid, 256, 0, stream>>>(view, ws.key_a, cnt, ds4, ws.snap);
         }
         if (hubs) {
             // large batch: long segments on the CTA-pipelined hub walker, short ones on the
@@ -1849,9 +1895,9 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
         } else {
             // single-CTA sort path: one float4 per lane, a warp covers 512 contiguous bytes of the span
             const int span4 = L * ds4;
-            launch_walk<1, 16, true>(view, 0, ws, E, ds4, (span4 + 31) / 32, lazy, false, dargs, stream);
+            launch_walk<1, 16, true>(view, 0, ws, cnt, ds4, (span4 + 31) / 32, lazy, false, dargs, stream);
         }
-        if (lazy) stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, 0, ws.key_a, E);
+        if (lazy) stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, 0, ws.key_a, cnt);
     } else {
         // per-layer walk: V float4 per lane so that one tile covers rows up to 512 floats
         int vpl = (ds4 + 31) / 32;
@@ -1866,13 +1912,13 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, int64_t ws_batch,
                 if (hrc != TPN_OK) return hrc;
             }
             switch (vpl) {
-                case 1: launch_walk<1, 16, false>(view, layer, ws, E, ds4, tiles, lazy, hubs, dargs, stream); break;
-                case 2: launch_walk<2, 8, false>(view, layer, ws, E, ds4, tiles, lazy, hubs, dargs, stream); break;
-                case 3: launch_walk<3, 4, false>(view, layer, ws, E, ds4, tiles, lazy, hubs, dargs, stream); break;
-                default: launch_walk<4, 4, false>(view, layer, ws, E, ds4, tiles, lazy, hubs, dargs, stream); break;
+                case 1: launch_walk<1, 16, false>(view, layer, ws, cnt, ds4, tiles, lazy, hubs, dargs, stream); break;
+                case 2: launch_walk<2, 8, false>(view, layer, ws, cnt, ds4, tiles, lazy, hubs, dargs, stream); break;
+                case 3: launch_walk<3, 4, false>(view, layer, ws, cnt, ds4, tiles, lazy, hubs, dargs, stream); break;
+                default: launch_walk<4, 4, false>(view, layer, ws, cnt, ds4, tiles, lazy, hubs, dargs, stream); break;
             }
             if (lazy && (tiles > 1 || hubs))
-                stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, layer, ws.key_a, E);
+                stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, layer, ws.key_a, cnt);
         }
     }
     const int lrc = check_launch();
@@ -1918,14 +1964,14 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
     msgs.t = t_dev;
     msgs.B = batch;
     msgs.direct_from = st->num_nodes;
-    return update_impl(st, msgs, (int)(2 * batch), batch, t_last, neg_lambda, decay, ws_dev, ws_bytes, err_flag_dev,
-                       reinterpret_cast<cudaStream_t>(stream_v));
+    return update_impl(st, msgs, (int)(2 * batch), nullptr, batch, t_last, neg_lambda, decay, ws_dev, ws_bytes,
+                       err_flag_dev, reinterpret_cast<cudaStream_t>(stream_v));
 }
 
 extern "C" int tpn_update_messages(tpn_state_t* st, const int64_t* tgt_dev, const int64_t* src_dev,
-                                   const double* t_dev, int64_t num_messages, int64_t num_local_rows,
-                                   double t_last, float neg_lambda, const float* decay, void* ws_dev,
-                                   size_t ws_bytes, int32_t* err_flag_dev, void* stream_v) {
+                                   const double* t_dev, int64_t num_messages, const int32_t* num_messages_dev,
+                                   int64_t num_local_rows, double t_last, float neg_lambda, const float* decay,
+                                   void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, void* stream_v) {
     using namespace tpn;
     int rc = validate_state(st);
     if (rc != TPN_OK) return rc;
@@ -1941,6 +1987,6 @@ extern "C" int tpn_update_messages(tpn_state_t* st, const int64_t* tgt_dev, cons
     msgs.t = t_dev;
     msgs.B = 0;
     msgs.direct_from = num_local_rows;
-    return update_impl(st, msgs, (int)num_messages, (num_messages + 1) / 2, t_last, neg_lambda, decay, ws_dev,
-                       ws_bytes, err_flag_dev, reinterpret_cast<cudaStream_t>(stream_v));
+    return update_impl(st, msgs, (int)num_messages, num_messages_dev, (num_messages + 1) / 2, t_last, neg_lambda,
+                       decay, ws_dev, ws_bytes, err_flag_dev, reinterpret_cast<cudaStream_t>(stream_v));
 }

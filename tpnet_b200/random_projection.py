@@ -105,17 +105,33 @@ class _Host:
 class RandomProjectionModule(nn.Module):
     def __init__(self, node_num: int, edge_num: int, dim_factor: int, num_layer: int, time_decay_weight: float,
                  device: str, use_matrix: bool, beginning_time: np.float64, not_scale: bool, enforce_dim: int,
-                 decay_mode: str = 'auto', init_p0: bool = True, state_device=None):
+                 decay_mode: str = 'auto', init_p0: bool = True, state_device=None,
+                 accumulation: str = 'reference', giant_chunk: int = 1024,
+                 state_buffer: Optional[torch.Tensor] = None):
         """Arguments as the reference constructor (TPNet.py:10-26).  ``decay_mode`` in
         {'auto', 'eager', 'lazy'} selects how the time decay of TPNet.py:83-85 is
         realised; all modes produce the same values.  ``init_p0=False`` leaves P_0 zero for the
         caller to fill and ``state_device`` allocates the packed state directly on a device
-        (both for states too large to stage through host memory)."""
+        (both for states too large to stage through host memory).  ``accumulation`` selects the order
+        in which the messages of ONE target row are added inside an update: ``'reference'`` (default)
+        adds them one at a time in the reference's order (CPU ``scatter_add_``, TPNet.py:93-96), bit for
+        bit; ``'chunked'`` cuts the messages of a row that receives >= 2048 of them in one call into
+        chunks of ``giant_chunk``, sums each chunk in order and adds the chunk sums in order —
+        deterministic, within fp32 rounding of the reference order (include/tpnet_b200.h,
+        ``tpn_state_t::giant_chunk``), and free of the hub's sequential add chain.  ``state_buffer``: a
+        zero-filled float32 tensor ``[node_num, num_layer + 1, row_stride]`` to use as the packed state
+        (the sharded module passes peer-visible memory)."""
         super().__init__()
         if not 1 <= num_layer <= _lib.TPN_MAX_LAYERS:
             raise ValueError(f'num_layer must be in 1..{_lib.TPN_MAX_LAYERS}')
         if decay_mode not in ('auto', 'eager', 'lazy'):
             raise ValueError("decay_mode must be 'auto', 'eager' or 'lazy'")
+        if accumulation not in ('reference', 'chunked'):
+            raise ValueError("accumulation must be 'reference' or 'chunked'")
+        if accumulation == 'chunked' and not (256 <= giant_chunk <= 2048 and giant_chunk % 32 == 0):
+            raise ValueError('giant_chunk must be a multiple of 32 in 256..2048')
+        self.accumulation = accumulation
+        self.giant_chunk = int(giant_chunk)
         self.node_num = node_num
         self.edge_num = edge_num
         if enforce_dim != -1:                                             # TPNet.py:30-33
@@ -137,8 +153,14 @@ class RandomProjectionModule(nn.Module):
         self.decay_mode = decay_mode
 
         # packed node-major state; P_l[u] = _state[u, l, :dim]
-        self._state = torch.zeros(self.node_num, self.num_layer + 1, self.row_stride, dtype=torch.float32,
-                                  device=state_device)
+        if state_buffer is not None:
+            if state_buffer.shape != (self.node_num, self.num_layer + 1, self.row_stride) or \
+                    state_buffer.dtype != torch.float32 or not state_buffer.is_contiguous():
+                raise ValueError('state_buffer must be a contiguous float32 [node_num, num_layer + 1, row_stride] tensor')
+            self._state = state_buffer
+        else:
+            self._state = torch.zeros(self.node_num, self.num_layer + 1, self.row_stride, dtype=torch.float32,
+                                      device=state_device)
         if self.use_matrix:
             self._state[:, 0, :self.dim] = torch.eye(self.node_num)      # TPNet.py:48-49
         elif init_p0:
@@ -277,6 +299,7 @@ class RandomProjectionModule(nn.Module):
             if self._err is None:
                 self._err = torch.zeros(1, dtype=torch.int32, device=self._state.device)
             st.err_flag = self._err.data_ptr()
+            st.giant_chunk = self.giant_chunk if self.accumulation == 'chunked' else 0
             h.st = st
             h.st_ref = ctypes.byref(st)
         st.epoch = h.epoch
@@ -381,17 +404,18 @@ class RandomProjectionModule(nn.Module):
         out = torch.empty(n, self.pair_wise_feature_dim, dtype=torch.float32, device=dev)
         if n:
             ptrs = self._ids_to_device([src_node_ids, dst_node_ids], ['id', 'id'])
-            rc = lib.tpn_pairwise(self._c_state(), ptrs[0], ptrs[1], n, 0 if self.not_scale else 1,
+            rc = lib.tpn_pairwise(self._c_state(), ptrs[0], ptrs[1], n, None, 0 if self.not_scale else 1,
                                   out.data_ptr(), self._stream())
             if rc:
                 _lib.check(rc, 'tpn_pairwise')
             self._h.launches += 1
         return out
 
-    def _head(self, gram: torch.Tensor) -> torch.Tensor:
+    def _head(self, gram: torch.Tensor, count: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``self.mlp`` on ``[n, F]`` features (TPNet.py:125/:129).  With autograd on (training) it is
         the PyTorch module; under ``torch.no_grad()`` the default-shape head (F = 64) runs as one
-        fused fp32 kernel (``tpn_head_forward``)."""
+        fused fp32 kernel (``tpn_head_forward``).  ``count``: device int32 with the number of valid rows
+        (routed calls of the sharded module; rows past it are left zero by the fused kernel)."""
         if torch.is_grad_enabled() or not self.fused_head or gram.shape[0] == 0:
             return self.mlp(gram)
         mlp = self.mlp
@@ -405,8 +429,10 @@ class RandomProjectionModule(nn.Module):
               and all(t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.device == gram.device
                       for t in (gram, l1.weight, l1.bias, l2.weight, l2.bias)))
         if ok:
-            out = torch.empty_like(gram)
-            rc = _lib.load().tpn_head_forward(gram.data_ptr(), gram.shape[0], f, hid, l1.weight.data_ptr(),
+            out = torch.empty_like(gram) if count is None else torch.zeros_like(gram)
+            rc = _lib.load().tpn_head_forward(gram.data_ptr(), gram.shape[0],
+                                              None if count is None else count.data_ptr(), f, hid,
+                                              l1.weight.data_ptr(),
                                               l1.bias.data_ptr(), l2.weight.data_ptr(), l2.bias.data_ptr(),
                                               out.data_ptr(), self._stream())
             if rc == _lib.TPN_OK:
@@ -525,6 +551,9 @@ class RandomProjectionModule(nn.Module):
         code = int(self._err.item()) if self._err is not None else 0
         if code != 0:
             self._err.zero_()
+            if code == 4:
+                raise RuntimeError('a routed call of the sharded state owned more items than it was sized for '
+                                   '(raise route_cap_factor); the excess was dropped')
             if code == 2:
                 raise RuntimeError('tpn_update_messages: a local source row was not a target of the same call '
                                    '(lazy decay needs both directions of every edge in the message list)')

@@ -2,22 +2,24 @@
 
 The reference is single-device; this file is the multi-GPU extension `north_star` asks for.
 Rows of node ``u`` live on rank ``u % G`` at local row ``u // G`` (modulo placement balances
-power-law hubs).  The edge batch is replicated on every rank (24 B/edge).  Per call:
+power-law hubs).  The edge batch / pair list is replicated on every rank (24 B/edge).
 
-  1. every rank derives the SAME routing plan from the replicated batch (``ShardPlan``): which
-     messages / pairs it owns (those whose target / first endpoint it owns, in batch order),
-     which of its rows other ranks need, and which remote rows it needs — remote rows are
-     de-duplicated per (owner, node), so a hub row crosses NVLink once per rank and batch;
-  2. senders pack whole node blocks (rows 0..L, brought current) with ``tpn_gather_blocks``;
-  3. ONE ``all_to_all_single`` (NCCL over NVLink/NVSwitch; gloo in the CPU tests) delivers the
-     blocks straight into the extension rows that follow the local rows of the state buffer,
-     so the kernels address local and received rows uniformly;
-  4. the local kernels run: ``tpn_update_messages`` (pre-batch snapshot of the local targets +
-     one all-layer walk launch; received rows are read in place; same per-row accumulation
-     order as a single GPU, hence bit-identical results) or ``tpn_pairwise``.
+Data plane ``exchange='peer'`` (default on CUDA): everything of a call runs on the device, per rank, with
+no host plan and no collective —
+  1. ``tpn_route_update`` / ``tpn_route_pairs``: stable compaction of the items this rank owns (target /
+     first endpoint owned) and a cache slot, in the extension rows behind the local rows, for every remote
+     second endpoint (de-duplicated through a mark table; a slot lives until the next write to the state);
+  2. ``tpn_pull_rows``: the new slots are filled straight out of the owners' HBM over NVLink (every rank's
+     state and stamps are mapped into every other rank with CUDA IPC), stamps included, so a cached row is
+     read exactly like a local row and sharded results equal the single-GPU ones bit for bit;
+  3. ``tpn_peer_barrier`` (flag words in peer memory) where the protocol needs one: after a write before the
+     peers' next pull, and between the pulls of an update and its writes;
+  4. the rank-local kernels with the device-side item count (``tpn_update_messages`` / ``tpn_pairwise``).
+All of it is plain kernel launches on one stream: a whole step can be captured in a CUDA graph.
 
-Only the exchange is a collective; everything else is rank-local.  The plan is computed on
-the host with numpy from the replicated batch (it can be precomputed for a resident batch).
+Data plane ``exchange='nccl'`` (portable; what the gloo CPU tests exercise): the routing plan is computed on
+the host (``make_plan`` / ``tpn_plan``), senders pack whole node blocks (``tpn_gather_blocks``) and ONE
+``all_to_all_single`` delivers them into the extension rows.
 """
 from __future__ import annotations
 
@@ -31,7 +33,8 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .random_projection import RandomProjectionModule
+from .peer import IpcPeerGroup, LocalPeerGroup, PeerBuffer, PeerGroup
+from .random_projection import _DEFAULT_LOG_EPOCHS, RandomProjectionModule, _round_up
 
 
 def owner_of(ids: np.ndarray, world: int) -> np.ndarray:
@@ -155,21 +158,60 @@ def exchange_blocks(send: torch.Tensor, send_counts: Sequence[int], recv: torch.
                            group=group)
 
 
+@dataclass
+class RoutedPairs:
+    """Result of a routed pair-wise call (peer data plane): the pairs this rank owns, padded to the capacity
+    the call was sized for.  ``count`` (device int32[1]) is the number of valid rows; rows past it are zero."""
+    keep: torch.Tensor          # int64 [cap]  position in the batch of the j-th kept pair
+    feat: torch.Tensor          # float32 [cap, F]
+    count: torch.Tensor         # int32 [1]
+
+    def trimmed(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(positions, features) of exactly the owned pairs — one device -> host read of the count."""
+        m = int(self.count.item())
+        if m > self.feat.shape[0]:
+            raise RuntimeError(f'{m} pairs routed to this rank but the call was sized for {self.feat.shape[0]}: '
+                               f'raise route_cap_factor')
+        return self.keep[:m], self.feat[:m]
+
+
 class ShardedRandomProjection(RandomProjectionModule):
     """Rank-local part of the node-sharded state.  Same constructor as the reference class plus
     the process group; ``node_num`` is the GLOBAL node count.  ``update`` and
     ``pair_wise_gram`` take the replicated global-id batch; ``pair_wise_gram`` returns the
-    features of the pairs this rank owns together with their positions in the batch."""
+    features of the pairs this rank owns together with their positions in the batch
+    (``get_pair_wise_feature(..., gather=True)`` re-assembles the reference's ``[n, F]`` tensor on every rank).
+
+    ``exchange``: 'peer' — routing, NVLink pulls and barriers on the device (module docstring; needs the state
+    on CUDA); 'nccl' — host plan + one all_to_all_single; 'auto' — 'peer' when the state is created on a CUDA
+    device (``state_device``), else 'nccl'.  ``peers``: a ``PeerGroup`` (default: ``IpcPeerGroup`` over
+    ``group`` when torch.distributed is initialised; ``LocalPeerGroup`` views put several ranks in one
+    process).  ``route_cap_factor`` bounds the share of a call's items one rank may own (the launches of the
+    rank-local kernels are sized for ``min(1, factor / world)`` of the call; an overflow is flagged, never silent).
+    """
 
     def __init__(self, node_num: int, edge_num: int, dim_factor: int, num_layer: int, time_decay_weight: float,
                  device: str, use_matrix: bool, beginning_time: np.float64, not_scale: bool, enforce_dim: int,
                  decay_mode: str = 'lazy', group=None, ext_rows: int = 1 << 16, p0: str = 'global',
-                 state_device=None):
+                 state_device=None, exchange: str = 'auto', peers: Optional[PeerGroup] = None,
+                 route_cap_factor: float = 3.5, accumulation: str = 'reference', giant_chunk: int = 1024):
         if use_matrix:
             raise ValueError('use_matrix keeps N x N matrices: not meaningful for a sharded state')
+        if exchange not in ('auto', 'peer', 'nccl'):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if peers is not None:
+            self.world, self.rank = int(peers.world), int(peers.rank)
+        else:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        sdev = torch.device(state_device) if state_device is not None else None
+        if exchange == 'auto':
+            exchange = 'peer' if (sdev is not None and sdev.type == 'cuda' and self.world > 1) else 'nccl'
+        if exchange == 'peer' and (sdev is None or sdev.type != 'cuda'):
+            raise ValueError("exchange='peer' needs the state on a CUDA device: pass state_device")
+        self.exchange = exchange
+        self.route_cap_factor = float(route_cap_factor)
         self.global_node_num = int(node_num)
         self.n_local = rows_on_rank(self.global_node_num, self.world, self.rank)
         self.ext_rows = int(ext_rows)
@@ -184,17 +226,43 @@ class ShardedRandomProjection(RandomProjectionModule):
             del full
         else:
             mine = None
+        state_buffer = None
+        self._peer_bufs = {}
+        if exchange == 'peer':
+            # peer-visible state: plain cudaMalloc memory (exportable with CUDA IPC), viewed as a tensor
+            rows = self.n_local + self.ext_rows
+            stride = _round_up(dim, 8)
+            buf = PeerBuffer(rows * (num_layer + 1) * stride * 4, sdev)
+            self._peer_bufs['state'] = buf
+            state_buffer = buf.tensor((rows, num_layer + 1, stride), torch.float32)
         super().__init__(node_num=self.n_local + self.ext_rows, edge_num=edge_num, dim_factor=dim_factor,
                          num_layer=num_layer, time_decay_weight=time_decay_weight, device=device, use_matrix=False,
                          beginning_time=beginning_time, not_scale=not_scale, enforce_dim=dim, decay_mode=decay_mode,
-                         init_p0=False, state_device=state_device)
+                         init_p0=False, state_device=state_device, accumulation=accumulation, giant_chunk=giant_chunk,
+                         state_buffer=state_buffer)
         with torch.no_grad():
             if mine is not None:
                 self.random_projections[0][:self.n_local].copy_(mine)
-        self.exchanged_rows = 0          # rows received so far (bench accounting)
+        self.exchanged_rows = 0          # rows received so far (bench accounting; 'nccl' data plane)
         self._send_buf: Optional[torch.Tensor] = None
         self._all_keep: Optional[np.ndarray] = None
         self._planner: Optional[NativePlanner] = None
+        # ---- peer data plane
+        self._peers = peers
+        self._shard: Optional[_lib.TpnShard] = None
+        self._shard_tensors = {}
+        self._route = {}                 # cached routing buffers, keyed by (kind, items)
+        self._dirty = True               # a rank may have written since the last barrier: barrier before pulling
+        self.barriers = 0                # barriers issued so far (bench accounting)
+        if exchange == 'peer':
+            if self.lazy:
+                # stamps live in peer memory too (a puller copies them with the rows); -1 = never written
+                sb = PeerBuffer(self.node_num * self.num_layer * 4, sdev)
+                self._peer_bufs['stamps'] = sb
+                self._stamps = sb.tensor((self.node_num, self.num_layer), torch.int32)
+                self._stamps.fill_(-1)
+                self._decay_log = torch.ones(_DEFAULT_LOG_EPOCHS, self.num_layer, dtype=torch.float64, device=sdev)
+            self._peer_bufs['flags'] = PeerBuffer(4 * max(self.world, 16), sdev)
 
     # ------------------------------------------------------------------ helpers
     def init_p0_on_device(self, seed: int) -> None:
@@ -235,6 +303,251 @@ class ShardedRandomProjection(RandomProjectionModule):
             self._stamps[self.n_local:self.n_local + R].fill_(self._h.epoch)     # received rows are current
         self.exchanged_rows += R
 
+    # ------------------------------------------------------------------ peer data plane: set-up
+    def connect(self) -> None:
+        """Rendezvous of the peer-visible buffers (collective over the ranks of the group; the first routed call
+        does it if the caller did not).  With a ``LocalPeerGroup`` every rank must be constructed first."""
+        if self.exchange != 'peer' or self._shard is not None:
+            return
+        dev = self._require_cuda()
+        if self._peers is None:
+            if not dist.is_initialized():
+                raise RuntimeError("exchange='peer' with world > 1 needs torch.distributed or a PeerGroup")
+            self._peers = IpcPeerGroup(self.group)
+        tables = {}
+        for name in ('state', 'stamps', 'flags'):
+            if name in self._peer_bufs:
+                ptrs = self._peers.exchange(name, self._peer_bufs[name])
+                tables[name] = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        t = self._shard_tensors
+        t['tables'] = tables
+        t['mark'] = torch.zeros(self.global_node_num, dtype=torch.int32, device=dev)
+        t['counters'] = torch.zeros(_lib.SHARD_COUNTERS, dtype=torch.int32, device=dev)
+        t['need'] = torch.zeros(max(self.ext_rows, 1), dtype=torch.int64, device=dev)
+        t['seq'] = torch.zeros(1, dtype=torch.int32, device=dev)
+        sh = _lib.TpnShard()
+        sh.world, sh.rank = self.world, self.rank
+        sh.global_nodes = self.global_node_num
+        sh.num_local_rows = self.n_local
+        sh.ext_rows = self.ext_rows
+        sh.peer_data = tables['state'].data_ptr()
+        sh.peer_stamps = tables['stamps'].data_ptr() if 'stamps' in tables else None
+        sh.peer_flags = tables['flags'].data_ptr()
+        sh.mark = t['mark'].data_ptr()
+        sh.counters = t['counters'].data_ptr()
+        sh.need_nodes = t['need'].data_ptr()
+        sh.barrier_seq = t['seq'].data_ptr()
+        self._shard = sh
+        self._peers.barrier()            # every rank has mapped every buffer before anyone launches a pull
+
+    def _c_shard(self):
+        if self._shard is None:
+            self.connect()
+        return ctypes.byref(self._shard)
+
+    def _cap(self, items: int) -> int:
+        """Launch capacity for the rank-local kernels of a call with `items` work items in total."""
+        share = min(1.0, self.route_cap_factor / self.world)
+        return int(min(items, math.ceil(items * share) + 1024))
+
+    def _route_buffers(self, kind: str, items: int):
+        key = (kind, items)
+        buf = self._route.get(key)
+        if buf is None:
+            dev = self._state.device
+            lib = _lib.load()
+            buf = dict(first=torch.empty(items, dtype=torch.int64, device=dev),
+                       second=torch.empty(items, dtype=torch.int64, device=dev),
+                       count=torch.zeros(1, dtype=torch.int32, device=dev),
+                       ws=torch.empty(lib.tpn_route_workspace_bytes(items), dtype=torch.uint8, device=dev))
+            if kind == 'update':
+                buf['t'] = torch.empty(items, dtype=torch.float64, device=dev)
+            if len(self._route) > 8:
+                self._route.clear()
+            self._route[key] = buf
+        return buf
+
+    def _barrier(self) -> None:
+        _lib.check(_lib.load().tpn_peer_barrier(self._c_shard(), self._stream()), 'tpn_peer_barrier')
+        self.barriers += 1
+
+    def _pull(self) -> None:
+        """Peers' writes are ordered before this rank's reads of their rows (one barrier after any write), then the
+        cache slots handed out by the latest routing call are filled from the owners' memory."""
+        if self._dirty:
+            self._barrier()
+            self._dirty = False
+        _lib.check(_lib.load().tpn_pull_rows(self._c_state(), self._c_shard(), self._stream()), 'tpn_pull_rows')
+
+    def _state_written(self) -> None:
+        """After any write to the local rows: cached copies held by (and of) other ranks are stale."""
+        self._dirty = True
+        if self._shard is not None:
+            _lib.check(_lib.load().tpn_shard_new_generation(self._c_shard(), self._stream()), 'tpn_shard_new_generation')
+
+    def _update_peer(self, src_node_ids, dst_node_ids, node_interact_times, next_time) -> None:
+        dev = self._require_cuda()
+        lib = _lib.load()
+        n = int(len(src_node_ids))
+        if n == 0:
+            raise IndexError('index -1 is out of bounds for axis 0 with size 0')
+        if len(dst_node_ids) != n or len(node_interact_times) != n:
+            raise ValueError('src, dst and time arrays must have the same length')
+        if next_time is None:
+            last = node_interact_times[-1]
+            next_time = float(last.item()) if isinstance(last, torch.Tensor) else float(last)
+        h = self._h
+        lam = self.time_decay_weight
+        base = np.exp(-lam * (np.float64(next_time) - np.float64(h.now)))
+        factors = (ctypes.c_float * self.num_layer)(*[float(np.float32(np.power(base, i)))
+                                                      for i in range(1, self.num_layer + 1)])
+        ptrs = self._global_ids_to_device([src_node_ids, dst_node_ids, node_interact_times], ['id', 'id', 'time'])
+        st = self._c_state()
+        sh = self._c_shard()
+        stream = self._stream()
+        rb = self._route_buffers('update', 2 * n)
+        rc = lib.tpn_route_update(sh, ptrs[0], ptrs[1], ptrs[2], n, rb['first'].data_ptr(), rb['second'].data_ptr(),
+                                  rb['t'].data_ptr(), rb['count'].data_ptr(), rb['ws'].data_ptr(), rb['ws'].numel(),
+                                  stream)
+        if rc:
+            _lib.check(rc, 'tpn_route_update')
+        self._pull()
+        self._barrier()                       # every rank has pulled its pre-batch rows: now the writes may start
+        cap = self._cap(2 * n)
+        need = lib.tpn_update_workspace_bytes(st, (cap + 1) // 2)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+        args = (rb['first'].data_ptr(), rb['second'].data_ptr(), rb['t'].data_ptr(), cap, rb['count'].data_ptr(),
+                self.n_local, float(next_time), float(np.float32(-lam)), factors, self._ws.data_ptr(),
+                self._ws.numel(), self._err.data_ptr(), stream)
+        rc = lib.tpn_update_messages(st, *args)
+        if rc == _lib.TPN_ERR_LOG_FULL:       # same epoch, same factors on every rank: they all restart together
+            self._restart_log()
+            st = self._c_state()
+            rc = lib.tpn_update_messages(st, *args)
+        if rc:
+            _lib.check(rc, 'tpn_update_messages')
+        h.epoch = int(h.st.epoch)
+        h.launches += 1
+        h.now = float(next_time)
+        self.now_time.data.fill_(h.now)
+        self._state_written()
+
+    #: host arrays at least this long are uploaded in slices (1/world per rank) and all-gathered over NVLink
+    SLICED_UPLOAD_MIN = 32768
+
+    def _sliced_upload(self, arrays, kinds):
+        """The batch is replicated on every rank's HOST; uploading all of it on every rank would move world x the
+        bytes over PCIe.  Rank r stages only elements [r*per, (r+1)*per) of each array (pinned memory, validated
+        on the way) and one all_gather per array over NVLink rebuilds the full arrays on every device."""
+        dev = self._state.device
+        n = int(arrays[0].shape[0])
+        per = (n + self.world - 1) // self.world
+        lo, hi = min(self.rank * per, n), min((self.rank + 1) * per, n)
+        key = ('upload', per, len(arrays))
+        ring = self._route.get(key)
+        if ring is None:
+            ring = dict(cursor=0, slots=[])
+            for _ in range(4):
+                ring['slots'].append(dict(
+                    host=[torch.empty(per, dtype=torch.int64).pin_memory() for _ in arrays],
+                    dev=[torch.empty(per, dtype=torch.int64, device=dev) for _ in arrays],
+                    full=[torch.empty(per * self.world, dtype=torch.int64, device=dev) for _ in arrays],
+                    done=torch.cuda.Event()))
+            self._route[key] = ring
+        slot = ring['slots'][ring['cursor']]
+        ring['cursor'] = (ring['cursor'] + 1) % len(ring['slots'])
+        slot['done'].synchronize()                       # the copies out of this slot's pinned memory have left
+        bad = False
+        for a, kind, h, d in zip(arrays, kinds, slot['host'], slot['dev']):
+            want = np.int64 if kind == 'id' else np.float64
+            part = np.ascontiguousarray(a[lo:hi], dtype=want)
+            if kind == 'id' and part.size and (part.min() < 0 or part.max() >= self.global_node_num):
+                bad = True
+            h.numpy().view(want)[:hi - lo] = part
+            d.copy_(h, non_blocking=True)
+        slot['done'].record()
+        out = []
+        for d, f in zip(slot['dev'], slot['full']):
+            dist.all_gather_into_tensor(f, d, group=self.group)
+            out.append(f.data_ptr())
+        self._h.keepalive = slot
+        if bad:                                          # after the collectives: the other ranks are not left waiting
+            raise IndexError(f'index out of range for node_num {self.global_node_num}')
+        return out
+
+    def _global_ids_to_device(self, arrays, kinds):
+        """Like _ids_to_device, for GLOBAL ids: host arrays are range-checked against the global node count."""
+        if (self.exchange == 'peer' and self.world > 1 and dist.is_initialized() and isinstance(self._peers, IpcPeerGroup)
+                and all(isinstance(a, np.ndarray) and a.ndim == 1 for a in arrays)
+                and arrays[0].shape[0] >= self.SLICED_UPLOAD_MIN
+                and all(a.shape[0] == arrays[0].shape[0] for a in arrays)):
+            return self._sliced_upload(arrays, kinds)
+        keep = self.node_num
+        self.node_num = self.global_node_num          # the stager validates against node_num
+        try:
+            return self._ids_to_device(arrays, kinds, wrap_negative=False)
+        finally:
+            self.node_num = keep
+
+    def _pairs_peer(self, a_ids, b_ids) -> RoutedPairs:
+        dev = self._require_cuda()
+        lib = _lib.load()
+        n = int(len(a_ids))
+        if len(b_ids) != n:
+            raise ValueError('src and dst id arrays must have the same length')
+        cap = self._cap(max(n, 1))
+        out = torch.zeros(cap, self.pair_wise_feature_dim, dtype=torch.float32, device=dev)
+        rb = self._route_buffers('pairs', max(n, 1))
+        keep = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        if n == 0:
+            rb['count'].zero_()
+            return RoutedPairs(keep[:0], out[:0], rb['count'])
+        ptrs = self._global_ids_to_device([a_ids, b_ids], ['id', 'id'])
+        st = self._c_state()
+        sh = self._c_shard()
+        stream = self._stream()
+        count = torch.zeros(1, dtype=torch.int32, device=dev)      # per call: results of several calls stay alive
+        rc = lib.tpn_route_pairs(sh, ptrs[0], ptrs[1], n, rb['first'].data_ptr(), rb['second'].data_ptr(),
+                                 keep.data_ptr(), count.data_ptr(), rb['ws'].data_ptr(), rb['ws'].numel(), stream)
+        if rc:
+            _lib.check(rc, 'tpn_route_pairs')
+        self._pull()
+        rc = lib.tpn_pairwise(st, rb['first'].data_ptr(), rb['second'].data_ptr(), cap, count.data_ptr(),
+                              0 if self.not_scale else 1, out.data_ptr(), stream)
+        if rc:
+            _lib.check(rc, 'tpn_pairwise')
+        self._h.launches += 1
+        return RoutedPairs(keep[:cap], out, count)
+
+    def routed_pair_wise_gram(self, src_node_ids, dst_node_ids) -> RoutedPairs:
+        """Peer data plane, no host synchronisation: padded features of the owned pairs + device-side count."""
+        return self._pairs_peer(src_node_ids, dst_node_ids)
+
+    def routed_pair_wise_feature(self, src_node_ids, dst_node_ids) -> RoutedPairs:
+        r = self._pairs_peer(src_node_ids, dst_node_ids)
+        return RoutedPairs(r.keep, self._head(r.feat, r.count), r.count)
+
+    def assemble(self, routed: RoutedPairs, n: int) -> torch.Tensor:
+        """The reference's ``[n, F]`` result on every rank: each rank contributes the rows of the pairs it owns
+        (one all_gather of the padded blocks; collective over the process group)."""
+        cap, F = routed.feat.shape
+        if self.world == 1 or not dist.is_initialized():
+            keep, feat = routed.trimmed()
+            full = torch.zeros(n, F, dtype=torch.float32, device=feat.device)
+            full[keep] = feat
+            return full
+        feats = torch.empty(self.world, cap, F, dtype=torch.float32, device=routed.feat.device)
+        keeps = torch.empty(self.world, cap, dtype=torch.int64, device=routed.feat.device)
+        counts = torch.empty(self.world, dtype=torch.int32, device=routed.feat.device)
+        dist.all_gather_into_tensor(feats, routed.feat.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(keeps, routed.keep.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(counts, routed.count, group=self.group)
+        full = torch.zeros(n, F, dtype=torch.float32, device=routed.feat.device)
+        valid = torch.arange(cap, device=counts.device)[None, :] < counts[:, None]
+        full[keeps[valid]] = feats[valid]
+        return full
+
     # ------------------------------------------------------------------ API
     def _make_plan(self, first: np.ndarray, second: np.ndarray) -> ShardPlan:
         if self.world == 1:
@@ -254,6 +567,8 @@ class ShardedRandomProjection(RandomProjectionModule):
         if self.world == 1 and plan is None:
             # one shard = the whole graph: the plain edge-batch path (no message list, no exchange)
             return RandomProjectionModule.update(self, src_node_ids, dst_node_ids, node_interact_times, next_time)
+        if self.exchange == 'peer' and plan is None:
+            return self._update_peer(src_node_ids, dst_node_ids, node_interact_times, next_time)
         dev = self._require_cuda()
         lib = _lib.load()
         t = np.asarray(node_interact_times, dtype=np.float64)
@@ -282,9 +597,7 @@ class ShardedRandomProjection(RandomProjectionModule):
             need = lib.tpn_update_workspace_bytes(st, (M + 1) // 2)
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
-            if self._err is None:
-                self._err = torch.zeros(1, dtype=torch.int32, device=dev)
-            args = (ptrs[0], ptrs[1], ptrs[2], M, self.n_local, next_time, float(np.float32(-lam)), factors,
+            args = (ptrs[0], ptrs[1], ptrs[2], M, None, self.n_local, next_time, float(np.float32(-lam)), factors,
                     self._ws.data_ptr(), self._ws.numel(), self._err.data_ptr(), self._stream())
             rc = lib.tpn_update_messages(st, *args)
             if rc == _lib.TPN_ERR_LOG_FULL:
@@ -331,6 +644,9 @@ class ShardedRandomProjection(RandomProjectionModule):
             if self._all_keep is None or self._all_keep.shape[0] != n:
                 self._all_keep = np.arange(n)
             return self._all_keep, RandomProjectionModule.pair_wise_gram(self, src_node_ids, dst_node_ids)
+        if self.exchange == 'peer' and plan is None:
+            keep, feat = self._pairs_peer(src_node_ids, dst_node_ids).trimmed()      # one read of the count
+            return keep, feat
         dev = self._require_cuda()
         lib = _lib.load()
         if plan is None:
@@ -340,16 +656,81 @@ class ShardedRandomProjection(RandomProjectionModule):
         out = torch.empty(m, self.pair_wise_feature_dim, dtype=torch.float32, device=dev)
         if m:
             ptrs = self._ids_to_device([plan.first_rows, plan.second_rows], ['id', 'id'])
-            rc = lib.tpn_pairwise(self._c_state(), ptrs[0], ptrs[1], m, 0 if self.not_scale else 1, out.data_ptr(),
+            rc = lib.tpn_pairwise(self._c_state(), ptrs[0], ptrs[1], m, None, 0 if self.not_scale else 1, out.data_ptr(),
                                   self._stream())
             if rc:
                 _lib.check(rc, 'tpn_pairwise')
             self._h.launches += 1
         return plan.keep, out
 
-    def get_pair_wise_feature(self, src_node_ids, dst_node_ids):
+    def get_pair_wise_feature(self, src_node_ids, dst_node_ids, gather: bool = False):
+        """Features of the pairs this rank owns, as ``(positions in the batch, [m, F])``; ``gather=True`` returns
+        the reference's ``[n, F]`` tensor (TPNet.py:112-129) on every rank (collective)."""
+        n = int(len(src_node_ids))
+        if self.exchange == 'peer' and self.world > 1:
+            routed = self.routed_pair_wise_feature(src_node_ids, dst_node_ids)
+            return self.assemble(routed, n) if gather else routed.trimmed()
         keep, feat = self.pair_wise_gram(src_node_ids, dst_node_ids)
-        return keep, self._head(feat)
+        feat = self._head(feat)
+        if not gather:
+            return keep, feat
+        keep_t = keep if isinstance(keep, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(keep)).to(feat.device)
+        return self.assemble(RoutedPairs(keep_t, feat, torch.tensor([feat.shape[0]], dtype=torch.int32,
+                                                                    device=feat.device)), n) \
+            if self.world == 1 else self._assemble_ragged(keep_t, feat, n)
+
+    def _assemble_ragged(self, keep: torch.Tensor, feat: torch.Tensor, n: int) -> torch.Tensor:
+        """'nccl' data plane: ranks hold different numbers of rows — pad to the largest, then assemble."""
+        m = torch.tensor([feat.shape[0]], dtype=torch.int64, device=feat.device)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+        cap = int(m.item())
+        pf = torch.zeros(cap, feat.shape[1], dtype=torch.float32, device=feat.device)
+        pk = torch.zeros(cap, dtype=torch.int64, device=feat.device)
+        pf[:feat.shape[0]] = feat
+        pk[:feat.shape[0]] = keep
+        return self.assemble(RoutedPairs(pk, pf, torch.tensor([feat.shape[0]], dtype=torch.int32, device=feat.device)), n)
+
+    # ------------------------------------------------------------------ state changes invalidate the remote-row caches
+    def _before_write(self) -> None:
+        """A write to the local rows outside update(): every peer must have finished the pulls it issued before."""
+        if self.exchange == 'peer' and self.world > 1 and self._state.is_cuda:
+            self._barrier()
+
+    def reset_random_projections(self):
+        self._before_write()
+        super().reset_random_projections()         # tpn_clear_walk_layers also sets every stamp to -1
+        self._state_written()
+
+    def reload_random_projections(self, random_projections):
+        self._before_write()
+        super().reload_random_projections(random_projections)
+        self._state_written()
+
+    def materialize(self) -> None:
+        """Collective in the peer data plane (every rank calls it at the same point, as backup / state_dict do):
+        the write-back of the pending decay must not race with a peer's pull."""
+        if self.exchange != 'peer' or self.world == 1 or not self._state.is_cuda:
+            return super().materialize()
+        self._before_write()
+        super().materialize()
+        self._state_written()
+
+    def _restart_log(self) -> None:
+        super()._restart_log()                     # every row rewritten, stamps restarted: cached copies are stale
+        self._state_written()
+
+    def check_errors(self) -> None:
+        super().check_errors()
+        if self._shard is not None:
+            code = int(self._shard_tensors['counters'][_lib.SHARD_CTR_ERROR].item())
+            if code:
+                self._shard_tensors['counters'][_lib.SHARD_CTR_ERROR] = 0
+                if code == 1:
+                    raise IndexError(f'node id out of range for node_num {self.global_node_num} in a sharded batch')
+                if code == 2:
+                    raise RuntimeError(f'the {self.ext_rows} extension rows cannot hold the remote rows of one '
+                                       f'generation: construct ShardedRandomProjection with a larger ext_rows')
+                raise RuntimeError('a peer rank never reached a barrier of the sharded data plane')
 
     def gather_global(self) -> List[torch.Tensor]:
         """All-gathers the L+1 global [N, d] matrices (tests / small graphs only)."""
