@@ -152,6 +152,12 @@ int tpn_update(tpn_state_t* st,
  *                              after the other on the caller's stream (default: concurrently, the
  *                              hub walker on a library-owned side stream forked/joined by events). */
 #define TPN_DEBUG_SERIAL_WALK 2
+/*   TPN_DEBUG_SNAPSHOT_P0    : the pre-batch snapshot also copies P_0 of every target, so the walkers read ALL
+ *                              source rows from one compact buffer (A/B measurements; results are identical). */
+#define TPN_DEBUG_SNAPSHOT_P0 4
+/*   TPN_DEBUG_HEAD_TENSOR    : tpn_head_forward runs on the tcgen05 tensor cores (fp16 x 2 split operands, fp32
+ *                              accumulation in TMEM; tpn_head_tc.cu) instead of the packed-FFMA kernel. */
+#define TPN_DEBUG_HEAD_TENSOR 8
 int tpn_set_debug_flags(int flags);
 
 

@@ -475,10 +475,21 @@ def test_pairwise_large_call(N, dim, L, n, mode):
     m.check_errors()
 
 
-@pytest.mark.parametrize('n', [1, 63, 64, 65, 1000, 100003])
-def test_fused_head_matches_torch_head(n):
-    """tpn_head_forward (no-grad path of get_pair_wise_feature) vs `self.mlp` in PyTorch: both are fp32
-    with different summation orders, so both are compared with the float64 head."""
+@pytest.fixture(params=['ffma', 'tensor'])
+def head_kernel(request):
+    """Both implementations of tpn_head_forward: packed-FFMA (fp32 CUDA cores) and tcgen05 (fp16 x 2 split operands,
+    fp32 accumulation in TMEM), selected by TPN_DEBUG_HEAD_TENSOR."""
+    lib = _lib.load()
+    old = lib.tpn_set_debug_flags(8 if request.param == 'tensor' else 0)
+    yield request.param
+    lib.tpn_set_debug_flags(old)
+
+
+@pytest.mark.parametrize('n', [1, 63, 64, 65, 127, 128, 129, 1000, 100003])
+def test_fused_head_matches_torch_head(n, head_kernel):
+    """tpn_head_forward (no-grad path of get_pair_wise_feature) vs `self.mlp` in PyTorch: both are fp32-accurate
+    with different summation orders (the tensor-core kernel: operands split into two fp16 numbers, 22 bits, fp32
+    accumulation), so both are compared with the float64 head."""
     torch.manual_seed(3)
     kw = dict(node_num=50, edge_num=5000, dim_factor=10, num_layer=3, time_decay_weight=1e-6, use_matrix=False,
               beginning_time=0.0, not_scale=False, enforce_dim=-1)
@@ -509,6 +520,47 @@ def test_fused_head_matches_torch_head(n):
         m.fused_head = False
         b = m.get_pair_wise_feature(ids, ids[::-1].copy())
     assert float((a - b).abs().max()) <= 2e-5 * (float(b.abs().max()) + 1.0)
+
+
+def test_tensor_core_head_dynamic_range_and_counts(head_kernel):
+    """Rows of very different magnitude (each row of the activations has its own power-of-two scale), raw Gram values
+    (`not_scale`: 1e6 and beyond — far outside fp16's range before scaling), all-zero rows, tiny weights; and the
+    device-side row count of routed calls (rows past the count stay untouched)."""
+    torch.manual_seed(5)
+    mlp = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.ReLU(), torch.nn.Linear(256, 64)).to(DEV)
+    lib = _lib.load()
+    n = 777
+    x = torch.rand(n, 64, device=DEV)
+    x *= torch.logspace(-6, 7, n, device=DEV)[:, None]            # row magnitudes from 1e-6 to 1e7
+    x[5] = 0
+    x[::9, ::3] *= -1.0
+    for wscale in (1.0, 1e-4, 300.0):
+        with torch.no_grad():
+            for p in mlp.parameters():
+                p.mul_(wscale)
+        ref64 = mlp.double()(x.double())
+        mlp.float()
+        y = torch.full((n, 64), 7.0, device=DEV)
+        cnt = torch.tensor([n - 100], dtype=torch.int32, device=DEV)
+        l1, l2 = mlp[0], mlp[2]
+        rc = lib.tpn_head_forward(x.data_ptr(), n, cnt.data_ptr(), 64, 256, l1.weight.data_ptr(), l1.bias.data_ptr(),
+                                  l2.weight.data_ptr(), l2.bias.data_ptr(), y.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert torch.all(y[n - 100:] == 7.0)                                   # rows past the device-side count
+        got, want = y[:n - 100].double(), ref64[:n - 100]
+        with torch.no_grad():
+            ref32 = mlp(x)[:n - 100].double()
+        # per row: error relative to the row's largest output (fp32 SGEMM noise is relative to sum |x||w|, so the
+        # torch fp32 result itself is only this accurate)
+        row = want.abs().max(dim=1, keepdim=True).values + 1e-30
+        err = ((got - want).abs() / row).max().item()
+        err32 = ((ref32 - want).abs() / row).max().item()
+        assert err <= 4 * err32 + 2e-6, (head_kernel, wscale, err, err32)
+        with torch.no_grad():
+            for p in mlp.parameters():
+                p.div_(wscale)
 
 
 def test_lazy_matches_eager_and_log_restart(monkeypatch):

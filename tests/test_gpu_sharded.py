@@ -82,11 +82,22 @@ def _sim_ranks(world, kw, mode, ext_rows, accumulation='reference', chunk=1024):
 
 
 def _each(ranks, streams, fn):
+    """One phase on every rank (each on its own stream), then a device-wide sync: with all ranks on one GPU the
+    phases are ordered by the driver instead of tpn_peer_barrier (LocalPeerGroup.host_barriers)."""
     out = []
     for m, s in zip(ranks, streams):
         with torch.cuda.stream(s):
             out.append(fn(m))
+    torch.cuda.synchronize()
     return out
+
+
+def _update_all(ranks, streams, s, d, ts, next_time=None):
+    pending = _each(ranks, streams, lambda m: m.update_begin(s, d, ts, next_time))      # reads: routing + pulls
+    for m, st, p in zip(ranks, streams, pending):                                     # writes
+        with torch.cuda.stream(st):
+            m.update_end(p)
+    torch.cuda.synchronize()
 
 
 def _global_layers(ranks, N, L, streams):
@@ -130,7 +141,7 @@ def test_peer_data_plane_equals_single_gpu(world, mode):
                 a = rng.integers(0, N, n).astype(np.int64)
                 b = rng.integers(0, N, n).astype(np.int64)
                 routed = _each(ranks, streams, lambda m: m.routed_pair_wise_gram(a, b))      # reads ...
-                _each(ranks, streams, lambda m: m.update(s, d, ts))                           # ... then the write
+                _update_all(ranks, streams, s, d, ts)                                         # ... then the write
                 want = ref.pair_wise_gram(a, b)
                 ref.update(s, d, ts)
                 torch.cuda.synchronize()
@@ -153,12 +164,13 @@ def test_peer_data_plane_equals_single_gpu(world, mode):
         saved_ref = ref.backup_random_projections()
         s = rng.integers(1, N, 500).astype(np.int64); d = rng.integers(1, N, 500).astype(np.int64)
         ts = np.sort(t + rng.random(500) * 100.0)
-        _each(ranks, streams, lambda m: m.update(s, d, ts)); ref.update(s, d, ts)
+        _update_all(ranks, streams, s, d, ts); ref.update(s, d, ts)
         for m, sv, st in zip(ranks, saved, streams):
             with torch.cuda.stream(st):
                 m.reload_random_projections(sv)
+        torch.cuda.synchronize()
         ref.reload_random_projections(saved_ref)
-        _each(ranks, streams, lambda m: m.update(s, d, ts)); ref.update(s, d, ts)
+        _update_all(ranks, streams, s, d, ts); ref.update(s, d, ts)
         full = _global_layers(ranks, N, L, streams)
         ref.materialize()
         for i in range(L + 1):
@@ -166,6 +178,30 @@ def test_peer_data_plane_equals_single_gpu(world, mode):
         for m in ranks:
             m.check_errors()
             assert m.barriers > 0
+
+
+def test_peer_barrier_kernel_single_rank():
+    """tpn_peer_barrier itself (world 1: the rank signals and waits for its own flag word): the sequence number
+    advances, nothing hangs, no error.  Several ranks need one GPU each: tests/dist_gpu_check.py."""
+    import ctypes
+    from tpnet_b200 import _lib
+    from tpnet_b200.peer import PeerBuffer
+    lib = _lib.load()
+    dev = torch.device('cuda:0')
+    flags = PeerBuffer(64, dev)
+    table = torch.tensor([flags.ptr], dtype=torch.int64, device=dev)
+    mark = torch.zeros(8, dtype=torch.int32, device=dev)
+    ctr = torch.zeros(8, dtype=torch.int32, device=dev)
+    need = torch.zeros(8, dtype=torch.int64, device=dev)
+    seq = torch.zeros(1, dtype=torch.int32, device=dev)
+    sh = _lib.TpnShard()
+    sh.world, sh.rank, sh.global_nodes, sh.num_local_rows, sh.ext_rows = 1, 0, 8, 8, 0
+    sh.mark, sh.counters, sh.need_nodes = mark.data_ptr(), ctr.data_ptr(), need.data_ptr()
+    sh.peer_flags, sh.barrier_seq = table.data_ptr(), seq.data_ptr()
+    for k in range(1, 4):
+        assert lib.tpn_peer_barrier(ctypes.byref(sh), torch.cuda.current_stream().cuda_stream) == 0
+        torch.cuda.synchronize()
+        assert int(seq.item()) == k and int(flags.tensor((1,), torch.int32).item()) == k and int(ctr[2].item()) == 0
 
 
 def test_peer_data_plane_chunked_accumulation_and_errors():
@@ -189,7 +225,7 @@ def test_peer_data_plane_chunked_accumulation_and_errors():
         assert np.bincount(np.concatenate([s, d])).max() >= 2048
         ts = np.sort(t + rng.random(B) * 500.0)
         t = ts[-1]
-        _each(ranks, streams, lambda m: m.update(s, d, ts)); ref.update(s, d, ts)
+        _update_all(ranks, streams, s, d, ts); ref.update(s, d, ts)
     full = _global_layers(ranks, N, L, streams)
     ref.materialize()
     for i in range(L + 1):
@@ -198,8 +234,7 @@ def test_peer_data_plane_chunked_accumulation_and_errors():
     bad = torch.tensor([5, N + 7, 9], dtype=torch.int64, device=dev)
     ok = torch.tensor([6, 8, 10], dtype=torch.int64, device=dev)
     tt = torch.full((3,), t + 1.0, dtype=torch.float64, device=dev)
-    _each(ranks, streams, lambda m: m.update(bad, ok, tt, next_time=t + 1.0))
-    torch.cuda.synchronize()
+    _update_all(ranks, streams, bad, ok, tt, next_time=t + 1.0)
     for m in ranks:
         with pytest.raises(IndexError):
             m.check_errors()

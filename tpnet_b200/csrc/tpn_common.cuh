@@ -52,6 +52,11 @@ struct DeviceScope {
 };
 // SM count of the current device (cached per device; 148 on B200)
 int device_sm_count();
+// TPN_DEBUG_* flags (tpn_set_debug_flags)
+int debug_flags();
+// tpn_head_tc.cu: the head on tcgen05 tensor cores
+int launch_head_tensor(const float* x, long long n, const int* n_dev, const float* w1, const float* b1, const float* w2,
+                       const float* b2, float* y, int dev_slot, cudaStream_t stream);
 
 inline int validate_state(const tpn_state_t* st) {
     if (st == nullptr || st->data == nullptr) return TPN_ERR_INVALID_ARGUMENT;

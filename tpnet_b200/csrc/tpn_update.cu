@@ -69,9 +69,10 @@ constexpr int kHub2SlotFloats = 64;      // floats of one message held by a ring
 constexpr int kHub2GiantFloats = TPN_HUB2_GIANT_FLOATS;     // slice width of giant segments: an SM sustains ~10 B/clk of row gathers
                                          // (outstanding-miss capacity), so 64 B per message keeps its data path
                                          // near the add chain's 4-6 cycles per message
-static_assert(kHub2GiantFloats == 16 || kHub2GiantFloats == 32, "giant slices are 64 or 128 bytes");
-constexpr int kGiantLs = kHub2GiantFloats == 16 ? 2 : 3;   // log2(lanes per giant message): 4 or 8 lanes of 16 bytes
-constexpr int kGiantSpm = 16 >> kGiantLs;                  // 32-message sub-blocks per ring stage: 4 or 2
+static_assert(kHub2GiantFloats == 8 || kHub2GiantFloats == 16 || kHub2GiantFloats == 32, "giant slices are 32, 64 or 128 bytes");
+constexpr int kGiantLs = kHub2GiantFloats == 8 ? 1 : (kHub2GiantFloats == 16 ? 2 : 3);   // log2(lanes per giant message): 2, 4 or 8 lanes of 16 bytes
+constexpr int kGiantSpm = 16 >> kGiantLs;                  // 32-message sub-blocks per ring stage: 8, 4 or 2
+constexpr int kGiantSpmMax = kGiantSpm > 4 ? kGiantSpm : 4;
 constexpr int kHub2Stages = kHub2Producers + 4;            // ring stages of 32 messages (8 KB each)
 // ctr[] slots (zeroed by prep_large_kernel)
 constexpr int kCtrGiant = 0, kCtrHub = 1, kCtrWork0 = 2, kCtrSmall = 6, kCtrHub2Work = 7, kCtrHub2Giant = 8;
@@ -154,7 +155,8 @@ struct Workspace {
 };
 
 inline size_t snap_bytes(size_t E, int num_layer, int64_t row_stride) {
-    return sizeof(float) * E * (size_t)(num_layer - 1) * (size_t)row_stride;
+    // rows 1..L-1 of every target (rows 0..L-1 with TPN_DEBUG_SNAPSHOT_P0): sized for the larger of the two
+    return sizeof(float) * E * (size_t)num_layer * (size_t)row_stride;
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -754,7 +756,8 @@ template <int V, int D, bool LAZY, bool ALL>
 __global__ void __launch_bounds__(kWalkThreads)
 walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ssrc,
             const float* __restrict__ sw, const uint32_t* __restrict__ sslot, const uint32_t* __restrict__ slen,
-            const float* __restrict__ snap, Count count, int ds4, int write_stamp, int hub_min, DecayArgs dnow) {
+            const float* __restrict__ snap, Count count, int ds4, int write_stamp, int hub_min, DecayArgs dnow,
+            int srow0) {
     const int wid = (blockIdx.x * kWalkThreads + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= count.get()) return;
@@ -765,7 +768,8 @@ walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const ui
     if (len >= hub_min) return;                                  // handled by walk_hub_kernel
     const int L = st.num_layer;
     const int span4 = ALL ? L * ds4 : ds4;               // float4 in the target span
-    const int snap4 = (L - 1) * ds4;                     // float4 per snapshot slot
+    const int soff = srow0 * ds4;                        // source columns below this come from the state (P_0)
+    const int snap4 = L * ds4 - soff;                    // float4 per snapshot slot
     const int col0 = blockIdx.y * (32 * V) + lane;
 
     float* tbase = st.data + (long long)key * st.node_stride + (long long)(ALL ? 1 : layer) * st.row_stride;
@@ -815,8 +819,8 @@ walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const ui
                     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (jj < nmsg && c < span4) {
                         if (ALL) {
-                            val = (c < ds4 || direct) ? ld4(sstate + 4 * (long long)c)
-                                                      : ld4(ssnap + 4 * (long long)(c - ds4));
+                            val = (c < soff || direct) ? ld4(sstate + 4 * (long long)c)
+                                                       : ld4(ssnap + 4 * (long long)(c - soff));
                             // cached rows of other ranks carry their own stamps, like any row (lazy mode;
                             // in eager mode the sweep already covered them): one multiply from the stamp
                             // to this call's epoch, exactly what the snapshot does for local sources
@@ -857,7 +861,8 @@ walk_kernel(StateView st, int layer, const uint32_t* __restrict__ skey, const ui
 // one warp per segment head; slot = sorted position of the head.
 template <bool LAZY>
 __global__ void __launch_bounds__(256)
-snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, Count count, int ds4, float* __restrict__ snap) {
+snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, Count count, int ds4, float* __restrict__ snap,
+                int srow0) {
     const int p = (blockIdx.x * 256 + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (p >= count.get()) return;
@@ -865,16 +870,17 @@ snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, Count count, in
     if ((long long)key >= st.num_nodes) return;
     if (p > 0 && skey[p - 1] == key) return;
     const int L = st.num_layer;
-    const int snap4 = (L - 1) * ds4;
-    const float* rows = st.data + (long long)key * st.node_stride + st.row_stride;    // row 1
+    const int snap4 = (L - srow0) * ds4;                 // rows srow0..L-1 (srow0 = 1: P_0 is read from the state)
+    const float* rows = st.data + (long long)key * st.node_stride + (long long)srow0 * st.row_stride;
     float* slot = snap + (long long)p * snap4 * 4;
-    // pending decay of rows 1..L-1: lane l fetches the stamp of layer l + 1 and computes its factor
-    // (one f64 division per layer, not per lane and column step); a negative factor marks a row
-    // that was never written (all zero): it is not read at all
+    // pending decay: lane j handles snapshot row j = state row srow0 + j (row 0, P_0, never decays): it fetches
+    // the row's stamp and computes its factor (one f64 division per row, not per lane and column step); a
+    // negative factor marks a row that was never written (all zero): it is not read at all
     float fmine = 1.0f;
-    if (LAZY && lane < L - 1) {
-        const long long stamp = st.stamps[(long long)key * L + lane];
-        fmine = stamp >= 0 ? decay_factor(st, lane, stamp) : -1.0f;
+    if (LAZY && lane < L - srow0 && srow0 + lane >= 1) {
+        const int li = srow0 + lane - 1;                 // decay-log column of state row srow0 + lane
+        const long long stamp = st.stamps[(long long)key * L + li];
+        fmine = stamp >= 0 ? decay_factor(st, li, stamp) : -1.0f;
     }
     float f[TPN_MAX_LAYERS];
 #pragma unroll
@@ -893,7 +899,7 @@ snapshot_kernel(StateView st, const uint32_t* __restrict__ skey, Count count, in
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + 32 * k;
             if (c < snap4) {
-                if (LAZY && fk[k] >= 0.f) scale4(v[k], fk[k]);
+                if (LAZY && fk[k] >= 0.f && fk[k] != 1.0f) scale4(v[k], fk[k]);
                 st4(slot + 4 * (long long)c, v[k]);
             }
         }
@@ -1129,7 +1135,7 @@ walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_
                   const float* __restrict__ sw, const uint32_t* __restrict__ sslot,
                   const uint32_t* __restrict__ slen, const float* __restrict__ snap,
                   const uint32_t* __restrict__ heads, const uint32_t* __restrict__ ctr, int E, int ds4,
-                  DecayArgs dnow) {
+                  DecayArgs dnow, int srow0) {
     constexpr int D = V >= 4 ? 2 : 4;                 // source spans in flight per round
     const int lane = threadIdx.x & 31;
     const int warps = gridDim.x * (kSmallWalkThreads / 32);
@@ -1138,7 +1144,8 @@ walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_
     if (it >= n_items) return;
     const int L = st.num_layer;
     const int span4 = L * ds4;
-    const int snap4 = (L - 1) * ds4;
+    const int soff = srow0 * ds4;                     // source columns below this come from the state (P_0)
+    const int snap4 = span4 - soff;
     int col[V], tl[V];
     bool in[V];
 #pragma unroll
@@ -1218,8 +1225,8 @@ walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_
                     for (int k = 0; k < V; ++k) {
                         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (jj < nmsg && in[k]) {
-                            val = (col[k] < ds4 || direct) ? ld4(sstate + 4 * (long long)col[k])
-                                                           : ld4(ssnap + 4 * (long long)(col[k] - ds4));
+                            val = (col[k] < soff || direct) ? ld4(sstate + 4 * (long long)col[k])
+                                                            : ld4(ssnap + 4 * (long long)(col[k] - soff));
                             if (DIRECT && LAZY && direct && col[k] >= ds4)
                                 scale4(val, pick4(fd1, fd2, fd3, 1.0f, tl[k] - 1));      // x * 1.0f is exact
                         }
@@ -1297,7 +1304,7 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                  const uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ hub_reg,
                  uint32_t* __restrict__ ctr, int spr_g, int slice_w_g, int spr_r, int slice_w_r, DecayArgs dnow,
                  const uint32_t* __restrict__ hub_len, const uint32_t* __restrict__ hub_part,
-                 float* __restrict__ partial, int chunked) {
+                 float* __restrict__ partial, int chunked, int srow0) {
     extern __shared__ __align__(128) unsigned char hub2_raw[];
     float* const ring = reinterpret_cast<float*>(hub2_raw);                       // [stages][32][kHub2SlotFloats]
     uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)kHub2Stages * 32 * kHub2SlotFloats);
@@ -1373,8 +1380,8 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                 auto row_ptr = [&](uint32_t v, uint32_t x) -> const float* {
                     if (DIRECT && (x & kDirect) != 0)         // received row: rows 0..L-1 contiguous in the state
                         return st.data + (long long)v * st.node_stride + (long long)r * rs + c0;
-                    if (r == 0) return st.data + (long long)v * st.node_stride + c0;            // P_0: never written
-                    return snap + (long long)x * (long long)(L - 1) * rs + (long long)(r - 1) * rs + c0;
+                    if (r < srow0) return st.data + (long long)v * st.node_stride + c0;         // P_0: never written
+                    return snap + (long long)x * (long long)(L - srow0) * rs + (long long)(r - srow0) * rs + c0;
                 };
                 for (int b = pw; b < nblk; b += kHub2Producers) {
                     const uint32_t g = blk_base + (uint32_t)b;
@@ -1384,17 +1391,17 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                     (void)pass;                       // only the timeline build reads it
                     HUB2_STAMP(pass, 0);
                     // (1) metadata of this lane's message in each sub-block of the stage (all in flight together)
-                    unsigned plo[4], phi[4];
-                    float wl[4], fl[4];
+                    unsigned plo[kGiantSpmMax], phi[kGiantSpmMax];
+                    float wl[kGiantSpmMax], fl[kGiantSpmMax];
 #pragma unroll
-                    for (int sb = 0; sb < 4; ++sb) {
+                    for (int sb = 0; sb < kGiantSpmMax; ++sb) {
                         const int j = (b * spm + sb) * 32 + lane;
                         const float* ptr = st.data;
                         wl[sb] = 0.f;
                         fl[sb] = 1.0f;
                         if (sb < spm && j < len) {
                             const uint32_t v = ssrc[head + j];
-                            const uint32_t x = (r >= 1 || DIRECT) ? sslot[head + j] : 0u;
+                            const uint32_t x = (r >= srow0 || DIRECT) ? sslot[head + j] : 0u;
                             float w = sw[head + j];
                             if (DIRECT) {                     // sign bit of the weight = "cached row of another rank"
                                 if (LAZY && r >= 1 && __float_as_int(w) < 0) {
@@ -1551,7 +1558,7 @@ combine_giants_kernel(StateView st, const uint32_t* __restrict__ skey, const uin
 }
 
 template <bool DIRECT>
-int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const DecayArgs& dnow, int chunk,
+int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const DecayArgs& dnow, int chunk, int srow0,
                      cudaStream_t stream) {
     static bool configured_tab[kMaxDevices];          // per device: the shared-memory opt-in is a device attribute
     bool& configured = configured_tab[g_dev_slot];
@@ -1579,12 +1586,14 @@ int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const D
         walk_hub2_kernel<true, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                              ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
                                                                              spr_g, slice_w_g, spr_r, slice_w_r, dnow,
-                                                                             ws.hub_len, ws.hub_part, ws.partial, chunked);
+                                                                             ws.hub_len, ws.hub_part, ws.partial, chunked,
+                                                                             srow0);
     else
         walk_hub2_kernel<false, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                               ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
                                                                               spr_g, slice_w_g, spr_r, slice_w_r, dnow,
-                                                                              ws.hub_len, ws.hub_part, ws.partial, chunked);
+                                                                              ws.hub_len, ws.hub_part, ws.partial, chunked,
+                                                                              srow0);
     if (chunked) {
         const unsigned cgrid = (unsigned)device_sm_count();
         if (lazy)
@@ -1599,23 +1608,23 @@ int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const D
 
 template <int V, bool DIRECT>
 void launch_walk_small_v(const StateView& v, const Workspace& ws, int E, int ds4, int tiles, bool lazy,
-                         const DecayArgs& dnow, cudaStream_t stream) {
+                         const DecayArgs& dnow, int srow0, cudaStream_t stream) {
     long long want = ((long long)E + kSmallWalkThreads / 32 - 1) / (kSmallWalkThreads / 32);
     const long long cap = (long long)device_sm_count() * 2 * 2;      // two resident CTAs per SM, two waves
     dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)tiles);
     if (lazy)
         walk_small_kernel<V, true, DIRECT><<<grid, kSmallWalkThreads, 0, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
                                                                                    ws.slen, ws.snap, ws.small_heads, ws.ctr,
-                                                                                   E, ds4, dnow);
+                                                                                   E, ds4, dnow, srow0);
     else
         walk_small_kernel<V, false, DIRECT><<<grid, kSmallWalkThreads, 0, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
                                                                                     ws.slen, ws.snap, ws.small_heads, ws.ctr,
-                                                                                    E, ds4, dnow);
+                                                                                    E, ds4, dnow, srow0);
 }
 
 template <bool DIRECT>
 void launch_walk_small(const StateView& v, const Workspace& ws, int E, int ds4, bool lazy, const DecayArgs& dnow,
-                       cudaStream_t stream) {
+                       int srow0, cudaStream_t stream) {
     const int span4 = v.num_layer * ds4;
     int vpl = (span4 + 31) / 32;
     int tiles = 1;
@@ -1624,12 +1633,12 @@ void launch_walk_small(const StateView& v, const Workspace& ws, int E, int ds4, 
         vpl = (vpl + tiles - 1) / tiles;
     }
     switch (vpl) {
-        case 1: launch_walk_small_v<1, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
-        case 2: launch_walk_small_v<2, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
-        case 3: launch_walk_small_v<3, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
-        case 4: launch_walk_small_v<4, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
-        case 5: launch_walk_small_v<5, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
-        default: launch_walk_small_v<6, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, stream); break;
+        case 1: launch_walk_small_v<1, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, srow0, stream); break;
+        case 2: launch_walk_small_v<2, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, srow0, stream); break;
+        case 3: launch_walk_small_v<3, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, srow0, stream); break;
+        case 4: launch_walk_small_v<4, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, srow0, stream); break;
+        case 5: launch_walk_small_v<5, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, srow0, stream); break;
+        default: launch_walk_small_v<6, DIRECT>(v, ws, E, ds4, tiles, lazy, dnow, srow0, stream); break;
     }
 }
 
@@ -1695,16 +1704,18 @@ int launch_walk_hub(const StateView& v, int layer, const Workspace& ws, int E4, 
 
 template <int V, int D, bool ALL>
 void launch_walk(const StateView& v, int layer, const Workspace& ws, Count E, int ds4, int tiles, bool lazy,
-                 bool hubs, const DecayArgs& dnow, cudaStream_t stream) {
+                 bool hubs, const DecayArgs& dnow, cudaStream_t stream, int srow0 = 1) {
     dim3 grid((unsigned)(((long long)E.cap * 32 + kWalkThreads - 1) / kWalkThreads), (unsigned)tiles);
     const int write_stamp = (!ALL && tiles == 1 && !hubs) ? 1 : 0;
     const int hub_min = hubs ? kHubMin : 0x7fffffff;
     if (lazy)
         walk_kernel<V, D, true, ALL><<<grid, kWalkThreads, 0, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
-                                                                        ws.slen, ws.snap, E, ds4, write_stamp, hub_min, dnow);
+                                                                        ws.slen, ws.snap, E, ds4, write_stamp, hub_min, dnow,
+                                                                        srow0);
     else
         walk_kernel<V, D, false, ALL><<<grid, kWalkThreads, 0, stream>>>(v, layer, ws.key_a, ws.ssrc, ws.sw, ws.sslot,
-                                                                         ws.slen, ws.snap, E, ds4, write_stamp, hub_min, dnow);
+                                                                         ws.slen, ws.snap, E, ds4, write_stamp, hub_min, dnow,
+                                                                         srow0);
 }
 
 }  // namespace
@@ -1861,11 +1872,14 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
         }
     }
 
+    // first source row that is read from the pre-batch snapshot: 1 (P_0 is never written: read in place), or —
+    // TPN_DEBUG_SNAPSHOT_P0 — 0: the snapshot also holds P_0, so every source read of the walkers hits one compact buffer
+    const int srow0 = (g_debug_flags & TPN_DEBUG_SNAPSHOT_P0) ? 0 : 1;
     if (snapshot_path) {
-        if (L >= 2) {
+        if (L - srow0 >= 1) {
             const unsigned grid = (unsigned)(((long long)E * 32 + 255) / 256);
-            if (lazy) snapshot_kernel<true><<<grid, 256, 0, stream>>>(view, ws.key_a, cnt, ds4, ws.snap);
-            else snapshot_kernel<false><<<grid, 256, 0, stream>>>(view, ws.key_a, cnt, ds4, ws.snap);
+            if (lazy) snapshot_kernel<true><<<grid, 256, 0, stream>>>(view, ws.key_a, cnt, ds4, ws.snap, srow0);
+            else snapshot_kernel<false><<<grid, 256, 0, stream>>>(view, ws.key_a, cnt, ds4, ws.snap, srow0);
         }
         if (hubs) {
             // large batch: long segments on the CTA-pipelined hub walker, short ones on the
@@ -1880,11 +1894,11 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
                 else
                     (void)cudaGetLastError();
             }
-            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, chunk, hub_stream)
-                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, chunk, hub_stream);
+            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, chunk, srow0, hub_stream)
+                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, chunk, srow0, hub_stream);
             if (hrc != TPN_OK) return hrc;
-            if (direct) launch_walk_small<true>(view, ws, E, ds4, lazy, dargs, stream);
-            else launch_walk_small<false>(view, ws, E, ds4, lazy, dargs, stream);
+            if (direct) launch_walk_small<true>(view, ws, E, ds4, lazy, dargs, srow0, stream);
+            else launch_walk_small<false>(view, ws, E, ds4, lazy, dargs, srow0, stream);
             if (hub_stream != stream) {
                 if (cudaEventRecord(side->join, hub_stream) != cudaSuccess ||
                     cudaStreamWaitEvent(stream, side->join, 0) != cudaSuccess) {
@@ -1895,7 +1909,7 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
         } else {
             // single-CTA sort path: one float4 per lane, a warp covers 512 contiguous bytes of the span
             const int span4 = L * ds4;
-            launch_walk<1, 16, true>(view, 0, ws, cnt, ds4, (span4 + 31) / 32, lazy, false, dargs, stream);
+            launch_walk<1, 16, true>(view, 0, ws, cnt, ds4, (span4 + 31) / 32, lazy, false, dargs, stream, srow0);
         }
         if (lazy) stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, 0, ws.key_a, cnt);
     } else {
@@ -1940,6 +1954,10 @@ extern "C" int tpn_debug_hub_timeline(unsigned long long* host_out, size_t count
                ? TPN_OK : TPN_ERR_CUDA;
 }
 #endif
+
+namespace tpn {
+int debug_flags() { return g_debug_flags; }
+}  // namespace tpn
 
 extern "C" int tpn_set_debug_flags(int flags) {
     const int old = tpn::g_debug_flags;

@@ -88,7 +88,13 @@ class PeerGroup:
 
 class LocalPeerGroup(PeerGroup):
     """All ranks in one process.  ``LocalPeerGroup.create(world)`` returns one view per rank; every rank
-    registers its buffers (``publish``) before any of them resolves the table (``exchange``)."""
+    registers its buffers (``publish``) before any of them resolves the table (``exchange``).
+
+    ``host_barriers``: ranks that share ONE GPU cannot use the spinning flag barrier (``tpn_peer_barrier``): a
+    kernel of rank A that waits for rank B can sit in front of rank B's work in the same hardware queue.  The
+    driver of the ranks orders the phases instead — every rank finishes its reads (``update_begin``, pair-wise
+    calls) before any rank writes (``update_end``) — and the module skips the device barrier."""
+    host_barriers = True
 
     def __init__(self, world: int, rank: int, table: Dict[str, List[Optional[int]]]):
         self.world, self.rank, self._table = int(world), int(rank), table

@@ -368,8 +368,10 @@ class ShardedRandomProjection(RandomProjectionModule):
         return buf
 
     def _barrier(self) -> None:
-        _lib.check(_lib.load().tpn_peer_barrier(self._c_shard(), self._stream()), 'tpn_peer_barrier')
         self.barriers += 1
+        if getattr(self._peers, 'host_barriers', False):
+            return          # LocalPeerGroup: the driver of the in-process ranks orders the phases itself (peer.py)
+        _lib.check(_lib.load().tpn_peer_barrier(self._c_shard(), self._stream()), 'tpn_peer_barrier')
 
     def _pull(self) -> None:
         """Peers' writes are ordered before this rank's reads of their rows (one barrier after any write), then the
@@ -386,6 +388,14 @@ class ShardedRandomProjection(RandomProjectionModule):
             _lib.check(_lib.load().tpn_shard_new_generation(self._c_shard(), self._stream()), 'tpn_shard_new_generation')
 
     def _update_peer(self, src_node_ids, dst_node_ids, node_interact_times, next_time) -> None:
+        pending = self.update_begin(src_node_ids, dst_node_ids, node_interact_times, next_time)
+        self._barrier()                       # every rank has pulled its pre-batch rows: now the writes may start
+        self.update_end(pending)
+
+    def update_begin(self, src_node_ids, dst_node_ids, node_interact_times, next_time=None):
+        """First half of a routed update: routing + pulls of the pre-batch remote rows (reads only).  ``update`` is
+        ``update_begin`` -> rank barrier -> ``update_end``; a driver that runs several ranks in one process calls
+        the halves itself (all ranks' ``update_begin``, then all ranks' ``update_end``)."""
         dev = self._require_cuda()
         lib = _lib.load()
         n = int(len(src_node_ids))
@@ -412,7 +422,16 @@ class ShardedRandomProjection(RandomProjectionModule):
         if rc:
             _lib.check(rc, 'tpn_route_update')
         self._pull()
-        self._barrier()                       # every rank has pulled its pre-batch rows: now the writes may start
+        return dict(n=n, rb=rb, next_time=float(next_time), factors=factors, lam=lam)
+
+    def update_end(self, pending) -> None:
+        """Second half of a routed update: the rank-local kernels (writes) and the new cache generation."""
+        dev = self._state.device
+        lib = _lib.load()
+        h = self._h
+        n, rb, next_time, factors, lam = (pending[k] for k in ('n', 'rb', 'next_time', 'factors', 'lam'))
+        st = self._c_state()
+        stream = self._stream()
         cap = self._cap(2 * n)
         need = lib.tpn_update_workspace_bytes(st, (cap + 1) // 2)
         if self._ws is None or self._ws.numel() < need:
