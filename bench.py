@@ -538,6 +538,7 @@ def sharded_parity(args, rank, world, device):
             ref.update(s, d, t)
     full = sh.gather_global()
     sh.check_errors()
+    sh.close()
     out = None
     if rank == 0:
         ref.materialize()
@@ -673,6 +674,7 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
         del graphs
 
     # per-phase device time (events around each call) for the roofline of the dominant kernel
+    pool = torch.cuda.graph_pool_handle() if use_graphs else None      # the step graphs' pool died with them
     t_pair, t_upd = [], []
     for st in steps[warm_n + K + W:warm_n + K + W + n_phase]:
         r = (stage_nccl if nccl else stage)(st)
@@ -787,6 +789,7 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
     dev_ms, e2e_ms, pair_ms, upd_ms = [float(x) for x in tt.tolist()]
     barriers = m.barriers
     row_stride = m.row_stride
+    m.close()
     del m
     torch.cuda.empty_cache()
     if rank != 0:

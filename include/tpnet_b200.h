@@ -155,9 +155,9 @@ int tpn_update(tpn_state_t* st,
 /*   TPN_DEBUG_SNAPSHOT_P0    : the pre-batch snapshot also copies P_0 of every target, so the walkers read ALL
  *                              source rows from one compact buffer (A/B measurements; results are identical). */
 #define TPN_DEBUG_SNAPSHOT_P0 4
-/*   TPN_DEBUG_HEAD_TENSOR    : tpn_head_forward runs on the tcgen05 tensor cores (fp16 x 2 split operands, fp32
- *                              accumulation in TMEM; tpn_head_tc.cu) instead of the packed-FFMA kernel. */
-#define TPN_DEBUG_HEAD_TENSOR 8
+/*   TPN_DEBUG_HEAD_FFMA      : tpn_head_forward runs the packed-FFMA fp32 kernel (tpn_head.cu) instead of the tcgen05
+ *                              tensor-core kernel (fp16 x 2 split operands, fp32 accumulation in TMEM; tpn_head_tc.cu). */
+#define TPN_DEBUG_HEAD_FFMA 8
 int tpn_set_debug_flags(int flags);
 
 
@@ -224,8 +224,10 @@ int tpn_pairwise_neighbors(const tpn_state_t* st, const int64_t* nbr_dev, const 
 
 /*
  * Forward of the pair-wise head `self.mlp` = Linear(F, 4F) -> ReLU -> Linear(4F, F)
- * (TPNet.py:64-65, applied at :125/:129) for INFERENCE: y = W2 relu(W1 x + b1) + b2 in fp32
- * (no TF32), one fused kernel, the hidden layer never leaves the SM.  Training keeps the head in
+ * (TPNet.py:64-65, applied at :125/:129) for INFERENCE: y = W2 relu(W1 x + b1) + b2, one fused kernel on the
+ * tcgen05 tensor cores, the hidden layer never leaves the SM.  fp32-level accuracy without fp32 tensor cores:
+ * every operand is split into two fp16 numbers (22 bits, exact power-of-two scaling), three MMAs per product,
+ * fp32 accumulators in TMEM (csrc/tpn_head_tc.cu; error vs a float64 head is at the level of an fp32 SGEMM's).  Training keeps the head in
  * PyTorch (autograd); callers use this only when no gradient is required.
  *   x_dev   : float32[n][features] device, 16-byte aligned (the output of tpn_pairwise /
  *             tpn_pairwise_neighbors viewed as [n, F])

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Times tpn_head_forward per 100,000 pairs: packed-FFMA kernel vs the tcgen05 kernel (TPN_DEBUG_HEAD_TENSOR), and
+"""Times tpn_head_forward per 100,000 pairs: packed-FFMA kernel (TPN_DEBUG_HEAD_FFMA) vs the tcgen05 kernel (default), and
 torch's own fp32 nn.Sequential (cuBLAS) for reference.  CUDA events, 50 launches each after warm-up."""
 import json
 import os
@@ -44,7 +44,7 @@ out = {'pairs': n, 'flop': 2 * n * (64 * 256 + 256 * 64)}
 with torch.no_grad():
     ref64 = mlp.double()(x.double())
     mlp.float()
-    for name, flag in (('ffma', 0), ('tensor', 8)):
+    for name, flag in (('ffma', 8), ('tensor', 0)):
         old = lib.tpn_set_debug_flags(flag)
         run()
         torch.cuda.synchronize()

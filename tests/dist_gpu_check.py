@@ -84,12 +84,14 @@ def main():
                 if not close:
                     print(f'PAIRWISE MISMATCH mode={mode} N={N}: {(feat - want).abs().max().item()}')
             sh.check_errors()
+            sh.close()                               # unmap the peers' buffers before anyone frees them
+            del sh, full
             flag = torch.tensor([1 if ok else 0], device=dev)
             dist.broadcast(flag, 0)
             ok = bool(flag.item())
             if rank == 0:
                 print(f'exchange={exchange} mode={mode} acc={acc} N={N} B={B} d={dim} L={L} world={world}: '
-                      f'{"ok" if ok else "FAILED"} (barriers on rank 0: {sh.barriers})')
+                      f'{"ok" if ok else "FAILED"}')
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

@@ -478,9 +478,9 @@ def test_pairwise_large_call(N, dim, L, n, mode):
 @pytest.fixture(params=['ffma', 'tensor'])
 def head_kernel(request):
     """Both implementations of tpn_head_forward: packed-FFMA (fp32 CUDA cores) and tcgen05 (fp16 x 2 split operands,
-    fp32 accumulation in TMEM), selected by TPN_DEBUG_HEAD_TENSOR."""
+    fp32 accumulation in TMEM; the default), selected by TPN_DEBUG_HEAD_FFMA."""
     lib = _lib.load()
-    old = lib.tpn_set_debug_flags(8 if request.param == 'tensor' else 0)
+    old = lib.tpn_set_debug_flags(8 if request.param == 'ffma' else 0)
     yield request.param
     lib.tpn_set_debug_flags(old)
 
@@ -773,3 +773,136 @@ def test_full_size_reddit_shape_properties(mode):
     g = f.reshape(-1, 8, 8)
     assert torch.equal(g, g.transpose(1, 2))
     m.check_errors()
+
+
+# --------------------------------------------------------------------------- BASELINE shapes against the oracle
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('name', ['wikipedia', 'reddit', 'flights'])
+def test_baseline_shape_stream_vs_oracle(name, mode):
+    """BASELINE.json configs[0..2] at FULL shape (Wikipedia 9,228 x d=120 L=2; Reddit 10,985 x d=140 L=3; Flights 13,170 x
+    d=150 L=3, day-quantised timestamps): a stream of TPNet batches (B=200) from the bench's own generator, the oracle run
+    beside the CUDA path.  Eager decay: BIT-EXACT after every batch (same rounding points, exp rounded once from f64 on
+    both sides); lazy: rtol 1e-5.  Then the decoder call (B pairs) and the encoder's structured call (2B rows x K=20
+    neighbours = 16,000 pair blocks) against the oracle's features."""
+    from tpnet_b200.synth import SHAPES, RecentNeighbors, edge_stream, tpnet_neighbor_batch
+    shape = SHAPES[name]
+    kw = dict(node_num=shape.node_num, edge_num=shape.edge_num, dim_factor=shape.dim_factor, num_layer=shape.num_layer,
+              time_decay_weight=shape.time_decay_weight, use_matrix=False, beginning_time=0.0, not_scale=False,
+              enforce_dim=-1)
+    o = WalkProjectionOracle(**kw)
+    assert o.dim == shape.dim
+    m = module_from_cfg(kw, o.P[0], mode)
+    nbr = RecentNeighbors(shape.node_num, 20)
+    batches = list(edge_stream(shape, 200, 12, seed=7))
+    if name == 'flights':
+        assert all(len(np.unique(t)) <= 2 for _, _, t in batches)            # day stamps: (almost) all weights are 1
+    for i, (s, d, t) in enumerate(batches):
+        o.update(s, d, t)
+        m.update(s, d, t)
+        nbr.insert(s, d)
+        if i in (0, 5, 11):
+            got = layers(m)
+            if mode == 'eager':
+                for l in range(1, shape.num_layer + 1):
+                    assert np.array_equal(got[l], o.P[l]), (name, i, l)
+            else:
+                assert_layers(got, o.P, mode)
+    s, d, t = batches[-1]
+    rng = np.random.default_rng(3)
+    neg = rng.integers(1, shape.node_num, 200).astype(np.int64)
+    for a, b in ((s, d), (s, neg)):                                          # decoder shape
+        got = m.pair_wise_gram(a, b).cpu().numpy()
+        ref = o.pair_wise_gram(a, b, exact=True)
+        raw = np.expm1(ref.astype(np.float64))
+        tol = 1e-5 * np.abs(ref) + 2e-6 * pair_tol(o, a, b, raw)
+        assert np.all(np.abs(got - ref) <= tol + 1e-7), name
+    nb, s2, d2 = tpnet_neighbor_batch(nbr, s, d)                             # encoder shape: [2B, K] neighbours
+    got = m.neighbor_pair_wise_gram(nb, s2, d2).cpu().numpy().reshape(400, 20, -1)
+    ref = o.neighbor_pair_wise_gram(nb, s2, d2, exact=True)
+    a_ids, b_ids = o.neighbor_pair_lists(nb, s2, d2)
+    raw = np.expm1(o.pair_wise_gram(a_ids, b_ids, exact=True).astype(np.float64))
+    tol = 1e-5 * np.abs(o.pair_wise_gram(a_ids, b_ids, exact=True)) + 2e-6 * pair_tol(o, a_ids, b_ids, raw)
+    F = m.pair_wise_feature_dim
+    tol = np.concatenate([tol[:400 * 20], tol[400 * 20:]], axis=1).reshape(400, 20, 2 * F)
+    assert np.all(np.abs(got - ref) <= tol + 1e-7), name
+    m.check_errors()
+
+
+@pytest.mark.parametrize('accumulation', ['reference', 'chunked'])
+def test_powerlaw_replica_vs_oracle(accumulation):
+    """The headline regime, down-scaled in node count only: power-law graph (zipf 1.2), 100,001 nodes,
+    d=210, L=3, lambda=1e-7, LAZY decay, batches of 100,000 edges (top hub: ~35,600 messages per batch, radix sort,
+    short-segment walker + hub walkers) against the oracle (np.add.at: the reference's sequential order; or the oracle's
+    restatement of the chunked order).  rtol 1e-5 element-wise with an absolute floor of 1e-6 of the layer's largest
+    entry (lazy decay rounds once per read instead of once per update)."""
+    import dataclasses
+    from tpnet_b200.synth import SHAPES, edge_stream
+    shape = dataclasses.replace(SHAPES['powerlaw'], num_src=100_000)
+    kw = dict(node_num=shape.node_num, edge_num=shape.edge_num, dim_factor=shape.dim_factor, num_layer=shape.num_layer,
+              time_decay_weight=shape.time_decay_weight, use_matrix=False, beginning_time=0.0, not_scale=False,
+              enforce_dim=-1)
+    o = WalkProjectionOracle(**kw)
+    assert o.dim == 210
+    m = RandomProjectionModule(device=DEV, decay_mode='lazy', accumulation=accumulation, giant_chunk=1024,
+                               **{**kw, 'beginning_time': np.float64(0.0)})
+    m.random_projections[0].data.copy_(torch.from_numpy(o.P[0]))
+    m = m.to(DEV)
+    chunk = 1024 if accumulation == 'chunked' else 0
+    for s, d, t in edge_stream(shape, 100_000, 3, seed=1234):
+        assert np.bincount(np.concatenate([s, d])).max() > 30000
+        o.update(s, d, t, giant_chunk=chunk)
+        m.update(s, d, t)
+    got = layers(m)
+    for l in range(1, 4):
+        scale = float(np.abs(o.P[l]).max())
+        np.testing.assert_allclose(got[l], o.P[l], rtol=1e-5, atol=1e-6 * scale, err_msg=f'layer {l}')
+    a = np.arange(1, 5001, dtype=np.int64)
+    b = np.random.default_rng(0).integers(1, shape.node_num, 5000).astype(np.int64)
+    got_f = m.pair_wise_gram(a, b).cpu().numpy()
+    ref = o.pair_wise_gram(a, b, exact=True)
+    raw = np.expm1(ref.astype(np.float64))
+    assert np.all(np.abs(got_f - ref) <= 1e-5 * np.abs(ref) + 2e-6 * pair_tol(o, a, b, raw) + 1e-7)
+    m.check_errors()
+
+
+def test_step_graphs_replay_equals_eager_calls():
+    """tpnet_b200.pipeline.StepGraphs: one CUDA graph per batch of a device-resident split (decoder
+    features of the positive / pre-drawn negative pairs + update), replayed in order for two "epochs" (reset in between),
+    against the same calls issued eagerly: features and final state bit-identical; out-of-order replay is refused."""
+    from tpnet_b200.pipeline import EpochBatches, StepGraphs
+    rng = np.random.default_rng(12)
+    N, E, B = 700, 2050, 200
+    src = rng.integers(1, N, E); dst = rng.integers(1, N, E); neg = rng.integers(1, N, E)
+    t = np.sort(rng.random(E) * 5e5)
+    kw = dict(node_num=N, edge_num=E + 1, dim_factor=10, num_layer=3, time_decay_weight=1e-6, use_matrix=False,
+              beginning_time=np.float64(t[0]), not_scale=False, enforce_dim=-1)
+    for mode in MODES:
+        torch.manual_seed(1)
+        m = RandomProjectionModule(device=DEV, decay_mode=mode, **kw).to(DEV)
+        torch.manual_seed(1)
+        e = RandomProjectionModule(device=DEV, decay_mode=mode, **kw).to(DEV)
+        e.load_state_dict(m.state_dict())
+        eb = EpochBatches(src, dst, t, B, DEV, extra={'neg': neg})
+        sg = StepGraphs(m, list(eb))
+        assert len(sg) == 11
+        p0 = m.random_projections[0].data.clone()
+        for epoch in range(2):
+            for b in eb:
+                out = sg.replay(b.index)
+                with torch.no_grad():
+                    want_pos = e.get_pair_wise_feature(b.src, b.dst)
+                    want_neg = e.get_pair_wise_feature(b.src, b.extra['neg'])
+                    e.update(b.src, b.dst, b.t, next_time=b.t_last)
+                assert torch.equal(out['pos'][:len(b)], want_pos) and torch.equal(out['neg'][:len(b)], want_neg), (mode, b.index)
+            assert float(m.now_time) == float(e.now_time) == t[-1]
+            m.materialize(); e.materialize()
+            for i in range(1, 4):
+                assert torch.equal(m.random_projections[i].data, e.random_projections[i].data), (mode, epoch, i)
+            if epoch == 0:
+                with pytest.raises(RuntimeError, match='out of order'):
+                    sg.replay(3)
+                for mod in (m, e):                               # next epoch: same start state (same P_0: copied back)
+                    mod.reset_random_projections()
+                    mod.random_projections[0].data.copy_(p0)
+                sg.rewind()
+        m.check_errors()

@@ -199,7 +199,7 @@ extern "C" int tpn_head_forward(const float* x_dev, int64_t n, const int32_t* n_
         y_dev == nullptr || ((reinterpret_cast<uintptr_t>(x_dev) | reinterpret_cast<uintptr_t>(y_dev)) & 15) != 0)
         return TPN_ERR_INVALID_ARGUMENT;
     DeviceScope scope(x_dev);
-    if (debug_flags() & TPN_DEBUG_HEAD_TENSOR) {
+    if (!(debug_flags() & TPN_DEBUG_HEAD_FFMA)) {
         const int trc = launch_head_tensor(x_dev, n, reinterpret_cast<const int*>(n_dev), w1_dev, b1_dev, w2_dev, b2_dev,
                                            y_dev, scope.slot(), reinterpret_cast<cudaStream_t>(stream_v));
         return trc != TPN_OK ? trc : check_launch();

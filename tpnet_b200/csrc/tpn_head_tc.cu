@@ -5,16 +5,21 @@
 //     v * 2^s = hi + lo,  hi = fp16(v * 2^s),  lo = fp16(v * 2^s - hi)            (22 significant bits, like 3xTF32)
 // with an exact power-of-two scale 2^s (per row for the activations, per matrix for the weights) that keeps hi and lo
 // in fp16's normal range, and each product is issued as THREE tensor-core MMAs with fp32 accumulation in TMEM:
-//     A·B ≈ A_hi·B_hi + A_hi·B_lo + A_lo·B_hi        (the dropped A_lo·B_lo term is 2^-22 relative)
-// The scales are undone exactly in the epilogues.  Error per operand 2^-22 — the same order as the summation-order
-// noise of an fp32 SGEMM over K = 64 / 256 (tests/test_gpu_parity.py compares both with the float64 head).
+//     A·B ≈ A_hi·B_lo + A_lo·B_hi + A_hi·B_hi        (the dropped A_lo·B_lo term is 2^-22 relative)
+// The scales are undone exactly in the epilogues.  The tensor core adds each K = 16 block of products to the fp32
+// accumulator with TRUNCATION (measured: the error of a plain 48-step accumulation, 1.0e-5, is reproduced exactly by
+// an emulation that truncates, 1.1e-5, and not by one that rounds, 2.0e-6), so the number of additions at full
+// magnitude is kept small: the two small cross products go first, the hi·hi product last (4 additions per
+// accumulator instead of 12), and GEMM2 uses one accumulator per 64-column K chunk, summed in fp32 by the epilogue.
+// Measured error against the float64 head: see profiles/r02_head_bench.json (packed-FFMA kernel 2.0e-6, cuBLAS 4.6e-6).
 //
 // One persistent CTA per SM, 128 pairs per tile:
 //   warps 0-3 ("row workers", thread r <-> pair r of the tile <-> TMEM lane r): load and split the X rows into the
 //       canonical K-major shared-memory layout; epilogue 1 (TMEM -> bias + ReLU -> split -> shared memory, in 64-column
 //       chunks that feed GEMM2 while the next chunk is converted); epilogue 2 (TMEM -> bias -> global).
 //   warp 4, one elected thread: issues tcgen05.mma (GEMM1: M128 N256 K16 x 4 k-steps x 3 products into TMEM columns
-//       0..255; GEMM2: M128 N64 K16 x 16 k-steps x 3 products into columns 256..319) and tcgen05.commit to mbarriers.
+//       0..255; GEMM2: M128 N64 K16 x 16 k-steps x 3 products into columns 256..511, one 64-column accumulator per
+//       K chunk) and tcgen05.commit to mbarriers.
 //   Both weight matrices stay in shared memory for the whole launch, split and laid out once per CTA (128 KB).
 // Operand layout: UMMA "K-major, no swizzle" canonical form — 8-row x 16-byte core matrices, consecutive along K
 // (LBO = 128 B), 8-row groups 1024 B apart (SBO) — described to the tensor core by 64-bit shared-memory descriptors.
@@ -31,7 +36,7 @@ constexpr int kF = 64;                 // features in / out
 constexpr int kHid = 256;              // hidden units
 constexpr int kTile = 128;             // pairs per tile = UMMA M = TMEM lanes
 constexpr int kTcThreads = 160;        // 4 row-worker warps + the MMA warp
-constexpr uint32_t kTmemCols = 512;    // D1: 256 columns, D2: 64 columns (allocation: power of two)
+constexpr uint32_t kTmemCols = 512;    // D1: 256 columns; D2: 4 accumulators (one per K chunk) x 64 columns
 constexpr uint32_t kD2Col = 256;
 constexpr uint32_t kLbo = 128;         // bytes between the two 16-byte K chunks of one MMA (core matrices along K)
 constexpr uint32_t kSbo = 1024;        // bytes between 8-row groups (K = 64 halfs = 8 core matrices of 128 B)
@@ -303,7 +308,15 @@ head_tc_kernel(const float* __restrict__ x, long long n, const float* __restrict
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 float d[32];
-                tmem_ld32(tmem + lane_base + kD2Col + (uint32_t)(half * 32), d);
+                {   // the four K-chunk accumulators, summed pairwise in fp32 (round to nearest)
+                    float d1[32], d2[32], d3[32];
+                    tmem_ld32(tmem + lane_base + kD2Col + (uint32_t)(half * 32), d);
+                    tmem_ld32(tmem + lane_base + kD2Col + 64u + (uint32_t)(half * 32), d1);
+                    tmem_ld32(tmem + lane_base + kD2Col + 128u + (uint32_t)(half * 32), d2);
+                    tmem_ld32(tmem + lane_base + kD2Col + 192u + (uint32_t)(half * 32), d3);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) d[j] = (d[j] + d1[j]) + (d2[j] + d3[j]);
+                }
                 if (valid) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -324,12 +337,17 @@ head_tc_kernel(const float* __restrict__ x, long long n, const float* __restrict
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             mbar_wait_bounded(&sm.x_full, it & 1u);
             tc_fence_after();
+            // small cross products first, hi * hi last: only its 4 additions happen at full accumulator magnitude
 #pragma unroll
             for (int ks = 0; ks < kF / 16; ++ks) {
                 const uint64_t adv = (uint64_t)((ks * kKStepBytes) >> 4);
-                mma_f16(tmem, xa[0] + adv, wb[0] + adv, idesc1, ks > 0 ? 1u : 0u);       // hi * hi
-                mma_f16(tmem, xa[0] + adv, wb[1] + adv, idesc1, 1u);                    // hi * lo
+                mma_f16(tmem, xa[0] + adv, wb[1] + adv, idesc1, ks > 0 ? 1u : 0u);       // hi * lo
                 mma_f16(tmem, xa[1] + adv, wb[0] + adv, idesc1, 1u);                    // lo * hi
+            }
+#pragma unroll
+            for (int ks = 0; ks < kF / 16; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * kKStepBytes) >> 4);
+                mma_f16(tmem, xa[0] + adv, wb[0] + adv, idesc1, 1u);                    // hi * hi
             }
             mma_commit(&sm.d1_full);
 #pragma unroll 1
@@ -340,12 +358,17 @@ head_tc_kernel(const float* __restrict__ x, long long n, const float* __restrict
                 tc_fence_after();
                 const uint64_t ha[2] = {smem_desc(sm.h[buf][0]), smem_desc(sm.h[buf][1])};
                 const uint64_t vb[2] = {smem_desc(sm.w2[0][c]), smem_desc(sm.w2[1][c])};
+                const uint32_t dacc = tmem + kD2Col + (uint32_t)(c * 64);       // this chunk's own accumulator
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * kKStepBytes) >> 4);
-                    mma_f16(tmem + kD2Col, ha[0] + adv, vb[0] + adv, idesc2, (c > 0 || ks > 0) ? 1u : 0u);
-                    mma_f16(tmem + kD2Col, ha[0] + adv, vb[1] + adv, idesc2, 1u);
-                    mma_f16(tmem + kD2Col, ha[1] + adv, vb[0] + adv, idesc2, 1u);
+                    mma_f16(dacc, ha[0] + adv, vb[1] + adv, idesc2, ks > 0 ? 1u : 0u);  // hi * lo
+                    mma_f16(dacc, ha[1] + adv, vb[0] + adv, idesc2, 1u);                // lo * hi
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t adv = (uint64_t)((ks * kKStepBytes) >> 4);
+                    mma_f16(dacc, ha[0] + adv, vb[0] + adv, idesc2, 1u);                // hi * hi
                 }
                 mma_commit(&sm.h_empty[buf]);
             }

@@ -1,4 +1,5 @@
-"""Device-resident batch pipeline.
+"""Device-resident batch pipeline: ``EpochBatches`` (a split uploaded once) and
+``StepGraphs`` (the per-batch sequence of the hot path captured as one CUDA graph per batch).
 
 The reference converts every batch's id / timestamp arrays to tensors and copies them to the device
 inside the batch loop (``train_link_prediction.py:262-276``, ``models/TPNet.py:74-77``).  ``EpochBatches``
@@ -11,7 +12,7 @@ TPNet.py:84-85) is read from the host copy of the timestamps.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, Iterator, Optional, Union
+from typing import Callable, Dict, Iterator, List, Optional, Sequence, Union
 
 import numpy as np
 import torch
@@ -82,3 +83,88 @@ def replay_updates(module, batches: EpochBatches) -> None:
     """``module.update`` over a resident split (e.g. rebuilding the walk state after a reload)."""
     for b in batches:
         module.update(b.src, b.dst, b.t, next_time=b.t_last)
+
+
+def tpnet_step(module, batch: Batch, out: Dict[str, torch.Tensor]) -> None:
+    """The hot-path calls of one TPNet batch under ``torch.no_grad()`` (evaluate_models_utils.py:64-184): decoder
+    features of the positive and the negative pairs, then the update.  ``batch.extra['neg']`` holds the pre-drawn
+    negative destinations (the evaluation samplers are seeded, utils/utils.py:339-359: the same negatives every epoch)."""
+    module.get_pair_wise_feature(batch.src, batch.dst, out=out['pos'][:len(batch)])
+    module.get_pair_wise_feature(batch.src, batch.extra['neg'], out=out['neg'][:len(batch)])
+    module.update(batch.src, batch.dst, batch.t, next_time=batch.t_last)
+
+
+class StepGraphs:
+    """One CUDA graph per batch of a FIXED stream of device-resident batches (a validation / test split, or a
+    training epoch with pre-drawn negatives): the per-batch sequence of hot-path calls is captured once, in stream
+    order, and replayed every epoch — the host's work per batch is one graph launch instead of ~10-40 kernel
+    launches with their argument marshalling (what ``bench.py`` times as `value`).
+
+    * ``step(module, batch, out)`` issues the calls of one batch (default: ``tpnet_step``) and writes its results
+      into ``out`` — ONE set of buffers shared by all graphs (``out=`` arguments of the feature calls), read by the
+      caller after ``replay(i)`` and before ``replay(i + 1)``.
+    * The graphs bake in what the host computes per update (the f64 decay factors of TPNet.py:84-85, the lazy-decay
+      epoch), so they are valid for ONE trajectory of the clock: replay them in order, starting from the state the
+      module had at capture time (e.g. right after ``reset_random_projections()`` or ``reload_random_projections``
+      of the same backup).  ``replay`` enforces the order; ``rewind()`` re-arms the sequence after the caller has
+      put the module back into the starting state.
+    """
+
+    def __init__(self, module, batches: Sequence[Batch], step: Callable = tpnet_step,
+                 out: Optional[Dict[str, torch.Tensor]] = None):
+        dev = module._require_cuda()
+        self.module = module
+        self.batches = list(batches)
+        if not self.batches:
+            raise ValueError('no batches to capture')
+        bmax = max(len(b) for b in self.batches)
+        f = module.pair_wise_feature_dim
+        self.out = out if out is not None else {
+            'pos': torch.empty(bmax, f, dtype=torch.float32, device=dev),
+            'neg': torch.empty(bmax, f, dtype=torch.float32, device=dev)}
+        h = module._h
+        module._c_state()                                    # workspaces / stamps exist before any capture
+        start = (h.now, h.epoch, float(h.st.cum_floor) if h.st is not None else 1.0, module.now_time.data.clone())
+        self._start = start
+        self._after: List[tuple] = []
+        self.graphs: List[torch.cuda.CUDAGraph] = []
+        pool = torch.cuda.graph_pool_handle()                # graphs replay in capture order: they can share memory
+        side = torch.cuda.Stream(dev)
+        with torch.no_grad(), torch.cuda.stream(side):
+            module._warm_buffers(bmax)                       # nothing is allocated lazily inside a capture
+            side.synchronize()
+            for b in self.batches:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, stream=side):
+                    step(module, b, self.out)
+                self.graphs.append(g)
+                self._after.append((h.now, h.epoch, float(h.st.cum_floor)))
+        torch.cuda.synchronize(dev)
+        self._restore(start[:3], start[3])
+        self._next = 0
+
+    def _restore(self, host, now_tensor=None) -> None:
+        h = self.module._h
+        h.now, h.epoch = host[0], host[1]
+        if h.st is not None:
+            h.st.epoch = host[1]
+            h.st.cum_floor = host[2]
+        if now_tensor is not None:
+            self.module.now_time.data.copy_(now_tensor)
+
+    def __len__(self) -> int:
+        return len(self.graphs)
+
+    def replay(self, i: int) -> Dict[str, torch.Tensor]:
+        if i != self._next:
+            raise RuntimeError(f'StepGraphs replay out of order: batch {i} requested, batch {self._next} is next '
+                               f'(the graphs bake in the clock trajectory; call rewind() after restoring the start state)')
+        self.graphs[i].replay()
+        self._restore(self._after[i])                        # host mirrors follow the device state
+        self._next += 1
+        return self.out
+
+    def rewind(self) -> None:
+        """Call after the module is back in the state it had at capture time (reset / reload of the same backup)."""
+        self._restore(self._start[:3], self._start[3])
+        self._next = 0

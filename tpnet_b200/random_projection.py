@@ -394,14 +394,24 @@ class RandomProjectionModule(nn.Module):
             self._h.launches += 1
         return [out[i] for i in range(self.num_layer + 1)]
 
-    def pair_wise_gram(self, src_node_ids: IdArray, dst_node_ids: IdArray) -> torch.Tensor:
+    def _out(self, out: Optional[torch.Tensor], shape) -> torch.Tensor:
+        """Result buffer of a feature call: a fresh tensor, or the caller's (``out=``: fixed addresses for CUDA graphs)."""
+        dev = self._state.device
+        if out is None:
+            return torch.empty(*shape, dtype=torch.float32, device=dev)
+        if tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 or out.device != dev or not out.is_contiguous():
+            raise ValueError(f'out must be a contiguous float32 tensor of shape {tuple(shape)} on {dev}')
+        return out
+
+    def pair_wise_gram(self, src_node_ids: IdArray, dst_node_ids: IdArray, out: Optional[torch.Tensor] = None
+                       ) -> torch.Tensor:
         """The input of ``self.mlp``: TPNet.py:119-128 (everything before the head)."""
         dev = self._require_cuda()
         lib = _lib.load()
         n = int(len(src_node_ids))
         if len(dst_node_ids) != n:
             raise ValueError('src and dst id arrays must have the same length')
-        out = torch.empty(n, self.pair_wise_feature_dim, dtype=torch.float32, device=dev)
+        out = self._out(out, (n, self.pair_wise_feature_dim))
         if n:
             ptrs = self._ids_to_device([src_node_ids, dst_node_ids], ['id', 'id'])
             rc = lib.tpn_pairwise(self._c_state(), ptrs[0], ptrs[1], n, None, 0 if self.not_scale else 1,
@@ -411,13 +421,15 @@ class RandomProjectionModule(nn.Module):
             self._h.launches += 1
         return out
 
-    def _head(self, gram: torch.Tensor, count: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def _head(self, gram: torch.Tensor, count: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None
+              ) -> torch.Tensor:
         """``self.mlp`` on ``[n, F]`` features (TPNet.py:125/:129).  With autograd on (training) it is
         the PyTorch module; under ``torch.no_grad()`` the default-shape head (F = 64) runs as one
         fused fp32 kernel (``tpn_head_forward``).  ``count``: device int32 with the number of valid rows
         (routed calls of the sharded module; rows past it are left zero by the fused kernel)."""
         if torch.is_grad_enabled() or not self.fused_head or gram.shape[0] == 0:
-            return self.mlp(gram)
+            res = self.mlp(gram)
+            return res if out is None else out.copy_(res)
         mlp = self.mlp
         if not (isinstance(mlp, nn.Sequential) and len(mlp) == 3 and isinstance(mlp[0], nn.Linear)
                 and isinstance(mlp[1], nn.ReLU) and isinstance(mlp[2], nn.Linear)):
@@ -429,7 +441,10 @@ class RandomProjectionModule(nn.Module):
               and all(t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.device == gram.device
                       for t in (gram, l1.weight, l1.bias, l2.weight, l2.bias)))
         if ok:
-            out = torch.empty_like(gram) if count is None else torch.zeros_like(gram)
+            if out is None:
+                out = torch.empty_like(gram) if count is None else torch.zeros_like(gram)
+            elif out.shape != gram.shape or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError('out must be a contiguous float32 tensor of the shape of the features')
             rc = _lib.load().tpn_head_forward(gram.data_ptr(), gram.shape[0],
                                               None if count is None else count.data_ptr(), f, hid,
                                               l1.weight.data_ptr(),
@@ -440,12 +455,14 @@ class RandomProjectionModule(nn.Module):
                 return out
             if rc != _lib.TPN_ERR_UNSUPPORTED:
                 _lib.check(rc, 'tpn_head_forward')
-        return self.mlp(gram)
+        res = self.mlp(gram)
+        return res if out is None else out.copy_(res)
 
-    def get_pair_wise_feature(self, src_node_ids: IdArray, dst_node_ids: IdArray) -> torch.Tensor:
+    def get_pair_wise_feature(self, src_node_ids: IdArray, dst_node_ids: IdArray, out: Optional[torch.Tensor] = None
+                              ) -> torch.Tensor:
         """TPNet.py:112-129.  Gradients flow to ``self.mlp`` only, as in the reference
-        (the projections are ``requires_grad=False``)."""
-        return self._head(self.pair_wise_gram(src_node_ids, dst_node_ids))
+        (the projections are ``requires_grad=False``).  ``out`` (no-grad calls): result buffer to write into."""
+        return self._head(self.pair_wise_gram(src_node_ids, dst_node_ids), out=out)
 
     def neighbor_pair_wise_gram(self, neighbor_node_ids: IdArray, src_node_ids: IdArray,
                                 dst_node_ids: IdArray) -> torch.Tensor:
@@ -481,7 +498,7 @@ class RandomProjectionModule(nn.Module):
         return out
 
     def get_neighbor_pair_wise_feature(self, neighbor_node_ids: IdArray, src_node_ids: IdArray,
-                                       dst_node_ids: IdArray) -> torch.Tensor:
+                                       dst_node_ids: IdArray, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Drop-in for TPNet.py:313-324: returns ``neighbor_random_features`` ``[m, K, 2F]`` — what
         the reference obtains from ``get_pair_wise_feature(np.tile(nbr.reshape(-1), 2),
         np.concatenate([np.repeat(src, K), np.repeat(dst, K)]))`` followed by the split / ``cat`` /
@@ -489,7 +506,9 @@ class RandomProjectionModule(nn.Module):
         ``[m*K*2, F]`` view (same values, same gradients to the head)."""
         g = self.neighbor_pair_wise_gram(neighbor_node_ids, src_node_ids, dst_node_ids)
         m, k = g.shape[0], g.shape[1]
-        return self._head(g.view(m * k * 2, self.pair_wise_feature_dim)).view(m, k, 2 * self.pair_wise_feature_dim)
+        f = self.pair_wise_feature_dim
+        flat_out = None if out is None else out.view(m * k * 2, f)
+        return self._head(g.view(m * k * 2, f), out=flat_out).view(m, k, 2 * f)
 
     def reset_random_projections(self):
         """TPNet.py:131-139.  (Called once per epoch by train_link_prediction.py:248: also the point where
@@ -527,6 +546,21 @@ class RandomProjectionModule(nn.Module):
             for i in range(1, self.num_layer + 1):
                 self.random_projections[i].copy_(layers[i - 1])
         self._after_external_write()
+
+    def _warm_buffers(self, batch: int) -> None:
+        """Everything a later call would allocate lazily, allocated now (before a CUDA-graph capture): the C state
+        mirror, the error flag, the update workspace for `batch` edges; one read-only feature call initialises the
+        kernels' per-device attributes."""
+        dev = self._require_cuda()
+        lib = _lib.load()
+        st = self._c_state()
+        need = lib.tpn_update_workspace_bytes(st, max(int(batch), 1))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+        self._ws_batch = max(self._ws_batch, int(batch))
+        ids = torch.zeros(max(int(batch), 1), dtype=torch.int64, device=dev)
+        with torch.no_grad():
+            self.get_pair_wise_feature(ids, ids)
 
     # ------------------------------------------------------------------ lazy-decay maintenance
     def materialize(self) -> None:

@@ -340,6 +340,28 @@ class ShardedRandomProjection(RandomProjectionModule):
         self._shard = sh
         self._peers.barrier()            # every rank has mapped every buffer before anyone launches a pull
 
+    def close(self) -> None:
+        """Collective teardown of the peer data plane: every rank stops using its peers' memory, unmaps it, and only
+        then may anyone free its buffers (freeing an exported allocation that a peer still maps is undefined).  Call
+        it on every rank before dropping the module when another sharded module will be created in the same job."""
+        if self._shard is None or self._peers is None:
+            return
+        if self._state.is_cuda:
+            torch.cuda.synchronize(self._state.device)
+        self._peers.barrier()
+        if hasattr(self._peers, 'close'):
+            self._peers.close()
+        self._peers.barrier()
+        self._shard = None
+        self._shard_tensors = {}
+
+    def __del__(self):
+        try:                                       # best effort without the barriers (interpreter shutdown, errors)
+            if getattr(self, '_shard', None) is not None and hasattr(self._peers, 'close'):
+                self._peers.close()
+        except Exception:
+            pass
+
     def _c_shard(self):
         if self._shard is None:
             self.connect()
