@@ -737,9 +737,27 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
         block_bytes = (shape.num_layer + 1) * m.row_stride * 4
         m._state_written()
         dist.barrier()
-        tt = torch.tensor([rows_pairs, rows_pos, pull_ms], dtype=torch.float64, device=device)
+        # where an eager update spends its time: routing + pull | barrier | rank-local kernels
+        ue = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        with torch.no_grad():
+            m.routed_pair_wise_feature(st['src'], st['dst'])          # as in a step: the update finds its rows cached
+        torch.cuda.synchronize()
+        dist.barrier()
+        ue[0].record()
+        pending = m.update_begin(st['src'], st['dst'], st['t'], st['t_last'])
+        ue[1].record()
+        m._barrier()
+        ue[2].record()
+        m.update_end(pending)
+        ue[3].record()
+        m._barrier()
+        ue[4].record()
+        torch.cuda.synchronize()
+        upd_parts = [ue[i].elapsed_time(ue[i + 1]) for i in range(4)]
+        dist.barrier()
+        tt = torch.tensor([rows_pairs, rows_pos, pull_ms] + upd_parts, dtype=torch.float64, device=device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        rows_pairs, rows_pos, pull_ms = [float(x) for x in tt.tolist()]
+        rows_pairs, rows_pos, pull_ms, *upd_parts = [float(x) for x in tt.tolist()]
         exch = {'data_plane': 'device-side routing + NVLink pulls out of the owners\' HBM (IPC-mapped peer memory) + '
                               'flag barriers; no NCCL in the step',
                 'rows_cached_per_rank_per_step': rows_pairs, 'bytes_per_rank_per_step': rows_pairs * block_bytes,
@@ -747,6 +765,8 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
                                           'achieved_GBps': rows_pos * block_bytes / (pull_ms * 1e-3) / 1e9,
                                           'peak_GBps': NVLINK_GBS,
                                           'note': 'upper bound on bytes: never-written rows are not fetched'},
+                'eager_update_ms': {'route_and_pull': upd_parts[0], 'barrier': upd_parts[1], 'rank_local_kernels': upd_parts[2],
+                                    'barrier_back_to_back': upd_parts[3]},
                 'barriers_per_step': 2}
 
     # end to end: numpy API, routing inside the timed region, head + scalar read-back

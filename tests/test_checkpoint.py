@@ -26,7 +26,9 @@ def test_roundtrip_single_file(tmp_path):
     path = ck.save_checkpoint(a, str(tmp_path), 'ep3')
     assert path.endswith('ep3.rank0-of-1.pt')
     payload = torch.load(path, weights_only=True)
-    assert payload['state'].shape == (53, 3, a.dim)                 # stored once, pad columns dropped
+    assert payload['format'] == ck.FORMAT and payload['rows'] == 53 and 'state' not in payload
+    import os
+    assert os.path.getsize(ck.state_path(path)) == 53 * 3 * a.dim * 4   # stored once, raw fp32, pad columns dropped
     ck.load_checkpoint(b, str(tmp_path), 'ep3')
     for i in range(3):
         assert torch.equal(a.random_projections[i].data, b.random_projections[i].data)
@@ -68,3 +70,22 @@ def test_incomplete_or_mismatched_checkpoints_are_refused(tmp_path):
     ck.save_checkpoint(a, str(tmp_path), 'y')
     with pytest.raises(ValueError, match='checkpoint is for'):
         ck.load_checkpoint(make(node_num=54), str(tmp_path), 'y')
+
+
+def test_chunked_state_file_and_v1_compatibility(tmp_path):
+    """Tiny chunk size: many chunks, ragged last one; and a v1 file (state inside the header) still loads."""
+    a, b, c = make(seed=3, node_num=101), make(seed=4, node_num=101), make(seed=5, node_num=101)
+    ck.save_checkpoint(a, str(tmp_path), 'small_chunks', chunk_bytes=7 * 3 * a.dim * 4)       # 7 rows per chunk
+    ck.load_checkpoint(b, str(tmp_path), 'small_chunks', chunk_bytes=5 * 3 * a.dim * 4)
+    for i in range(3):
+        assert torch.equal(a.random_projections[i].data, b.random_projections[i].data)
+    v1 = ck.pack_shard(a._state[:, :, :a.dim].clone(), 1, 0, 101, 99.25, 12.5, a.mlp.state_dict())
+    torch.save(v1, ck.shard_path(str(tmp_path), 'old', 0, 1))
+    ck.load_checkpoint(c, str(tmp_path), 'old')
+    for i in range(3):
+        assert torch.equal(a.random_projections[i].data, c.random_projections[i].data)
+    # a truncated state file is refused
+    with open(ck.state_path(ck.shard_path(str(tmp_path), 'small_chunks', 0, 1)), 'r+b') as fh:
+        fh.truncate(100)
+    with pytest.raises(ValueError, match='bytes, expected'):
+        ck.load_checkpoint(b, str(tmp_path), 'small_chunks')

@@ -398,12 +398,8 @@ extern "C" int tpn_peer_barrier(const tpn_shard_t* sh, void* stream_v) {
     if (rc != TPN_OK) return rc;
     if (sh->peer_flags == nullptr || sh->barrier_seq == nullptr) return TPN_ERR_INVALID_ARGUMENT;
     DeviceScope scope(sh->mark);
-    int khz = 0, dev = 0;
-    long long limit = 4000000000ll;                    // ~2 s of SM clock
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) == cudaSuccess && khz > 0)
-        limit = (long long)khz * 2000ll;               // kHz * 2000 = cycles in 2 s
-    else
-        (void)cudaGetLastError();
+    // ~2 s of SM clock at 2 GHz (a constant: querying the clock rate costs about a millisecond of host time per call)
+    const long long limit = 4000000000ll;
     peer_barrier_kernel<<<1, 64, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(make_shard_view(sh), limit);
     return check_launch();
 }

@@ -3,12 +3,19 @@
 The sharded data plane reads other ranks' rows straight out of their HBM over NVLink, so every rank's state,
 stamps and barrier words must be mapped into every other rank's address space:
 
-  * ``PeerBuffer``      — device memory owned by the library (``tpn_peer_alloc``: plain ``cudaMalloc``, so that
-                          the whole allocation can be exported with CUDA IPC), handed to PyTorch as a tensor
-                          through ``__cuda_array_interface__``; freed when the last tensor view dies.
-  * ``IpcPeerGroup``    — one process per GPU (torchrun): the 64-byte IPC handles travel through the process
-                          group (``all_gather_object``), each rank opens its peers' handles
-                          (``cudaIpcOpenMemHandle`` with lazy peer access) and gets plain device pointers.
+  * ``PeerBuffer``      — peer-visible device memory, handed to PyTorch as a tensor.  ``symmetric=True`` (what a
+                          one-process-per-GPU job uses): ``torch.distributed._symmetric_memory.empty`` —
+                          cuMemCreate / cuMemMap allocations with 2 MiB pages.  Otherwise memory owned by the
+                          library (``tpn_peer_alloc``: plain ``cudaMalloc``, exportable with legacy CUDA IPC),
+                          viewed through ``__cuda_array_interface__``.
+  * ``SymmPeerGroup``   — one process per GPU (torchrun), the default: ``symmetric_memory.rendezvous`` maps every
+                          rank's buffer into every other rank and returns plain device pointers.  MEASURED
+                          (scripts/peer_probe.py, profiles/r02_peer_probe.json): random 3.4 KB row blocks out of a
+                          14 GB peer buffer are pulled at 640 GB/s through this mapping, but only at 171 GB/s
+                          through a legacy-IPC mapping of the same buffer (consecutive rows: 647 GB/s on both) —
+                          the IPC mapping is TLB-bound for random access.
+  * ``IpcPeerGroup``    — the same rendezvous with legacy CUDA IPC handles (``cudaIpcOpenMemHandle``), kept for
+                          setups without symmetric-memory support; see the measurement above.
   * ``LocalPeerGroup``  — all ranks inside ONE process (several ranks may even share one GPU): the "peer"
                           pointers are simply the other ranks' pointers.  This is how the single-GPU test box
                           runs the complete routed data plane (routing, pulls, barriers, device-side counts);
@@ -30,12 +37,20 @@ _ITEMSIZE = {torch.float32: 4, torch.int32: 4, torch.uint8: 1, torch.int64: 8, t
 class PeerBuffer:
     """Zero-filled device memory from ``tpn_peer_alloc`` on ``device``; ``tensor(shape, dtype)`` views it."""
 
-    def __init__(self, nbytes: int, device: torch.device):
+    def __init__(self, nbytes: int, device: torch.device, symmetric: bool = False):
         self._lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('peer-visible memory lives on CUDA devices only')
-        self.nbytes = max(int(nbytes), 16)
+        self.nbytes = (max(int(nbytes), 16) + 15) // 16 * 16
+        self.symmetric = bool(symmetric)
+        self._t = None
+        if self.symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self._t = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+            self._t.zero_()
+            self.ptr = int(self._t.data_ptr())
+            return
         ptr = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.tpn_peer_alloc(ctypes.byref(ptr), self.nbytes), 'tpn_peer_alloc')
@@ -47,6 +62,8 @@ class PeerBuffer:
             numel *= int(s)
         if numel * _ITEMSIZE[dtype] > self.nbytes:
             raise ValueError('view larger than the buffer')
+        if self._t is not None:
+            return self._t[:numel * _ITEMSIZE[dtype]].view(dtype).view(*[int(s) for s in shape])
         holder = _ArrayView(self, tuple(int(s) for s in shape), _TYPESTR[dtype])
         return torch.as_tensor(holder, device=self.device)
 
@@ -57,7 +74,10 @@ class PeerBuffer:
 
     def __del__(self):
         try:
-            if getattr(self, 'ptr', 0):
+            if getattr(self, '_t', None) is not None:
+                self._t = None
+                self.ptr = 0
+            elif getattr(self, 'ptr', 0):
                 self._lib.tpn_peer_free(self.ptr)
                 self.ptr = 0
         except Exception:  # interpreter shutdown
@@ -116,8 +136,40 @@ class LocalPeerGroup(PeerGroup):
         return [int(p) for p in ptrs]
 
 
+class SymmPeerGroup(PeerGroup):
+    """One process per GPU: torch symmetric memory maps every rank's buffer into every other rank (2 MiB pages).
+    Buffers must be ``PeerBuffer(..., symmetric=True)`` of the same size on every rank; ``exchange`` is collective."""
+    symmetric = True
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self._handles = []
+
+    def exchange(self, name: str, buf: PeerBuffer) -> List[int]:
+        import torch.distributed._symmetric_memory as symm_mem
+        if buf._t is None:
+            raise ValueError('SymmPeerGroup needs PeerBuffer(..., symmetric=True)')
+        hdl = symm_mem.rendezvous(buf._t, self.group)
+        self._handles.append(hdl)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != buf.ptr:
+            raise RuntimeError(f'symmetric-memory rendezvous of "{name}" returned an unexpected pointer table')
+        return ptrs
+
+    def barrier(self) -> None:
+        self._dist.barrier(group=self.group)
+
+    def close(self) -> None:
+        self._handles = []
+
+
 class IpcPeerGroup(PeerGroup):
-    """One process per GPU: pointers of the other ranks' buffers through CUDA IPC."""
+    """One process per GPU: pointers of the other ranks' buffers through legacy CUDA IPC (see the module docstring
+    for why this is not the default)."""
 
     def __init__(self, group=None):
         import torch.distributed as dist

@@ -33,7 +33,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .peer import IpcPeerGroup, LocalPeerGroup, PeerBuffer, PeerGroup
+from .peer import IpcPeerGroup, LocalPeerGroup, PeerBuffer, PeerGroup, SymmPeerGroup
 from .random_projection import _DEFAULT_LOG_EPOCHS, RandomProjectionModule, _round_up
 
 
@@ -228,11 +228,14 @@ class ShardedRandomProjection(RandomProjectionModule):
             mine = None
         state_buffer = None
         self._peer_bufs = {}
+        # one process per GPU: symmetric memory (2 MiB pages; the legacy-IPC mapping is TLB-bound, peer.py);
+        # an explicit PeerGroup (in-process ranks, IPC) brings its own kind of buffer
+        self._symmetric = exchange == 'peer' and (peers is None or getattr(peers, 'symmetric', False))
+        self._rows_alloc = rows_on_rank(self.global_node_num, self.world, 0) + self.ext_rows      # same on every rank
         if exchange == 'peer':
-            # peer-visible state: plain cudaMalloc memory (exportable with CUDA IPC), viewed as a tensor
             rows = self.n_local + self.ext_rows
             stride = _round_up(dim, 8)
-            buf = PeerBuffer(rows * (num_layer + 1) * stride * 4, sdev)
+            buf = PeerBuffer(self._rows_alloc * (num_layer + 1) * stride * 4, sdev, symmetric=self._symmetric)
             self._peer_bufs['state'] = buf
             state_buffer = buf.tensor((rows, num_layer + 1, stride), torch.float32)
         super().__init__(node_num=self.n_local + self.ext_rows, edge_num=edge_num, dim_factor=dim_factor,
@@ -257,12 +260,12 @@ class ShardedRandomProjection(RandomProjectionModule):
         if exchange == 'peer':
             if self.lazy:
                 # stamps live in peer memory too (a puller copies them with the rows); -1 = never written
-                sb = PeerBuffer(self.node_num * self.num_layer * 4, sdev)
+                sb = PeerBuffer(self._rows_alloc * self.num_layer * 4, sdev, symmetric=self._symmetric)
                 self._peer_bufs['stamps'] = sb
                 self._stamps = sb.tensor((self.node_num, self.num_layer), torch.int32)
                 self._stamps.fill_(-1)
                 self._decay_log = torch.ones(_DEFAULT_LOG_EPOCHS, self.num_layer, dtype=torch.float64, device=sdev)
-            self._peer_bufs['flags'] = PeerBuffer(4 * max(self.world, 16), sdev)
+            self._peer_bufs['flags'] = PeerBuffer(4 * max(self.world, 16), sdev, symmetric=self._symmetric)
 
     # ------------------------------------------------------------------ helpers
     def init_p0_on_device(self, seed: int) -> None:
@@ -313,7 +316,7 @@ class ShardedRandomProjection(RandomProjectionModule):
         if self._peers is None:
             if not dist.is_initialized():
                 raise RuntimeError("exchange='peer' with world > 1 needs torch.distributed or a PeerGroup")
-            self._peers = IpcPeerGroup(self.group)
+            self._peers = SymmPeerGroup(self.group)
         tables = {}
         for name in ('state', 'stamps', 'flags'):
             if name in self._peer_bufs:
@@ -519,7 +522,8 @@ class ShardedRandomProjection(RandomProjectionModule):
 
     def _global_ids_to_device(self, arrays, kinds):
         """Like _ids_to_device, for GLOBAL ids: host arrays are range-checked against the global node count."""
-        if (self.exchange == 'peer' and self.world > 1 and dist.is_initialized() and isinstance(self._peers, IpcPeerGroup)
+        if (self.exchange == 'peer' and self.world > 1 and dist.is_initialized()
+                and isinstance(self._peers, (IpcPeerGroup, SymmPeerGroup))
                 and all(isinstance(a, np.ndarray) and a.ndim == 1 for a in arrays)
                 and arrays[0].shape[0] >= self.SLICED_UPLOAD_MIN
                 and all(a.shape[0] == arrays[0].shape[0] for a in arrays)):
