@@ -345,22 +345,15 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True, sampler_leg=False)
         m.update(s, d, t)
     torch.cuda.synchronize()
 
+    from tpnet_b200.pipeline import StepGraphs
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     dsteps = [to_dev(st, device) for st in steps[:K + W]]
-    graphs = []
+    # the product's per-batch CUDA graphs (tpnet_b200/pipeline.py) around this workload's step
+    sg = StepGraphs(m, dsteps, step=lambda mod, ds, out: resident_step(mod, ds), out={}, max_batch=BATCH)
     side = torch.cuda.Stream(device)
-    pool = torch.cuda.graph_pool_handle()       # graphs replay in capture order, so they can share memory
-    with torch.cuda.stream(side):
-        resident_step(m, dsteps[0])             # allocations / attribute opt-ins happen outside the captures
-        side.synchronize()
-        for ds in dsteps:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool, stream=side):
-                resident_step(m, ds)
-            graphs.append(g)
-    torch.cuda.synchronize()
-    for g in graphs[:W]:
-        g.replay()
+    pool = torch.cuda.graph_pool_handle()
+    for i in range(W):
+        sg.replay(i)
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     wall0 = time.perf_counter()
@@ -368,7 +361,7 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True, sampler_leg=False)
         if not args.no_flush:
             flush.zero_()                                   # evict the 126 MB L2 between steps (untimed)
         ev[k][0].record()
-        graphs[W + k].replay()
+        sg.replay(W + k)
         ev[k][1].record()
     torch.cuda.synchronize()
     wall1 = time.perf_counter()
@@ -421,7 +414,7 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True, sampler_leg=False)
                    'num_layer': shape.num_layer, 'node_num': shape.node_num, 'parallelism': 'single GPU',
                    'decay_mode': 'lazy' if m.lazy else 'eager',
                    'l2': 'warm (no flush)' if args.no_flush else 'flushed between steps (256 MiB memset, untimed)',
-                   'timing': 'CUDA events per step, one CUDA graph per step',
+                   'timing': 'CUDA events per step, one CUDA graph per step (tpnet_b200.pipeline.StepGraphs)',
                    'algorithmic_bytes_per_step': step_bytes,
                    'wall_ms_per_step_incl_flush': (wall1 - wall0) * 1e3 / K},
         'pairs_per_s': pps * K / (dev_ms * 1e-3),
@@ -455,7 +448,7 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True, sampler_leg=False)
                                'at_reference_threads': {'value': BATCH / sec3, 'cores': REF_THREADS,
                                                         'note': 'torch.set_num_threads(3), the reference\'s own setting '
                                                                 '(train_link_prediction.py:124)'}}
-    del graphs, pair_graphs, m, flush
+    del sg, pair_graphs, m, flush
     torch.cuda.empty_cache()
     return out
 

@@ -110,14 +110,16 @@ class StepGraphs:
       put the module back into the starting state.
     """
 
-    def __init__(self, module, batches: Sequence[Batch], step: Callable = tpnet_step,
-                 out: Optional[Dict[str, torch.Tensor]] = None):
+    def __init__(self, module, batches: Sequence, step: Callable = tpnet_step,
+                 out: Optional[Dict[str, torch.Tensor]] = None, max_batch: Optional[int] = None):
+        """``batches``: ``Batch`` objects (``EpochBatches``) for the default step, or whatever a custom ``step``
+        consumes (then pass ``out`` — possibly empty — and ``max_batch``, the largest number of edges per update)."""
         dev = module._require_cuda()
         self.module = module
         self.batches = list(batches)
         if not self.batches:
             raise ValueError('no batches to capture')
-        bmax = max(len(b) for b in self.batches)
+        bmax = int(max_batch) if max_batch is not None else max(len(b) for b in self.batches)
         f = module.pair_wise_feature_dim
         self.out = out if out is not None else {
             'pos': torch.empty(bmax, f, dtype=torch.float32, device=dev),

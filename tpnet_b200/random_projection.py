@@ -520,7 +520,7 @@ class RandomProjectionModule(nn.Module):
         _lib.check(lib.tpn_clear_walk_layers(self._c_state(), self._stream()), 'tpn_clear_walk_layers')
         self._h.epoch = 0
         self._h.now = self._h.begin
-        self.now_time.data = self.begging_time.clone()
+        self.now_time.data.copy_(self.begging_time.data)     # in place: the parameter keeps its storage (CUDA graphs)
         if not self.use_matrix:
             std = 1 / math.sqrt(self.dim)
             p0 = self.random_projections[0]
@@ -542,7 +542,7 @@ class RandomProjectionModule(nn.Module):
         """TPNet.py:149-157."""
         now_time, layers = random_projections
         with torch.no_grad():
-            self.now_time.data = now_time.clone().to(self.now_time.device)
+            self.now_time.data.copy_(now_time.to(self.now_time.device))       # in place: same storage (CUDA graphs)
             for i in range(1, self.num_layer + 1):
                 self.random_projections[i].copy_(layers[i - 1])
         self._after_external_write()

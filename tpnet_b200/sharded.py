@@ -298,6 +298,13 @@ class ShardedRandomProjection(RandomProjectionModule):
             rc = lib.tpn_gather_blocks(self._c_state(), ptr, S, send.data_ptr(), self._stream())
             if rc:
                 _lib.check(rc, 'tpn_gather_blocks')
+        if self.world > 1 and dist.is_initialized():
+            # decided collectively: a rank that raised alone would leave the others waiting in the all_to_all
+            over = torch.tensor([1 if R > self.ext_rows else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(over, op=dist.ReduceOp.MAX, group=self.group)
+            if int(over.item()):
+                raise RuntimeError(f'a rank needs more remote rows than the {self.ext_rows} extension rows hold '
+                                   f'(this rank: {R}): construct ShardedRandomProjection with a larger ext_rows')
         recv = self._ext_view(R)
         if self.world > 1:
             exchange_blocks(send, plan.send_counts, recv, plan.recv_counts, self.group)
