@@ -76,6 +76,8 @@ def parse_args():
     ap.add_argument('--no-flush', action='store_true', help='small shapes: keep L2 warm between steps')
     ap.add_argument('--no-graphs', action='store_true', help='power-law: launch the steps eagerly instead of as CUDA graphs')
     ap.add_argument('--no-also', action='store_true', help='N=1: skip the secondary measurements')
+    ap.add_argument('--e2e-sync-read', action='store_true',
+                    help='e2e: read every step\'s result with a blocking .item() instead of the pinned 2-slot ring')
     ap.add_argument('--no-parity', action='store_true', help='N>1: skip the sharded-vs-single-GPU parity leg')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'nccl'], help='N>1: data plane of the sharded state')
     ap.add_argument('--cpu-sample-steps', type=int, default=None)
@@ -268,7 +270,41 @@ def resident_step(m, ds):
         m.update(ds['src'], ds['dst'], ds['t'], next_time=ds['t_last'])
 
 
-def api_step(m, st):
+READBACK_NOTE = {
+    True: '(blocking .item() per step)',
+    False: '(D2H copy into a pinned slot every step; the host reads the value of step k after step k+1 is enqueued)',
+}
+
+
+class ResultReader:
+    """Device -> host read of every step's scalar result through a 2-slot pinned ring: the value of step k is read on
+    the host after step k+1 has been enqueued (how a loop that accumulates its metric uses it), so the read-back of one
+    step does not drain the GPU before the next step's staging starts.  Every step still pays its D2H copy and its
+    host-side read inside the timed region; `drain()` reads the last one.  `--e2e-sync-read` restores `.item()`."""
+
+    def __init__(self):
+        self.buf = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.ev = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+        self.pending = None
+        self.total = 0.0
+
+    def push(self, r):
+        i = self.k & 1
+        self.buf[i].copy_(r.reshape(1), non_blocking=True)
+        self.ev[i].record()
+        self.drain()
+        self.pending = i
+        self.k += 1
+
+    def drain(self):
+        if self.pending is not None:
+            self.ev[self.pending].synchronize()
+            self.total += float(self.buf[self.pending][0])
+            self.pending = None
+
+
+def api_step(m, st, reader=None):
     """One step through the public numpy API, head included, scalar result read back."""
     with torch.no_grad():
         m.get_neighbor_pair_wise_feature(*st['nbr_pos'])       # encoder features (feed the Mixer in TPNet)
@@ -277,6 +313,9 @@ def api_step(m, st):
         neg = m.get_pair_wise_feature(st['src'], st['neg'])
         m.update(st['src'], st['dst'], st['t'])
         res = pos.sum() - neg.sum()
+    if reader is not None:
+        reader.push(res)                                       # D2H copy now, host read one step later
+        return None
     return float(res.item())                                   # D2H read of the step's result
 
 
@@ -390,12 +429,17 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True, sampler_leg=False)
     pairs_per_launch = 2 * dsteps[0]['nbr_pos'][0].numel()        # two pair blocks per (row, neighbour)
 
     api = steps[K + W:]
+    reader = None if args.e2e_sync_read else ResultReader()
     for st in api[:W]:
-        api_step(m, st)
+        api_step(m, st, reader)
+    if reader is not None:
+        reader.drain()
     torch.cuda.synchronize()
     e0 = time.perf_counter()
     for st in api[W:W + K]:
-        api_step(m, st)
+        api_step(m, st, reader)
+    if reader is not None:
+        reader.drain()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - e0) * 1e3
     h2d = 2 * ((2 * BATCH * NUM_NEIGHBORS + 4 * BATCH) * 8) + 2 * (2 * BATCH * 8) + 3 * BATCH * 8
@@ -429,7 +473,8 @@ def run_tpnet_shape(args, shape, device, K, W, with_cpu=True, sampler_leg=False)
                              (shape.node_num * (shape.num_layer + 1) * m.row_stride * 4 / 1e6)},
         'e2e': {'value': BATCH * K / (e2e_ms * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / K,
-                'path': 'RandomProjectionModule.get_pair_wise_feature/update with numpy ids, self.mlp included'},
+                'path': 'RandomProjectionModule.get_pair_wise_feature/update with numpy ids, self.mlp included, scalar '
+                        'result read back ' + READBACK_NOTE[bool(args.e2e_sync_read)]},
         'gpu_launches': kernels_per_step * K,
     }
     if sampler_leg:
@@ -778,10 +823,16 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
                     _, ng = m.get_pair_wise_feature(s, neg)
                 m.update(s, d, t)
                 r = pos.sum() - ng.sum()
+            if reader is not None:
+                reader.push(r)
+                return None
             return float(r.item())
 
+        reader = None if args.e2e_sync_read else ResultReader()
         for st in api[:W]:
             api_one(st)
+        if reader is not None:
+            reader.drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -789,6 +840,8 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
         n_api = len(api) - W
         for st in api[W:]:
             api_one(st)
+        if reader is not None:
+            reader.drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -835,8 +888,10 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
     # ncu DRAM bytes are a property of the N=1 launch: not carried over to the sharded runs
     roof['traffic'] = traffic_note(tkey) if world == 1 else None
     h2d = 3 * B * 8 + 2 * (2 * B * 8)
-    upd_launches = 1 + 9 + 1 + 1 + 1 + 1 + 1 + 1                # prep, 3 x (hist, prefix, scatter), payload, sort_giants |
-    #                                                             combine, snapshot, hub2, small, stamps
+    upd_launches = 1 + 1 + 1 + 1 + 1                            # fused front end (prep + radix passes + payload + giant
+    #                                                             ordering, one cooperative launch), snapshot, hub2, small, stamps
+    if accumulation == 'chunked':
+        upd_launches += 1                                       # combine_giants
     per_step = 2 * 2 + upd_launches if world == 1 else (2 * (4 + 1 + 2) + 1 + 4 + 1 + 1 + upd_launches)
     line = {
         'metric': METRIC, 'value': B * K / (dev_ms * 1e-3), 'unit': 'edges/s', 'n_gpus': world, 'steps': K,
@@ -872,7 +927,7 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
                        'path': ('ShardedRandomProjection.routed_pair_wise_feature/update with numpy ids: every rank stages '
                                 '1/N of each array, the slices are all-gathered over NVLink, routing on the device; '
                                 if peer else 'ShardedRandomProjection.get_pair_wise_feature/update with numpy ids; ')
-                               + 'self.mlp included, scalar result read back'}
+                               + 'self.mlp included, scalar result read back ' + READBACK_NOTE[bool(args.e2e_sync_read)]}
         line['barriers_total'] = barriers
     return line
 

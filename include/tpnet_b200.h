@@ -158,6 +158,10 @@ int tpn_update(tpn_state_t* st,
 /*   TPN_DEBUG_HEAD_FFMA      : tpn_head_forward runs the packed-FFMA fp32 kernel (tpn_head.cu) instead of the tcgen05
  *                              tensor-core kernel (fp16 x 2 split operands, fp32 accumulation in TMEM; tpn_head_tc.cu). */
 #define TPN_DEBUG_HEAD_FFMA 8
+/*   TPN_DEBUG_LEGACY_FRONT   : large batches run the sort front end as 12-13 separate launches (prep, histogram /
+ *                              prefix / scatter per radix pass, payload, giant ordering) instead of the one
+ *                              cooperative launch with grid barriers; results are identical. */
+#define TPN_DEBUG_LEGACY_FRONT 16
 int tpn_set_debug_flags(int flags);
 
 

@@ -906,3 +906,42 @@ def test_step_graphs_replay_equals_eager_calls():
                     mod.random_projections[0].data.copy_(p0)
                 sg.rewind()
         m.check_errors()
+
+
+@pytest.mark.parametrize('N,dim,L,B', [(40_000, 16, 2, 30_000),          # 16-bit keys: 2 radix passes
+                                       (200_001, 24, 3, 70_001),         # 18 bits: 3 passes, ragged last tile
+                                       (17_000_000, 8, 1, 50_000),       # 25 bits: 4 passes (both histogram buffers reused)
+                                       (3_000, 40, 3, 2_049)])           # just above the single-CTA sort: 3 tiles
+def test_fused_front_end_equals_separate_launches(N, dim, L, B):
+    """Large batches: the sort front end as ONE cooperative launch with grid barriers (default) against the same
+    phases as 12-13 separate launches (TPN_DEBUG_LEGACY_FRONT).  Stable sort, same payload: the states must be
+    bit-identical, with hubs (zipf endpoints), equal and real timestamps, lazy and eager decay."""
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=1e-6, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=dim)
+    for mode in (['lazy'] if N > 1_000_000 else MODES):
+        torch.manual_seed(3)
+        a = RandomProjectionModule(device=DEV, decay_mode=mode, **kw).to(DEV)
+        b = RandomProjectionModule(device=DEV, decay_mode=mode, **kw).to(DEV)
+        b.random_projections[0].data.copy_(a.random_projections[0].data)
+        t = 0.0
+        for it in range(3):
+            s = (1 + (rng.zipf(1.3, B) - 1) % (N - 1)).astype(np.int64)
+            d = rng.integers(1, N, B).astype(np.int64)
+            ts = np.sort(t + rng.random(B) * 1000.0) if it else np.full(B, 50.0)
+            t = float(ts[-1])
+            a.update(s, d, ts)
+            old = lib.tpn_set_debug_flags(16)
+            try:
+                b.update(s, d, ts)
+            finally:
+                lib.tpn_set_debug_flags(old)
+        a.materialize()
+        b.materialize()
+        for i in range(1, L + 1):
+            assert torch.equal(a.random_projections[i].data, b.random_projections[i].data), (mode, i)
+        a.check_errors()
+        b.check_errors()
+        del a, b
+        torch.cuda.empty_cache()

@@ -80,6 +80,7 @@ constexpr int kCtrChunks = 9;            // chunked accumulation: partial-sum ro
 constexpr uint32_t kNoPart = 0xffffffffu;   // hub_part[e]: the entry accumulates straight into its target row
 constexpr int kCtrSmClaim = 16;          // [256] first hub2 CTA of each SM claims the SM's giant-segment slot
 constexpr int kCtrSlots = kCtrSmClaim + 256;
+constexpr int kBarWords = 32;            // [0]: arrivals of the fused front end's grid barrier (monotonic within a launch)
 
 struct DecayArgs {
     float c[TPN_MAX_LAYERS];
@@ -136,7 +137,9 @@ struct Workspace {
     uint32_t* val_b;   // [E]
     uint32_t* ssrc;    // [E] source node of the p-th sorted message
     float* sw;         // [E] weight of the p-th sorted message
-    uint32_t* hist;    // [256 * nblk]
+    uint32_t* hist;    // [256 * (nblk + 1)]
+    uint32_t* hist2;   // [256 * (nblk + 1)] fused front end: histogram of the NEXT pass, counted while scattering
+    uint32_t* bar;     // [kBarWords] grid barrier of the fused front end (zeroed by a memset node before the launch)
     uint32_t* sslot;   // [E] sorted position of the segment head of the p-th message's SOURCE node
     uint32_t* slen;    // [E] number of messages with the same target as the p-th sorted message
     float* snap;       // [E][(L-1)*row_stride] pre-batch rows 1..L-1 of each target (snapshot path only)
@@ -176,6 +179,8 @@ Workspace carve(void* base, int64_t batch, int num_layer, int64_t row_stride) {
     ws.ssrc = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.sw = reinterpret_cast<float*>(take(4 * E));
     ws.hist = reinterpret_cast<uint32_t*>(take(4 * kRadixBins * (nblk + 1)));
+    ws.hist2 = reinterpret_cast<uint32_t*>(take(4 * kRadixBins * (nblk + 1)));
+    ws.bar = reinterpret_cast<uint32_t*>(take(4 * kBarWords));
     ws.sslot = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.slen = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.has_snap = snap_bytes(E, num_layer, row_stride) <= kSnapMaxBytes;
@@ -481,7 +486,8 @@ struct ScatterSmem {
 __device__ __forceinline__ void scatter_tile(ScatterSmem& sm, const uint32_t* __restrict__ kin,
                                              const uint32_t* __restrict__ vin, uint32_t* __restrict__ kout,
                                              uint32_t* __restrict__ vout, int E, int shift,
-                                             const uint32_t* __restrict__ offs, int nblk, int prefixed, int tile) {
+                                             const uint32_t* __restrict__ offs, int nblk, int prefixed, int tile,
+                                             uint32_t* __restrict__ hist_next = nullptr) {
     constexpr int kWarps = kRadixWarps;
     uint32_t (&wcount)[kRadixWarps][kRadixBins + 1] = sm.wcount;
     uint32_t (&wtot)[kRadixWarps] = sm.wtot;
@@ -556,6 +562,9 @@ __device__ __forceinline__ void scatter_tile(ScatterSmem& sm, const uint32_t* __
             const uint32_t pos = wcount[wid][dgt] + rank[i];
             kout[pos] = k[i];
             vout[pos] = v[i];
+            // fused front end: the next pass's histogram of the output tile this key lands in (integer count)
+            if (hist_next != nullptr)
+                atomicAdd(&hist_next[(pos / kRadixTile) * kRadixBins + ((k[i] >> (shift + 8)) & 0xff)], 1u);
         }
     }
 }
@@ -730,6 +739,131 @@ __global__ void __launch_bounds__(1024)
 sort_giants_kernel(uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ slen, const uint32_t* __restrict__ ctr) {
     __shared__ GiantSmem sm;
     sort_giants_body(sm, hub_giant, slen, ctr);
+}
+
+// ---------------------------------------------------------------- fused front end (large path)
+// prep + every radix pass + payload + giant ordering in ONE cooperative launch (<= one CTA per SM, all resident),
+// phases separated by a grid barrier, instead of 12-13 dependent launches of a few microseconds each:
+//   phase 0      weights, keys, tile histograms of pass 0 (the keys are still in registers); hist2 zeroed
+//   per pass     per-digit prefix over tiles (one warp per digit)  | barrier |  stable scatter of every tile, which
+//                also counts the NEXT pass's [tile][digit] histogram of the positions it writes (integer atomics:
+//                counts are order-independent)  | barrier |
+//   last phases  payload (sorted sources / weights / snapshot slots / segment lengths / work lists), then CTA 0
+//                orders the giants.
+// The barrier: one arrival counter in the workspace, zeroed by a memset node in front of the launch and monotonic
+// inside it; the spin is bounded (a grid that is not co-resident flags error 8 instead of hanging the GPU).
+struct FrontArgs {
+    PrepArgs prep;
+    PayloadArgs pay;
+    uint32_t *key_a, *key_b, *val_a, *val_b, *hist, *hist2, *bar;
+    int passes;
+    int sort_giants;
+};
+
+__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t& target, int* err_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        uint32_t seen;
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+            if (seen >= target) break;
+            if (++spins > (1ll << 22)) {                     // seconds: the grid is not co-resident
+                if (err_flag != nullptr) *err_flag = 8;
+                break;
+            }
+        } while (true);
+    }
+    __syncthreads();
+}
+
+union FrontSmem {
+    uint32_t bins[kRadixBins];
+    ScatterSmem scatter;
+    GiantSmem giants;
+};
+
+__global__ void __launch_bounds__(kRadixThreads)
+front_kernel(FrontArgs a) {
+    __shared__ FrontSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int E = a.prep.count.get();
+    const int nblk = (E + kRadixTile - 1) / kRadixTile;
+    uint32_t target = 0;
+    // ---- phase 0: prep + histogram of pass 0 (tile by tile), hist2 zeroed
+    {
+        const int ncap = (a.prep.count.cap + kRadixTile - 1) / kRadixTile;
+        const int cells = (ncap + 1) * kRadixBins;
+        for (int i = blockIdx.x * kRadixThreads + tid; i < cells; i += gridDim.x * kRadixThreads) a.hist2[i] = 0;
+        // tiles past the count still run prep_body for their first threads: counters / flags / log row of thread m
+        static_assert(kCtrSlots <= kRadixTile, "tile 0 zeroes the per-call counters");
+        const int ntile0 = nblk > 0 ? nblk : 1;
+        for (int tile = blockIdx.x; tile < ntile0; tile += gridDim.x) {
+            sm.bins[tid] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < kRadixItems; ++i) {
+                const int m = tile * kRadixTile + i * kRadixThreads + tid;
+                prep_body(a.prep, m);
+                if (m < E) atomicAdd(&sm.bins[a.prep.key[m] & 0xff], 1u);
+            }
+            __syncthreads();
+            if (tile < nblk) a.hist[tile * kRadixBins + tid] = sm.bins[tid];
+            __syncthreads();
+        }
+    }
+    grid_barrier(a.bar, target, a.prep.err_flag);
+    uint32_t *kin = a.key_a, *kout = a.key_b, *vin = a.val_a, *vout = a.val_b;
+    uint32_t *hcur = a.hist, *hnext = a.hist2;
+    for (int p = 0; p < a.passes; ++p) {
+        // ---- prefix over tiles, one warp per digit
+        for (int dgt = blockIdx.x * kRadixWarps + wid; dgt < kRadixBins; dgt += gridDim.x * kRadixWarps)
+            prefix_digit(hcur, nblk, dgt, lane);
+        grid_barrier(a.bar, target, a.prep.err_flag);
+        // ---- scatter (+ histogram of the next pass)
+        const int shift = 8 * p;
+        const bool more = p + 1 < a.passes;
+        for (int tile = blockIdx.x; tile < nblk; tile += gridDim.x) {
+            scatter_tile(sm.scatter, kin, vin, kout, vout, E, shift, hcur, nblk, 1, tile, more ? hnext : nullptr);
+            __syncthreads();
+        }
+        grid_barrier(a.bar, target, a.prep.err_flag);
+        if (more && p + 2 < a.passes) {
+            // the histogram just consumed becomes the one after next: zero it (nobody reads it before the next barrier)
+            const int cells = (nblk + 1) * kRadixBins;
+            for (int i = blockIdx.x * kRadixThreads + tid; i < cells; i += gridDim.x * kRadixThreads) hcur[i] = 0;
+        }
+        uint32_t* t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+        t = hcur; hcur = hnext; hnext = t;
+    }
+    // ---- payload
+    PayloadArgs pay = a.pay;
+    pay.order = vin;
+    pay.skey = kin;          // odd number of passes: the sorted keys live in key_b; payload copies them to key_a
+    for (int p0 = blockIdx.x * kRadixThreads; p0 < E; p0 += gridDim.x * kRadixThreads) payload_body(pay, p0 + tid);
+    if (!a.sort_giants) return;
+    grid_barrier(a.bar, target, a.prep.err_flag);
+    if (blockIdx.x == 0) sort_giants_body(sm.giants, a.pay.hub_giant, a.pay.slen, a.pay.ctr);
+}
+
+// cooperative launches (the fused front end) need the device attribute; queried once per device
+bool front_kernel_ok() {
+    static int table[kMaxDevices];          // 0 = not queried, 1 = yes, -1 = no
+    int& t = table[g_dev_slot];
+    if (t == 0) {
+        int dev = 0, coop = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) {
+            (void)cudaGetLastError();
+            coop = 0;
+        }
+        t = coop ? 1 : -1;
+    }
+    return t == 1;
 }
 
 // ---------------------------------------------------------------- eager decay sweep (large path)
@@ -1845,6 +1979,26 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
         fa.pay.hub_part = ws.hub_part;
         fa.pay.giant_cbase = ws.giant_cbase;
         fa.pay.chunk = (snapshot_path && hubs) ? chunk : 0;
+        const bool fused_front = (g_debug_flags & TPN_DEBUG_LEGACY_FRONT) == 0 && front_kernel_ok();
+        if (fused_front) {
+            // ONE cooperative launch (<= one CTA per SM): prep, every radix pass, payload, giant ordering
+            FrontArgs fr;
+            fr.prep = fa.prep;
+            fr.pay = fa.pay;
+            fr.key_a = ws.key_a; fr.key_b = ws.key_b; fr.val_a = ws.val_a; fr.val_b = ws.val_b;
+            fr.hist = ws.hist; fr.hist2 = ws.hist2; fr.bar = ws.bar;
+            fr.passes = passes;
+            fr.sort_giants = (snapshot_path && chunk == 0) ? 1 : 0;
+            const int sms = device_sm_count();
+            const unsigned grid = (unsigned)(nblk < 1 ? 1 : (nblk < sms ? nblk : sms));
+            void* kargs[] = {&fr};
+            if (cudaMemsetAsync(ws.bar, 0, 4 * kBarWords, stream) != cudaSuccess ||
+                cudaLaunchCooperativeKernel((const void*)front_kernel, dim3(grid), dim3(kRadixThreads), kargs, 0,
+                                            stream) != cudaSuccess) {
+                set_cuda_error(cudaGetLastError());
+                return TPN_ERR_CUDA;
+            }
+        } else
         {
             // >= 2 blocks: the first kCtrSlots threads also zero the per-call counters
             prep_large_kernel<<<(unsigned)((E + 255) / 256 < 2 ? 2 : (E + 255) / 256), 256, 0, stream>>>(fa.prep);

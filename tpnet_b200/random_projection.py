@@ -588,6 +588,9 @@ class RandomProjectionModule(nn.Module):
             if code == 4:
                 raise RuntimeError('a routed call of the sharded state owned more items than it was sized for '
                                    '(raise route_cap_factor); the excess was dropped')
+            if code == 8:
+                raise RuntimeError('tpn_update: the grid barrier of the fused sort front end timed out (its CTAs were '
+                                   'not co-resident); the update of that call is invalid')
             if code == 2:
                 raise RuntimeError('tpn_update_messages: a local source row was not a target of the same call '
                                    '(lazy decay needs both directions of every edge in the message list)')
