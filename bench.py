@@ -78,6 +78,9 @@ def parse_args():
     ap.add_argument('--no-also', action='store_true', help='N=1: skip the secondary measurements')
     ap.add_argument('--e2e-sync-read', action='store_true',
                     help='e2e: read every step\'s result with a blocking .item() instead of the pinned 2-slot ring')
+    ap.add_argument('--no-prepare', action='store_true',
+                    help='N=1: do not start the state-independent half of the update (update_prepare) ahead of the '
+                         'pair-wise calls of the same batch')
     ap.add_argument('--no-parity', action='store_true', help='N>1: skip the sharded-vs-single-GPU parity leg')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'nccl'], help='N>1: data plane of the sharded state')
     ap.add_argument('--cpu-sample-steps', type=int, default=None)
@@ -663,6 +666,9 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
             m.update(st['src'], st['dst'], st['t'], next_time=st['t_last'])
 
     def resident(st):
+        if world == 1 and not args.no_prepare:
+            # the half of the update that does not write the state starts now, on the module's side stream
+            m.update_prepare(st['src'], st['dst'], st['t'], next_time=st['t_last'])
         resident_pairs(st, 'pos')
         resident_pairs(st, 'neg')
         resident_update(st)
@@ -815,6 +821,8 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
         def api_one(st):
             s, d, t, neg = st
             with torch.no_grad():
+                if world == 1 and not args.no_prepare:
+                    m.update_prepare(s, d, t)
                 if peer:
                     pos = m.routed_pair_wise_feature(s, d).feat          # zero rows past the count
                     ng = m.routed_pair_wise_feature(s, neg).feat

@@ -59,7 +59,7 @@
 extern "C" {
 #endif
 
-#define TPN_ABI_VERSION 10
+#define TPN_ABI_VERSION 11
 
 #define TPN_MAX_LAYERS 4
 
@@ -143,6 +143,24 @@ int tpn_update(tpn_state_t* st,
                const int64_t* src_dev, const int64_t* dst_dev, const double* t_dev, int64_t batch,
                double t_last, float neg_lambda, const float* decay,
                void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, void* stream);
+
+/* tpn_update in two halves (no reference counterpart; same arguments, same results, bit for bit).
+ *   TPN_UPDATE_PREPARE : everything that does NOT write the state — the weights, the stable sort of the messages by
+ *                        target, the work lists and (lazy decay) the pre-batch snapshot.  `st` is not modified.
+ *                        May be launched on a side stream while other kernels still READ the state (the pair-wise
+ *                        calls of the same batch: TPNet.py's loop computes features of a batch, then updates with it).
+ *   TPN_UPDATE_APPLY   : the rest (eager sweep + snapshot, the walkers, the stamps); advances st->epoch.  Must be
+ *                        ordered after the PREPARE half (caller: event) and after every read of the pre-batch state.
+ *   TPN_UPDATE_WHOLE   : both, i.e. tpn_update.
+ * The same workspace, arguments and `st` must be passed to both halves, with no other tpn_update* call between.
+ * Batches of <= 2048 edges are not split (PREPARE is a no-op, APPLY does everything). */
+#define TPN_UPDATE_WHOLE 0
+#define TPN_UPDATE_PREPARE 1
+#define TPN_UPDATE_APPLY 2
+int tpn_update_phase(tpn_state_t* st,
+                     const int64_t* src_dev, const int64_t* dst_dev, const double* t_dev, int64_t batch,
+                     double t_last, float neg_lambda, const float* decay,
+                     void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev, void* stream, int phase);
 
 /* Test hook: selects code paths that are otherwise chosen by size.  Returns the previous flags.
  *   TPN_DEBUG_PER_LAYER_WALK : large batches use one walk launch per layer (top-down) instead of
@@ -271,8 +289,11 @@ int tpn_clear_walk_layers(tpn_state_t* st, void* stream);
  * `torch.from_numpy(ids).to(device)` at TPNet.py:74-77 and the implicit conversion at :109).
  * A stager owns a ring of pinned host slots and device slots on the current device.
  * tpn_stage copies `count` host arrays of 8-byte elements back to back into the next slot,
- * issues ONE cudaMemcpyAsync on `stream` and returns the device address of each array in
- * dev_out[i]; the addresses stay valid until the ring wraps (`slots` later calls).
+ * issues ONE cudaMemcpyAsync and returns the device address of each array in dev_out[i]; the
+ * addresses stay valid until the ring wraps (`slots` later calls).  With >= 4 slots the copy runs on
+ * the stager's own stream and `stream` only waits for its event (work enqueued on `stream`
+ * afterwards sees the data): the copy of one call overlaps the kernels of the two calls before it.
+ * Consumers must be enqueued on `stream` (or joined into it) before the second-next tpn_stage call.
  *   kinds[i] = TPN_STAGE_RAW      : copied verbatim (float64 timestamps)
  *            = TPN_STAGE_ID_WRAP  : int64 ids, -num_nodes <= id < num_nodes, negatives wrap
  *                                   (what tensor indexing does, TPNet.py:109)

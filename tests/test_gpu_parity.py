@@ -945,3 +945,53 @@ def test_fused_front_end_equals_separate_launches(N, dim, L, B):
         b.check_errors()
         del a, b
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize('mode', MODES)
+def test_update_prepare_overlaps_reads_and_changes_nothing(mode):
+    """`update_prepare` starts the half of the update that does not write the state on a side stream; pair-wise calls
+    issued between it and `update` still see the PRE-batch state, and the state after `update` is bit-identical to a
+    module that never prepared.  Also: a prepared half that is not followed by the matching update (different arrays,
+    reset in between) is dropped and the whole update runs."""
+    rng = np.random.default_rng(9)
+    N, dim, L, B = 5000, 48, 3, 6000
+    kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=1e-6, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=dim)
+    torch.manual_seed(4)
+    a = RandomProjectionModule(device=DEV, decay_mode=mode, **kw).to(DEV)
+    b = RandomProjectionModule(device=DEV, decay_mode=mode, **kw).to(DEV)
+    b.random_projections[0].data.copy_(a.random_projections[0].data)
+    t = 0.0
+    for it in range(5):
+        s = (1 + (rng.zipf(1.4, B) - 1) % (N - 1)).astype(np.int64)
+        d = rng.integers(1, N, B).astype(np.int64)
+        ts = np.sort(t + rng.random(B) * 5000.0)
+        t = float(ts[-1])
+        ds, dd, dt = (torch.from_numpy(x).to(DEV) for x in (s, d, ts))
+        with torch.no_grad():
+            ref_feat = b.pair_wise_gram(ds, dd)
+            if it == 3:                                      # prepared, then a DIFFERENT batch arrives: whole update
+                assert a.update_prepare(dd, ds, dt, next_time=t)
+            else:
+                assert a.update_prepare(ds, dd, dt, next_time=t)
+            got_feat = a.pair_wise_gram(ds, dd)              # reads the pre-batch state while the side stream works
+            assert torch.equal(got_feat, ref_feat), it
+        a.update(ds, dd, dt, next_time=t)
+        b.update(ds, dd, dt, next_time=t)
+        if it == 1:                                          # numpy arrays through the staging ring
+            s2 = rng.integers(1, N, B).astype(np.int64)
+            ts2 = np.sort(t + rng.random(B) * 10.0)
+            t = float(ts2[-1])
+            assert a.update_prepare(s2, d, ts2)
+            a.update(s2, d, ts2)
+            b.update(s2, d, ts2)
+    a.materialize()
+    b.materialize()
+    for i in range(1, L + 1):
+        assert torch.equal(a.random_projections[i].data, b.random_projections[i].data), i
+    assert a.update_prepare(ds, dd, dt, next_time=t + 1.0)
+    a.reset_random_projections()                             # drops the prepared half
+    assert a._pending is None
+    assert not a.update_prepare(ds[:100], dd[:100], dt[:100], next_time=t)      # single-CTA sort path: nothing to split
+    a.check_errors()
+    b.check_errors()

@@ -20,12 +20,13 @@ TPN_ERR_UNSUPPORTED = -5
 TPN_ERR_INDEX = -6
 STAGE_RAW, STAGE_ID_WRAP, STAGE_ID = 0, 1, 2
 TPN_MAX_LAYERS = 4
-ABI_VERSION = 10
+UPDATE_WHOLE, UPDATE_PREPARE, UPDATE_APPLY = 0, 1, 2
+ABI_VERSION = 11
 
 #: every symbol include/tpnet_b200.h declares (tests assert the .so exports all of them)
 EXPORTED_SYMBOLS = (
     'tpn_version', 'tpn_error_string', 'tpn_last_cuda_error', 'tpn_device_info',
-    'tpn_update_workspace_bytes', 'tpn_update', 'tpn_pairwise', 'tpn_gather',
+    'tpn_update_workspace_bytes', 'tpn_update', 'tpn_update_phase', 'tpn_pairwise', 'tpn_gather',
     'tpn_materialize', 'tpn_reset_epoch', 'tpn_clear_walk_layers',
     'tpn_stager_create', 'tpn_stager_destroy', 'tpn_stage',
     'tpn_update_messages', 'tpn_gather_blocks', 'tpn_set_debug_flags', 'tpn_pairwise_neighbors', 'tpn_head_forward',
@@ -98,6 +99,9 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.tpn_update.restype = c_int
     lib.tpn_update.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_double, c_float,
                                POINTER(c_float), c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.tpn_update_phase.restype = c_int
+    lib.tpn_update_phase.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_double, c_float,
+                                     POINTER(c_float), c_void_p, c_size_t, c_void_p, c_void_p, c_int]
     lib.tpn_update_messages.restype = c_int
     lib.tpn_update_messages.argtypes = [POINTER(TpnState), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                         c_double, c_float, POINTER(c_float), c_void_p, c_size_t, c_void_p, c_void_p]

@@ -104,6 +104,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load without the wait: several loads are issued back to back and waited for once (tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // bounded wait: a lost arrival becomes a trap (an error the host sees), never a hung GPU
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
     const long long t0 = clock64();
@@ -233,97 +251,111 @@ head_tc_kernel(const float* __restrict__ x, long long n, const float* __restrict
     uint32_t it = 0;                      // tiles done by this CTA (phase of the once-per-tile barriers)
     if (warp < 4) {
         // =================================================================== row workers
+        // Software pipeline over the tiles of this CTA: the X rows of tile i+1 are loaded into registers while tile
+        // i is in its epilogues, and they are split into shared memory as soon as epilogue 1 of tile i has drained
+        // D1 — so GEMM1(i+1) runs on the tensor core while the workers are in epilogue 2 of tile i.
         const int r = tid;                                   // pair of the tile == TMEM lane
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;      // a warp reaches TMEM lanes [32 * (warp % 4), + 32)
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        float4 xn[kF / 4];                                   // X row of the NEXT tile (in flight / waiting to be split)
+        auto load_x = [&](long long tile) {
             const long long row = tile * kTile + r;
-            const bool valid = row < n;
-            // ---- X row -> scaled, split, canonical layout
-            float xr[kF];
+            const bool ok = tile < ntiles && row < n;
+#pragma unroll
+            for (int q = 0; q < kF / 4; ++q) xn[q] = ok ? ld4(x + row * kF + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        // xn -> scaled, split, canonical layout; returns 1 / (row scale * W1 scale)
+        auto split_x = [&]() -> float {
             float vmax = 0.f;
 #pragma unroll
-            for (int q = 0; q < kF / 4; ++q) {
-                const float4 v = valid ? ld4(x + row * kF + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
-                vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-            }
+            for (int q = 0; q < kF / 4; ++q)
+                vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(xn[q].x), fabsf(xn[q].y)), fmaxf(fabsf(xn[q].z), fabsf(xn[q].w))));
             const float sx = pow2_scale(vmax);
-            const float inv1 = w1_inv / sx;                  // exact (powers of two)
 #pragma unroll
             for (int k8 = 0; k8 < kF / 8; ++k8) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = xr[k8 * 8 + j] * sx;
+                const float4 a = xn[2 * k8], b = xn[2 * k8 + 1];
+                const float v[8] = {a.x * sx, a.y * sx, a.z * sx, a.w * sx, b.x * sx, b.y * sx, b.z * sx, b.w * sx};
                 uint4 hi, lo;
                 split8(v, hi, lo);
                 *reinterpret_cast<uint4*>(&sm.x[0][canon(r, k8 * 8)]) = hi;
                 *reinterpret_cast<uint4*>(&sm.x[1][canon(r, k8 * 8)]) = lo;
             }
             fence_proxy_async_smem();
+            tc_fence_before();            // this thread's TMEM reads of the previous tile are ordered before the arrival
             mbar_arrive(&sm.x_full);
-
-            // ---- epilogue 1: h = relu(D1 / (sx * s1) + b1); row maximum first (the scale of the split), then the chunks
+            return w1_inv / sx;                              // exact (powers of two)
+        };
+        long long tile = blockIdx.x;
+        load_x(tile);
+        float inv1 = split_x();
+        load_x(tile + gridDim.x);
+        for (; tile < ntiles; tile += gridDim.x, ++it) {
+            const long long row = tile * kTile + r;
+            const bool valid = row < n;
+            // ---- epilogue 1: h = relu(D1 / (sx * s1) + b1), one 64-column chunk at a time; every chunk gets its own
+            // power-of-two scale (its own row maximum), undone per chunk in epilogue 2 — no separate maximum pass
             mbar_wait_bounded(&sm.d1_full, it & 1u);
             tc_fence_after();
-            float hmax = 0.f;
-#pragma unroll 1
-            for (int p = 0; p < kHid / 32; ++p) {
-                float d[32];
-                tmem_ld32(tmem + lane_base + (uint32_t)(p * 32), d);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) hmax = fmaxf(hmax, fmaf(d[j], inv1, sm.b1[p * 32 + j]));
-            }
-            const float sh = pow2_scale(hmax);               // hmax already >= 0: relu
-            const float inv2 = w2_inv / sh;
+            float inv2[4];
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int buf = c & 1;
                 const uint32_t use = it * 2u + (uint32_t)(c >> 1);
+                float d0[32], d1[32];
+                tmem_ld32_nowait(tmem + lane_base + (uint32_t)(c * 64), d0);
+                tmem_ld32_nowait(tmem + lane_base + (uint32_t)(c * 64 + 32), d1);
+                tmem_ld_wait();
+                float hmax = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    d0[j] = fmaxf(fmaf(d0[j], inv1, sm.b1[c * 64 + j]), 0.f);
+                    d1[j] = fmaxf(fmaf(d1[j], inv1, sm.b1[c * 64 + 32 + j]), 0.f);
+                    hmax = fmaxf(hmax, fmaxf(d0[j], d1[j]));
+                }
+                const float sh = pow2_scale(hmax);
+                inv2[c] = w2_inv / sh;
                 mbar_wait_bounded(&sm.h_empty[buf], (use & 1u) ^ 1u);       // GEMM2 is done with this buffer
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    float d[32];
-                    const int col = c * 64 + half * 32;
-                    tmem_ld32(tmem + lane_base + (uint32_t)col, d);
 #pragma unroll
-                    for (int k8 = 0; k8 < 4; ++k8) {
-                        float v[8];
+                for (int k8 = 0; k8 < 8; ++k8) {
+                    float v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            v[j] = fmaxf(fmaf(d[k8 * 8 + j], inv1, sm.b1[col + k8 * 8 + j]), 0.f) * sh;
-                        uint4 hi, lo;
-                        split8(v, hi, lo);
-                        const int kk = half * 32 + k8 * 8;
-                        *reinterpret_cast<uint4*>(&sm.h[buf][0][canon(r, kk)]) = hi;
-                        *reinterpret_cast<uint4*>(&sm.h[buf][1][canon(r, kk)]) = lo;
-                    }
+                    for (int j = 0; j < 8; ++j) v[j] = (k8 < 4 ? d0[k8 * 8 + j] : d1[(k8 - 4) * 8 + j]) * sh;
+                    uint4 hi, lo;
+                    split8(v, hi, lo);
+                    *reinterpret_cast<uint4*>(&sm.h[buf][0][canon(r, k8 * 8)]) = hi;
+                    *reinterpret_cast<uint4*>(&sm.h[buf][1][canon(r, k8 * 8)]) = lo;
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&sm.h_full[buf]);
             }
-
-            // ---- epilogue 2: y = D2 / (sh * s2) + b2
+            // ---- D1 is drained and GEMM1 of this tile completed long ago: hand the next tile's X to the tensor core
+            const float inv2_0 = inv2[0], inv2_1 = inv2[1], inv2_2 = inv2[2], inv2_3 = inv2[3];
+            if (tile + gridDim.x < ntiles) {
+                inv1 = split_x();
+                load_x(tile + 2 * (long long)gridDim.x);
+            }
+            // ---- epilogue 2: y = sum over the K chunks of D2_c / (sh_c * s2), + b2
             mbar_wait_bounded(&sm.d2_full, it & 1u);
             tc_fence_after();
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 float d[32];
-                {   // the four K-chunk accumulators, summed pairwise in fp32 (round to nearest)
+                {   // the four K-chunk accumulators, each with its own scale, summed pairwise in fp32
                     float d1[32], d2[32], d3[32];
-                    tmem_ld32(tmem + lane_base + kD2Col + (uint32_t)(half * 32), d);
-                    tmem_ld32(tmem + lane_base + kD2Col + 64u + (uint32_t)(half * 32), d1);
-                    tmem_ld32(tmem + lane_base + kD2Col + 128u + (uint32_t)(half * 32), d2);
-                    tmem_ld32(tmem + lane_base + kD2Col + 192u + (uint32_t)(half * 32), d3);
+                    tmem_ld32_nowait(tmem + lane_base + kD2Col + (uint32_t)(half * 32), d);
+                    tmem_ld32_nowait(tmem + lane_base + kD2Col + 64u + (uint32_t)(half * 32), d1);
+                    tmem_ld32_nowait(tmem + lane_base + kD2Col + 128u + (uint32_t)(half * 32), d2);
+                    tmem_ld32_nowait(tmem + lane_base + kD2Col + 192u + (uint32_t)(half * 32), d3);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) d[j] = (d[j] + d1[j]) + (d2[j] + d3[j]);
+                    for (int j = 0; j < 32; ++j)
+                        d[j] = (d[j] * inv2_0 + d1[j] * inv2_1) + (d2[j] * inv2_2 + d3[j] * inv2_3);
                 }
                 if (valid) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int o = half * 32 + q * 4;
-                        st4(y + row * kF + o, make_float4(fmaf(d[q * 4], inv2, sm.b2[o]), fmaf(d[q * 4 + 1], inv2, sm.b2[o + 1]),
-                                                          fmaf(d[q * 4 + 2], inv2, sm.b2[o + 2]),
-                                                          fmaf(d[q * 4 + 3], inv2, sm.b2[o + 3])));
+                        st4(y + row * kF + o, make_float4(d[q * 4] + sm.b2[o], d[q * 4 + 1] + sm.b2[o + 1],
+                                                          d[q * 4 + 2] + sm.b2[o + 2], d[q * 4 + 3] + sm.b2[o + 3]));
                     }
                 }
             }
@@ -334,10 +366,10 @@ head_tc_kernel(const float* __restrict__ x, long long n, const float* __restrict
         constexpr uint32_t idesc1 = instr_desc(kTile, kHid), idesc2 = instr_desc(kTile, kF);
         const uint64_t xa[2] = {smem_desc(sm.x[0]), smem_desc(sm.x[1])};
         const uint64_t wb[2] = {smem_desc(sm.w1[0]), smem_desc(sm.w1[1])};
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            mbar_wait_bounded(&sm.x_full, it & 1u);
+        // GEMM1 of one tile: small cross products first, hi * hi last (only its 4 additions happen at full magnitude)
+        auto gemm1 = [&](uint32_t t) {
+            mbar_wait_bounded(&sm.x_full, t & 1u);     // X of tile t is in shared memory — and D1 of tile t-1 is drained
             tc_fence_after();
-            // small cross products first, hi * hi last: only its 4 additions happen at full accumulator magnitude
 #pragma unroll
             for (int ks = 0; ks < kF / 16; ++ks) {
                 const uint64_t adv = (uint64_t)((ks * kKStepBytes) >> 4);
@@ -350,6 +382,10 @@ head_tc_kernel(const float* __restrict__ x, long long n, const float* __restrict
                 mma_f16(tmem, xa[0] + adv, wb[0] + adv, idesc1, 1u);                    // hi * hi
             }
             mma_commit(&sm.d1_full);
+        };
+        long long tile = blockIdx.x;
+        if (tile < ntiles) gemm1(0);
+        for (; tile < ntiles; tile += gridDim.x, ++it) {
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int buf = c & 1;
@@ -373,6 +409,8 @@ head_tc_kernel(const float* __restrict__ x, long long n, const float* __restrict
                 mma_commit(&sm.h_empty[buf]);
             }
             mma_commit(&sm.d2_full);
+            // GEMM1 of the next tile runs while the workers are in epilogue 2 of this one
+            if (tile + gridDim.x < ntiles) gemm1(it + 1u);
         }
     }
 

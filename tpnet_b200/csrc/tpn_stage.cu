@@ -4,8 +4,12 @@
 // call (models/TPNet.py:74-77 and the implicit conversion at :109) — a pageable, synchronous
 // copy.  Here one C call copies the arrays into a ring of pinned host slots (validating the
 // ids on the way, which replaces the bounds check torch indexing performs), issues ONE
-// cudaMemcpyAsync per call on the caller's stream and records an event so that a slot is
-// never overwritten before its copy has left.  No Python-level stream/event objects.
+// cudaMemcpyAsync per call and records an event so that a slot is never overwritten before its
+// copy has left.  The copy runs on the stager's OWN stream: the caller's stream only waits for the
+// event, so the H2D copy of call k+1 overlaps the kernels of call k instead of queueing behind them
+// (a copy issued on the compute stream is serialised with every kernel launched before it).  A device
+// slot is rewritten `slots` calls later; the copy stream first waits for an event recorded on the
+// caller's stream one call after the slot's consumers were enqueued.  No Python-level stream/event objects.
 #include <omp.h>
 #include <stdlib.h>
 #include <string.h>
@@ -18,8 +22,11 @@ struct tpn_stager {
     int cursor;
     char** host;          // pinned
     char** dev;
-    cudaEvent_t* done;
+    cudaEvent_t* done;    // copy of slot i has left the pinned buffer (recorded on the copy stream)
+    cudaEvent_t* seen;    // seen[j % slots]: recorded on the caller's stream at the START of call j
     bool* used;
+    cudaStream_t copy_stream;
+    long long calls;
 };
 
 namespace {
@@ -30,15 +37,20 @@ void release(tpn_stager* sg) {
         if (sg->host && sg->host[i]) cudaFreeHost(sg->host[i]);
         if (sg->dev && sg->dev[i]) cudaFree(sg->dev[i]);
         if (sg->done && sg->done[i]) cudaEventDestroy(sg->done[i]);
+        if (sg->seen && sg->seen[i]) cudaEventDestroy(sg->seen[i]);
     }
+    if (sg->copy_stream != nullptr) cudaStreamDestroy(sg->copy_stream);
     free(sg->host);
     free(sg->dev);
     free(sg->done);
+    free(sg->seen);
     free(sg->used);
     sg->host = nullptr;
     sg->dev = nullptr;
     sg->done = nullptr;
+    sg->seen = nullptr;
     sg->used = nullptr;
+    sg->copy_stream = nullptr;
 }
 
 // host threads of the staging pass: TPN_STAGE_THREADS, else min(8, cores / 2) — and never more than the
@@ -67,12 +79,25 @@ int allocate(tpn_stager* sg, size_t slot_bytes, int slots) {
     sg->host = (char**)calloc(slots, sizeof(char*));
     sg->dev = (char**)calloc(slots, sizeof(char*));
     sg->done = (cudaEvent_t*)calloc(slots, sizeof(cudaEvent_t));
+    sg->seen = (cudaEvent_t*)calloc(slots, sizeof(cudaEvent_t));
     sg->used = (bool*)calloc(slots, sizeof(bool));
-    if (!sg->host || !sg->dev || !sg->done || !sg->used) return TPN_ERR_INVALID_ARGUMENT;
+    sg->calls = 0;
+    sg->copy_stream = nullptr;
+    if (!sg->host || !sg->dev || !sg->done || !sg->seen || !sg->used) return TPN_ERR_INVALID_ARGUMENT;
+    // TPN_STAGE_COPY_STREAM=0: copies on the caller's stream (A/B measurements)
+    const char* env = getenv("TPN_STAGE_COPY_STREAM");
+    if (slots >= 4 && !(env != nullptr && env[0] == '0')) {
+        const cudaError_t e = cudaStreamCreateWithFlags(&sg->copy_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            sg->copy_stream = nullptr;               // fall back to the caller's stream
+        }
+    }
     for (int i = 0; i < slots; ++i) {
         cudaError_t e = cudaHostAlloc((void**)&sg->host[i], slot_bytes, cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaMalloc((void**)&sg->dev[i], slot_bytes);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sg->done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sg->seen[i], cudaEventDisableTiming);
         if (e != cudaSuccess) {
             tpn::set_cuda_error(e);
             return TPN_ERR_CUDA;
@@ -118,6 +143,7 @@ extern "C" int tpn_stage(tpn_stager_t* sg, const void* const* host, const int64_
     }
     if (total > sg->slot_bytes) {                     // grow: rare (first call with a bigger batch)
         cudaError_t e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess && sg->copy_stream != nullptr) e = cudaStreamSynchronize(sg->copy_stream);
         if (e != cudaSuccess) {
             tpn::set_cuda_error(e);
             return TPN_ERR_CUDA;
@@ -170,8 +196,31 @@ extern "C" int tpn_stage(tpn_stager_t* sg, const void* const* host, const int64_
         dev_out[i] = sg->dev[k] + off;
         off += (size_t)n * 8;
     }
-    cudaError_t e = cudaMemcpyAsync(sg->dev[k], sg->host[k], total, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaEventRecord(sg->done[k], stream);
+    cudaError_t e = cudaSuccess;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (sg->copy_stream != nullptr && cudaStreamIsCapturing(stream, &cap) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cap = cudaStreamCaptureStatusNone;
+    }
+    if (sg->copy_stream != nullptr && cap == cudaStreamCaptureStatusNone) {
+        // call j (slot k = j % slots).  seen[j % slots] <- "everything the caller enqueued before call j".  The device
+        // slot was last used by call j - slots; its consumers were enqueued before call j - slots + 1 — or, when they
+        // ran on a side stream of the caller (update_prepare), were joined into the caller's stream a call or two later.
+        // The copy waits for the event of call j - 2: it still overlaps the kernels of the two calls before it, and
+        // with slots >= 4 everything that ever read the slot is covered.
+        const int S = sg->slots;
+        const int js = (int)(sg->calls % S);
+        e = cudaEventRecord(sg->seen[js], stream);
+        if (e == cudaSuccess && sg->calls >= 2)
+            e = cudaStreamWaitEvent(sg->copy_stream, sg->seen[(int)((sg->calls - 2) % S)], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sg->dev[k], sg->host[k], total, cudaMemcpyHostToDevice, sg->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(sg->done[k], sg->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, sg->done[k], 0);
+    } else {
+        e = cudaMemcpyAsync(sg->dev[k], sg->host[k], total, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaEventRecord(sg->done[k], stream);
+    }
+    sg->calls += 1;
     if (e != cudaSuccess) {
         tpn::set_cuda_error(e);
         return TPN_ERR_CUDA;

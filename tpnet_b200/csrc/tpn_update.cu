@@ -742,22 +742,20 @@ sort_giants_kernel(uint32_t* __restrict__ hub_giant, const uint32_t* __restrict_
 }
 
 // ---------------------------------------------------------------- fused front end (large path)
-// prep + every radix pass + payload + giant ordering in ONE cooperative launch (<= one CTA per SM, all resident),
-// phases separated by a grid barrier, instead of 12-13 dependent launches of a few microseconds each:
+// prep + every radix pass in ONE cooperative launch (<= one CTA per SM, all resident), phases separated by a grid
+// barrier, instead of 10 dependent launches of a few microseconds each.  Payload and giant ordering stay separate
+// launches: the payload's binary searches are latency-bound and want ~800 CTAs, not one per tile (measured: 100 us
+// with the payload inside the 98-CTA launch, 49 us + 13 us + 4 us as three launches; profiles/r02k_*).
 //   phase 0      weights, keys, tile histograms of pass 0 (the keys are still in registers); hist2 zeroed
 //   per pass     per-digit prefix over tiles (one warp per digit)  | barrier |  stable scatter of every tile, which
 //                also counts the NEXT pass's [tile][digit] histogram of the positions it writes (integer atomics:
 //                counts are order-independent)  | barrier |
-//   last phases  payload (sorted sources / weights / snapshot slots / segment lengths / work lists), then CTA 0
-//                orders the giants.
 // The barrier: one arrival counter in the workspace, zeroed by a memset node in front of the launch and monotonic
 // inside it; the spin is bounded (a grid that is not co-resident flags error 8 instead of hanging the GPU).
 struct FrontArgs {
     PrepArgs prep;
-    PayloadArgs pay;
     uint32_t *key_a, *key_b, *val_a, *val_b, *hist, *hist2, *bar;
     int passes;
-    int sort_giants;
 };
 
 __device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t& target, int* err_flag) {
@@ -783,7 +781,6 @@ __device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t& target, in
 union FrontSmem {
     uint32_t bins[kRadixBins];
     ScatterSmem scatter;
-    GiantSmem giants;
 };
 
 __global__ void __launch_bounds__(kRadixThreads)
@@ -830,8 +827,9 @@ front_kernel(FrontArgs a) {
             scatter_tile(sm.scatter, kin, vin, kout, vout, E, shift, hcur, nblk, 1, tile, more ? hnext : nullptr);
             __syncthreads();
         }
+        if (!more) break;                                    // the kernel boundary orders the last scatter
         grid_barrier(a.bar, target, a.prep.err_flag);
-        if (more && p + 2 < a.passes) {
+        if (p + 2 < a.passes) {
             // the histogram just consumed becomes the one after next: zero it (nobody reads it before the next barrier)
             const int cells = (nblk + 1) * kRadixBins;
             for (int i = blockIdx.x * kRadixThreads + tid; i < cells; i += gridDim.x * kRadixThreads) hcur[i] = 0;
@@ -840,14 +838,6 @@ front_kernel(FrontArgs a) {
         t = vin; vin = vout; vout = t;
         t = hcur; hcur = hnext; hnext = t;
     }
-    // ---- payload
-    PayloadArgs pay = a.pay;
-    pay.order = vin;
-    pay.skey = kin;          // odd number of passes: the sorted keys live in key_b; payload copies them to key_a
-    for (int p0 = blockIdx.x * kRadixThreads; p0 < E; p0 += gridDim.x * kRadixThreads) payload_body(pay, p0 + tid);
-    if (!a.sort_giants) return;
-    grid_barrier(a.bar, target, a.prep.err_flag);
-    if (blockIdx.x == 0) sort_giants_body(sm.giants, a.pay.hub_giant, a.pay.slen, a.pay.ctr);
 }
 
 // cooperative launches (the fused front end) need the device attribute; queried once per device
@@ -1867,7 +1857,11 @@ namespace {
 
 int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* count_dev, int64_t ws_batch, double t_last,
                 float neg_lambda, const float* decay, void* ws_dev, size_t ws_bytes, int32_t* err_flag_dev,
-                cudaStream_t stream) {
+                cudaStream_t stream, int phase = TPN_UPDATE_WHOLE) {
+    // phase (tpn_update_phase): TPN_UPDATE_PREPARE launches only what does not write the state — the sort front end
+    // and, in lazy mode, the pre-batch snapshot (the eager sweep writes the state, so an eager snapshot waits for
+    // TPN_UPDATE_APPLY) — and leaves the caller's struct untouched; TPN_UPDATE_APPLY launches the rest with the same
+    // arguments.  The two halves may run on different streams (the caller orders them) with reads of the state between.
     // E is the number of messages, or — count_dev != nullptr, routed calls of a sharded state — its upper bound
     const Count cnt{E, reinterpret_cast<const int*>(count_dev)};
     Workspace ws = carve(ws_dev, ws_batch, st->num_layer, st->row_stride);
@@ -1922,7 +1916,12 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
     StateView view = make_view(st);
     view.epoch = new_epoch;
 
+    const bool do_front = phase != TPN_UPDATE_APPLY;          // sort front end
+    const bool do_rest = phase != TPN_UPDATE_PREPARE;          // everything that writes the state
+    // the snapshot reads decayed pre-batch rows: lazy -> with the front end; eager -> after the sweep
+    const bool snap_early = lazy && !small_path;
     if (small_path) {
+        if (phase == TPN_UPDATE_PREPARE) return TPN_OK;        // single-CTA sort: nothing worth splitting
         SweepArgs sw_args;
         sw_args.total4 = eager_sweep ? sweep_total4 : 0;
         sw_args.ds4 = ds4;
@@ -1935,7 +1934,7 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
         prep_small_kernel<<<grid, kPrepThreads, 0, stream>>>(msgs, E, t_last_f, neg_lambda, st->num_nodes, ws.key_a,
                                                              ws.ssrc, ws.sw, ws.sslot, ws.slen, err_flag_dev, log_w, L,
                                                              new_epoch, dargs, view, sw_args);
-    } else {
+    } else if (do_front) {
         int bits = 0;
         while ((1ll << bits) <= st->num_nodes) ++bits;    // keys are in [0, num_nodes] (num_nodes = dropped)
         const int passes = (bits + 7) / 8;
@@ -1981,14 +1980,12 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
         fa.pay.chunk = (snapshot_path && hubs) ? chunk : 0;
         const bool fused_front = (g_debug_flags & TPN_DEBUG_LEGACY_FRONT) == 0 && front_kernel_ok();
         if (fused_front) {
-            // ONE cooperative launch (<= one CTA per SM): prep, every radix pass, payload, giant ordering
+            // ONE cooperative launch (<= one CTA per SM): prep and every radix pass
             FrontArgs fr;
             fr.prep = fa.prep;
-            fr.pay = fa.pay;
             fr.key_a = ws.key_a; fr.key_b = ws.key_b; fr.val_a = ws.val_a; fr.val_b = ws.val_b;
             fr.hist = ws.hist; fr.hist2 = ws.hist2; fr.bar = ws.bar;
             fr.passes = passes;
-            fr.sort_giants = (snapshot_path && chunk == 0) ? 1 : 0;
             const int sms = device_sm_count();
             const unsigned grid = (unsigned)(nblk < 1 ? 1 : (nblk < sms ? nblk : sms));
             void* kargs[] = {&fr};
@@ -1998,6 +1995,11 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
                 set_cuda_error(cudaGetLastError());
                 return TPN_ERR_CUDA;
             }
+            const bool odd = (passes & 1) != 0;
+            fa.pay.order = odd ? ws.val_b : ws.val_a;
+            fa.pay.skey = odd ? ws.key_b : ws.key_a;     // odd number of passes: sorted keys in key_b; payload copies them
+            payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(fa.pay);
+            if (snapshot_path && chunk == 0) sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr);
         } else
         {
             // >= 2 blocks: the first kCtrSlots threads also zero the per-call counters
@@ -2018,24 +2020,26 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
             payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(fa.pay);
             if (snapshot_path && chunk == 0) sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr);
         }
-        if (eager_sweep) {
-            const long long want = (sweep_total4 + 255) / 256;
-            const long long cap = (long long)device_sm_count() * 16;
-            const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
-            sweep_decay_kernel<<<grid, 256, 0, stream>>>(view, dargs, sweep_total4, ds4);
-        }
+    }
+    if (!small_path && do_rest && eager_sweep) {
+        const long long want = (sweep_total4 + 255) / 256;
+        const long long cap = (long long)device_sm_count() * 16;
+        const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+        sweep_decay_kernel<<<grid, 256, 0, stream>>>(view, dargs, sweep_total4, ds4);
     }
 
     // first source row that is read from the pre-batch snapshot: 1 (P_0 is never written: read in place), or —
     // TPN_DEBUG_SNAPSHOT_P0 — 0: the snapshot also holds P_0, so every source read of the walkers hits one compact buffer
     const int srow0 = (g_debug_flags & TPN_DEBUG_SNAPSHOT_P0) ? 0 : 1;
     if (snapshot_path) {
-        if (L - srow0 >= 1) {
+        if (L - srow0 >= 1 && (snap_early ? do_front : do_rest)) {
             const unsigned grid = (unsigned)(((long long)E * 32 + 255) / 256);
             if (lazy) snapshot_kernel<true><<<grid, 256, 0, stream>>>(view, ws.key_a, cnt, ds4, ws.snap, srow0);
             else snapshot_kernel<false><<<grid, 256, 0, stream>>>(view, ws.key_a, cnt, ds4, ws.snap, srow0);
         }
-        if (hubs) {
+        if (!do_rest) {
+            // TPN_UPDATE_PREPARE ends here
+        } else if (hubs) {
             // large batch: long segments on the CTA-pipelined hub walker, short ones on the
             // persistent warp walker (disjoint target rows; both read only pre-batch values)
             const bool direct = msgs.B == 0;
@@ -2065,8 +2069,8 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
             const int span4 = L * ds4;
             launch_walk<1, 16, true>(view, 0, ws, cnt, ds4, (span4 + 31) / 32, lazy, false, dargs, stream, srow0);
         }
-        if (lazy) stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, 0, ws.key_a, cnt);
-    } else {
+        if (lazy && do_rest) stamp_targets_kernel<<<(E + 255) / 256, 256, 0, stream>>>(view, 0, ws.key_a, cnt);
+    } else if (do_rest) {
         // per-layer walk: V float4 per lane so that one tile covers rows up to 512 floats
         int vpl = (ds4 + 31) / 32;
         int tiles = 1;
@@ -2090,7 +2094,7 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
         }
     }
     const int lrc = check_launch();
-    if (lrc == TPN_OK) {
+    if (lrc == TPN_OK && do_rest) {
         st->epoch = new_epoch;
         st->cum_floor = new_floor;
     }
@@ -2138,6 +2142,27 @@ extern "C" int tpn_update(tpn_state_t* st, const int64_t* src_dev, const int64_t
     msgs.direct_from = st->num_nodes;
     return update_impl(st, msgs, (int)(2 * batch), nullptr, batch, t_last, neg_lambda, decay, ws_dev, ws_bytes,
                        err_flag_dev, reinterpret_cast<cudaStream_t>(stream_v));
+}
+
+extern "C" int tpn_update_phase(tpn_state_t* st, const int64_t* src_dev, const int64_t* dst_dev, const double* t_dev,
+                                int64_t batch, double t_last, float neg_lambda, const float* decay, void* ws_dev,
+                                size_t ws_bytes, int32_t* err_flag_dev, void* stream_v, int phase) {
+    using namespace tpn;
+    int rc = validate_state(st);
+    if (rc != TPN_OK) return rc;
+    if (batch < 1 || batch > ((int64_t)1 << 26) || src_dev == nullptr || dst_dev == nullptr || t_dev == nullptr ||
+        ws_dev == nullptr || st->num_nodes >= (int64_t)0xffffffffll || phase < TPN_UPDATE_WHOLE || phase > TPN_UPDATE_APPLY)
+        return TPN_ERR_INVALID_ARGUMENT;
+    DeviceScope scope(st->data);
+    g_dev_slot = scope.slot();
+    MsgSource msgs;
+    msgs.a = reinterpret_cast<const long long*>(src_dev);
+    msgs.b = reinterpret_cast<const long long*>(dst_dev);
+    msgs.t = t_dev;
+    msgs.B = batch;
+    msgs.direct_from = st->num_nodes;
+    return update_impl(st, msgs, (int)(2 * batch), nullptr, batch, t_last, neg_lambda, decay, ws_dev, ws_bytes,
+                       err_flag_dev, reinterpret_cast<cudaStream_t>(stream_v), phase);
 }
 
 extern "C" int tpn_update_messages(tpn_state_t* st, const int64_t* tgt_dev, const int64_t* src_dev,

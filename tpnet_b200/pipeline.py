@@ -88,7 +88,10 @@ def replay_updates(module, batches: EpochBatches) -> None:
 def tpnet_step(module, batch: Batch, out: Dict[str, torch.Tensor]) -> None:
     """The hot-path calls of one TPNet batch under ``torch.no_grad()`` (evaluate_models_utils.py:64-184): decoder
     features of the positive and the negative pairs, then the update.  ``batch.extra['neg']`` holds the pre-drawn
-    negative destinations (the evaluation samplers are seeded, utils/utils.py:339-359: the same negatives every epoch)."""
+    negative destinations (the evaluation samplers are seeded, utils/utils.py:339-359: the same negatives every epoch).
+    The half of the update that does not write the state (sort by target, work lists, pre-batch snapshot) is started
+    first, on the module's side stream, and overlaps the feature kernels; ``update`` then only runs the rest."""
+    module.update_prepare(batch.src, batch.dst, batch.t, next_time=batch.t_last)
     module.get_pair_wise_feature(batch.src, batch.dst, out=out['pos'][:len(batch)])
     module.get_pair_wise_feature(batch.src, batch.extra['neg'], out=out['neg'][:len(batch)])
     module.update(batch.src, batch.dst, batch.t, next_time=batch.t_last)

@@ -182,6 +182,9 @@ class RandomProjectionModule(nn.Module):
         self._ws: Optional[torch.Tensor] = None
         self._ws_batch = 0
         self._err: Optional[torch.Tensor] = None
+        self._pending = None            # update_prepare: (array ids, n, next_time, C arguments) of the half in flight
+        self._prep_stream: Optional[torch.cuda.Stream] = None
+        self._prep_done: Optional[torch.cuda.Event] = None
         self.validate_ids = True
         self.fused_head = True          # no-grad calls: fused fp32 head kernel when the head has the default shape
         self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module.materialize())
@@ -234,6 +237,7 @@ class RandomProjectionModule(nn.Module):
         self._state = new_state
         self._stamps = None
         self._decay_log = None
+        self._cancel_prepare()
         self._ws = None
         self._ws_batch = 0
         self._err = None
@@ -338,10 +342,17 @@ class RandomProjectionModule(nn.Module):
         return h.stager.upload(host, ck, self.node_num, self._stream())
 
     # ------------------------------------------------------------------ reference API
-    def update(self, src_node_ids: IdArray, dst_node_ids: IdArray, node_interact_times: IdArray,
-               next_time: Optional[float] = None):
-        """TPNet.py:67-99.  ``next_time`` is only needed when the arrays are CUDA tensors
-        (it is ``node_interact_times[-1]``, which the host needs for the f64 decay factors)."""
+    def _cancel_prepare(self) -> None:
+        """A prepared half (update_prepare) is dropped before anything else rewrites the state or its bookkeeping;
+        the next update then runs whole."""
+        if getattr(self, '_pending', None) is not None:
+            torch.cuda.current_stream(self._state.device).wait_event(self._prep_done)
+            self._pending = None
+
+    def _update_args(self, src_node_ids: IdArray, dst_node_ids: IdArray, node_interact_times: IdArray,
+                     next_time: Optional[float]):
+        """Host half of TPNet.py:67-99: argument checks, the f64 decay factors, ids / timestamps on the device, the
+        workspace.  Returns (n, next_time, C arguments after the state pointer and before the stream)."""
         dev = self._require_cuda()
         lib = _lib.load()
         n = int(len(src_node_ids))
@@ -367,14 +378,65 @@ class RandomProjectionModule(nn.Module):
                 self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
             self._ws_batch = n
         args = (ptrs[0], ptrs[1], ptrs[2], n, float(next_time), float(np.float32(-lam)), factors,
-                self._ws.data_ptr(), self._ws.numel(), self._err.data_ptr(), self._stream())
-        rc = lib.tpn_update(st, *args)
+                self._ws.data_ptr(), self._ws.numel(), self._err.data_ptr())
+        return n, float(next_time), args
+
+    def update_prepare(self, src_node_ids: IdArray, dst_node_ids: IdArray, node_interact_times: IdArray,
+                       next_time: Optional[float] = None) -> bool:
+        """Optional, no reference counterpart: starts the half of the NEXT ``update`` that does not write the state
+        (weights, stable sort by target, work lists, lazy mode: the pre-batch snapshot) on a side stream, so that it
+        overlaps the calls that still read the pre-batch state — the reference's loop computes the pair-wise features
+        of a batch and then updates with the same batch (train_link_prediction.py:370-373,
+        evaluate_models_utils.py:182-184).  The following ``update`` call with the same arrays only runs the rest.
+        Results are identical with or without it; any other ``update`` call falls back to the whole update.
+        Returns False when nothing was started (small batch, or the decay log must be restarted first)."""
+        dev = self._require_cuda()
+        lib = _lib.load()
+        self._pending = None
+        n, next_time, args = self._update_args(src_node_ids, dst_node_ids, node_interact_times, next_time)
+        if 2 * n <= 4096:
+            return False
+        if self._prep_stream is None:
+            self._prep_stream = torch.cuda.Stream(dev)
+            self._prep_done = torch.cuda.Event()
+        cur = torch.cuda.current_stream(dev)
+        side = self._prep_stream
+        side.wait_stream(cur)                        # fork: the staged ids and every earlier write of the state
+        rc = lib.tpn_update_phase(self._c_state(), *args, side.cuda_stream, _lib.UPDATE_PREPARE)
+        if rc == _lib.TPN_ERR_LOG_FULL:              # the log restart rewrites the state: not while it is being read
+            cur.wait_stream(side)
+            return False
+        if rc:
+            _lib.check(rc, 'tpn_update_phase(prepare)')
+        self._prep_done.record(side)
+        self._pending = (id(src_node_ids), id(dst_node_ids), id(node_interact_times), n, next_time, args)
+        return True
+
+    def update(self, src_node_ids: IdArray, dst_node_ids: IdArray, node_interact_times: IdArray,
+               next_time: Optional[float] = None):
+        """TPNet.py:67-99.  ``next_time`` is only needed when the arrays are CUDA tensors
+        (it is ``node_interact_times[-1]``, which the host needs for the f64 decay factors)."""
+        dev = self._require_cuda()
+        lib = _lib.load()
+        pend, self._pending = self._pending, None
+        phase = _lib.UPDATE_WHOLE
+        if pend is not None:
+            torch.cuda.current_stream(dev).wait_event(self._prep_done)       # join (also frees the workspace)
+            if pend[:4] == (id(src_node_ids), id(dst_node_ids), id(node_interact_times), int(len(src_node_ids))) and \
+                    (next_time is None or float(next_time) == pend[4]):
+                n, next_time, args = pend[3], pend[4], pend[5]
+                phase = _lib.UPDATE_APPLY
+        if phase == _lib.UPDATE_WHOLE:
+            n, next_time, args = self._update_args(src_node_ids, dst_node_ids, node_interact_times, next_time)
+        st = self._c_state()
+        rc = lib.tpn_update_phase(st, *args, self._stream(), phase)
         if rc == _lib.TPN_ERR_LOG_FULL:
             self._restart_log()
             st = self._c_state()
-            rc = lib.tpn_update(st, *args)
+            rc = lib.tpn_update_phase(st, *args, self._stream(), _lib.UPDATE_WHOLE)
         if rc:
             _lib.check(rc, 'tpn_update')
+        h = self._h
         h.epoch = int(h.st.epoch)
         h.launches += 1
         h.now = float(next_time)
@@ -513,6 +575,7 @@ class RandomProjectionModule(nn.Module):
     def reset_random_projections(self):
         """TPNet.py:131-139.  (Called once per epoch by train_link_prediction.py:248: also the point where
         an out-of-range id of a device-resident batch — which a kernel can only flag — is raised.)"""
+        self._cancel_prepare()
         self._require_cuda()
         if self._h.device_ids_seen:
             self.check_errors()
@@ -540,6 +603,7 @@ class RandomProjectionModule(nn.Module):
 
     def reload_random_projections(self, random_projections):
         """TPNet.py:149-157."""
+        self._cancel_prepare()
         now_time, layers = random_projections
         with torch.no_grad():
             self.now_time.data.copy_(now_time.to(self.now_time.device))       # in place: same storage (CUDA graphs)
@@ -558,6 +622,9 @@ class RandomProjectionModule(nn.Module):
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
         self._ws_batch = max(self._ws_batch, int(batch))
+        if self._prep_stream is None:
+            self._prep_stream = torch.cuda.Stream(dev)
+            self._prep_done = torch.cuda.Event()
         ids = torch.zeros(max(int(batch), 1), dtype=torch.int64, device=dev)
         with torch.no_grad():
             self.get_pair_wise_feature(ids, ids)
@@ -565,6 +632,7 @@ class RandomProjectionModule(nn.Module):
     # ------------------------------------------------------------------ lazy-decay maintenance
     def materialize(self) -> None:
         """Bring every row current (no-op in eager mode or off-GPU)."""
+        self._cancel_prepare()
         if self._state.device.type != 'cuda' or not self.lazy or self._stamps is None or self._h.epoch == 0:
             return
         lib = _lib.load()
@@ -572,6 +640,7 @@ class RandomProjectionModule(nn.Module):
         self._h.launches += 1
 
     def _restart_log(self) -> None:
+        self._cancel_prepare()
         lib = _lib.load()
         self.materialize()
         _lib.check(lib.tpn_reset_epoch(self._c_state(), self._stream()), 'tpn_reset_epoch')

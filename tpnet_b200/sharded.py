@@ -614,6 +614,13 @@ class ShardedRandomProjection(RandomProjectionModule):
         plan = self._make_plan(tgt, oth)
         return plan, np.ascontiguousarray(tm[plan.keep])
 
+    def update_prepare(self, src_node_ids, dst_node_ids, node_interact_times, next_time=None) -> bool:
+        """One shard: the plain module's early half.  Several shards: not split (routing and the pulls of the update
+        follow the pair-wise calls of the batch, whose cached rows they reuse) — returns False."""
+        if self.world == 1:
+            return RandomProjectionModule.update_prepare(self, src_node_ids, dst_node_ids, node_interact_times, next_time)
+        return False
+
     def update(self, src_node_ids, dst_node_ids, node_interact_times, next_time=None, plan=None):
         """TPNet.py:67-99 on the sharded state.  All ranks must call it with the same batch."""
         if self.world == 1 and plan is None:
