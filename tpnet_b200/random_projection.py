@@ -397,7 +397,7 @@ class RandomProjectionModule(nn.Module):
         if 2 * n <= 4096:
             return False
         if self._prep_stream is None:
-            self._prep_stream = torch.cuda.Stream(dev)
+            self._prep_stream = torch.cuda.Stream(dev, priority=-1)      # its CTAs go first when SM slots free up
             self._prep_done = torch.cuda.Event()
         cur = torch.cuda.current_stream(dev)
         side = self._prep_stream
@@ -623,7 +623,7 @@ class RandomProjectionModule(nn.Module):
             self._ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
         self._ws_batch = max(self._ws_batch, int(batch))
         if self._prep_stream is None:
-            self._prep_stream = torch.cuda.Stream(dev)
+            self._prep_stream = torch.cuda.Stream(dev, priority=-1)      # its CTAs go first when SM slots free up
             self._prep_done = torch.cuda.Event()
         ids = torch.zeros(max(int(batch), 1), dtype=torch.int64, device=dev)
         with torch.no_grad():
