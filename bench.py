@@ -78,12 +78,15 @@ def parse_args():
     ap.add_argument('--no-also', action='store_true', help='N=1: skip the secondary measurements')
     ap.add_argument('--e2e-sync-read', action='store_true',
                     help='e2e: read every step\'s result with a blocking .item() instead of the pinned 2-slot ring')
+    ap.add_argument('--no-feature-overlap', action='store_true',
+                    help='N=1: both decoder calls on one stream (default: the (src, neg) call on the module\'s feature stream)')
     ap.add_argument('--no-prepare', action='store_true',
                     help='N=1: do not start the state-independent half of the update (update_prepare) ahead of the '
                          'pair-wise calls of the same batch')
     ap.add_argument('--no-parity', action='store_true', help='N>1: skip the sharded-vs-single-GPU parity leg')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'nccl'], help='N>1: data plane of the sharded state')
     ap.add_argument('--cpu-sample-steps', type=int, default=None)
+    ap.add_argument('--no-cpu', action='store_true', help='A/B runs: skip the cpu_baseline leg (the line is then not a bench line)')
     ap.add_argument('--cpu-threads', type=int, default=None, help='--impl reference: host threads (default: all cores)')
     ap.add_argument('--warm-batches', type=int, default=None, help='untimed batches that fill the state')
     ap.add_argument('--pl-nodes', type=int, default=None, help='override the power-law node count (debug)')
@@ -669,8 +672,17 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
         if world == 1 and not args.no_prepare:
             # the half of the update that does not write the state starts now, on the module's side stream
             m.update_prepare(st['src'], st['dst'], st['t'], next_time=st['t_last'])
-        resident_pairs(st, 'pos')
-        resident_pairs(st, 'neg')
+        if world == 1 and not args.no_feature_overlap:
+            # the two decoder calls are independent: the head of one overlaps the row gather of the other
+            cur, fs = torch.cuda.current_stream(device), m.feature_stream()
+            fs.wait_stream(cur)
+            with torch.cuda.stream(fs):
+                resident_pairs(st, 'neg')
+            resident_pairs(st, 'pos')
+            cur.wait_stream(fs)
+        else:
+            resident_pairs(st, 'pos')
+            resident_pairs(st, 'neg')
         resident_update(st)
 
     # Every step is captured once into a CUDA graph and replayed once, in order (the host-side launch latency of
@@ -1002,7 +1014,9 @@ def main():
             if rank == 0:
                 line['parity'] = parity
         if rank == 0:
-            if world == 1:
+            if world == 1 and args.no_cpu:
+                line['cpu_baseline'] = None
+            elif world == 1:
                 n_cpu = args.cpu_sample_steps or 3
                 shape = powerlaw_shape(args)
                 sec, n_small, kind = cpu_port_powerlaw(shape, args.pl_batch, 1, n_cpu, threads, scale_down=10)

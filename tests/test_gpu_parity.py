@@ -276,15 +276,18 @@ def test_update_bit_exact_with_equal_timestamps(B, N, dim, L, mode):
     m.check_errors()
 
 
-@pytest.mark.parametrize('flags', [0, 1, 2], ids=['concurrent', 'per-layer', 'serial'])
+@pytest.mark.parametrize('flags', [0, 1, 2, 32, 64], ids=['concurrent', 'per-layer', 'serial', 'no-stream', 'stream-all'])
 @pytest.mark.parametrize('mode', ['eager', 'lazy', 'lazy-frozen'])
 @pytest.mark.parametrize('B,N,dim,L,skew', [(6000, 300, 210, 3, 1.3), (2100, 50, 140, 3, 1.1), (9000, 2000, 36, 4, 1.5),
                                             (5000, 40, 300, 1, 1.2), (3000, 30, 64, 2, 1.05), (4000, 60, 1000, 2, 1.3),
-                                            (3000, 70000, 16, 2, 1.2)])      # 1, 2 and 3 radix passes
+                                            (3000, 70000, 16, 2, 1.2),       # 1, 2 and 3 radix passes
+                                            (20000, 100, 48, 3, 1.4),        # several giants
+                                            (4000, 60, 64, 2, 2.2)])         # one target holds 2/3 of the batch: streamed by default
 def test_hub_walker_bit_exact(B, N, dim, L, skew, mode, flags):
     """Long segments (>= 64 messages on one target) leave the warp walker for the CTA-pipelined
-    hub walkers (cp.async / TMA rings + mbarriers): giant (>= 2048) and regular hubs, 64-float
-    column slices (d=210 -> 216-float rows -> 4 slices of 56/56/56/48 per row; d=1000 -> 16),
+    hub walkers (cp.async / TMA rings + mbarriers): giant (>= 2048) and regular hubs — giants STREAMED by default
+    when one of them holds more than 3/8 of the batch's messages (products materialised by producer CTAs, chains fed by
+    bulk copies; 'no-stream': never, 'stream-all': every giant) — 64-float column slices (d=210 -> 216-float rows -> 4 slices of 56/56/56/48 per row; d=1000 -> 16),
     the snapshot + all-layer launches (hub walker on the side stream concurrently with the
     short-segment walker, or serially) and the per-layer launches, eager and lazy decay.
     Equal timestamps make w == 1, so eager (and lazy with a frozen clock) must equal the

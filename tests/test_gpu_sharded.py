@@ -113,16 +113,26 @@ def _global_layers(ranks, N, L, streams):
     return full
 
 
-@pytest.mark.parametrize('world', [2, 4])
+@pytest.mark.parametrize('world,flags', [(2, 0), (4, 0), (2, 64)], ids=['world2', 'world4', 'world2-stream-all'])
 @pytest.mark.parametrize('mode', ['eager', 'lazy'])
-def test_peer_data_plane_equals_single_gpu(world, mode):
-    """Sharded over `world` ranks == the plain module, BIT FOR BIT (eager and lazy: a cached remote row carries
+def test_peer_data_plane_equals_single_gpu(world, mode, flags):
+    """'stream-all' (TPN_DEBUG_STREAM_ALL): every giant segment of the routed message-mode updates takes the streamed
+    path of the hub walker (received rows with their own stamps included).
+    Sharded over `world` ranks == the plain module, BIT FOR BIT (eager and lazy: a cached remote row carries
     its owner's stamps, so it is read with the same single multiply as on one GPU), through batches that take the
     single-CTA sort, the radix sort, the short-segment walker and the hub walkers; pair-wise features of the
     routed call; reset / backup / reload; error flags."""
     import numpy as np
-    from tpnet_b200 import RandomProjectionModule
+    from tpnet_b200 import RandomProjectionModule, _lib
     dev = 'cuda:0'
+    old_flags = _lib.load().tpn_set_debug_flags(flags)
+    try:
+        _peer_data_plane_case(world, mode, dev, np, RandomProjectionModule)
+    finally:
+        _lib.load().tpn_set_debug_flags(old_flags)
+
+
+def _peer_data_plane_case(world, mode, dev, np, RandomProjectionModule):
     for (N, dim, L, sizes) in [(403, 20, 3, (200, 3000)), (2003, 140, 3, (9000, 200, 25000)), (997, 36, 2, (40000,))]:
         kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=1e-4, device=dev,
                   use_matrix=False, beginning_time=np.float64(0.0), not_scale=False, enforce_dim=dim)

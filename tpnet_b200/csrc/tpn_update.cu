@@ -77,6 +77,11 @@ constexpr int kHub2Stages = kHub2Producers + 4;            // ring stages of 32 
 // ctr[] slots (zeroed by prep_large_kernel)
 constexpr int kCtrGiant = 0, kCtrHub = 1, kCtrWork0 = 2, kCtrSmall = 6, kCtrHub2Work = 7, kCtrHub2Giant = 8;
 constexpr int kCtrChunks = 9;            // chunked accumulation: partial-sum rows handed out so far
+// streamed giants (walk_hub2_kernel): the first ctr[kCtrStream] entries of the (sorted) giant list have their message
+// products materialised by producer CTAs and their add chains fed from that stream by bulk copies
+constexpr int kCtrStream = 10, kCtrStreamBlocks = 11, kCtrStreamProd = 12, kCtrStreamActive = 13;
+constexpr int kStreamSlice = kHub2GiantFloats;      // floats between messages of a slice chunk: a giant's ring-stage layout
+constexpr int kStreamBlock = 32 * kGiantSpm;        // messages per production block (one flag; one 8 KB bulk copy per slice)
 constexpr uint32_t kNoPart = 0xffffffffu;   // hub_part[e]: the entry accumulates straight into its target row
 constexpr int kCtrSmClaim = 16;          // [256] first hub2 CTA of each SM claims the SM's giant-segment slot
 constexpr int kCtrSlots = kCtrSmClaim + 256;
@@ -153,7 +158,13 @@ struct Workspace {
     uint32_t* giant_cbase; // [E / kGiantMin + 2] first partial-sum row of the i-th giant (chunked accumulation)
     float* partial;        // [E / kChunkMin + E / kGiantMin + 2][L*row_stride] partial sums of giant chunks
     int* svst;             // [L-1][E] pre-batch stamp of the source row of each sorted message (lazy, per-layer path)
+    float* gprod;          // [E][nslice * 32] products fmul_rn(source, w) of the messages of streamed giants, per block
+                           //     of 128 messages slice-major: [slice][message][32 columns]
+    uint32_t* gflag;       // [E / 128 + E / kGiantMin + 2] block q of the streamed giants has been produced (zeroed per call
+                           //     by sort_giants_kernel)
+    uint32_t* gblk;        // [kGiantSortMax + 1] first block of the i-th giant of the sorted list (prefix sum)
     bool has_snap;
+    bool has_stream;       // the product buffer of the streamed giants fits (and the giant list can always be ordered)
     size_t bytes;
 };
 
@@ -163,6 +174,16 @@ inline size_t snap_bytes(size_t E, int num_layer, int64_t row_stride) {
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr size_t kStreamMaxBytes = (size_t)4 << 30;      // product buffer of the streamed giants: above this, hub walker
+constexpr int kGiantSortMaxC = 2048;     // giants ordered (and streamed) per call; more than this: unordered, hub walker
+inline int stream_slices(int num_layer, int64_t row_stride) {           // = L * spr_g of launch_walk_hub2
+    return num_layer * (int)((row_stride + kStreamSlice - 1) / kStreamSlice);
+}
+inline size_t stream_prod_bytes(size_t E, int num_layer, int64_t row_stride) {
+    return sizeof(float) * E * (size_t)stream_slices(num_layer, row_stride) * kStreamSlice + 256;
+}
+inline size_t stream_flag_words(size_t E) { return E / kStreamBlock + E / kGiantMin + 4; }
 
 Workspace carve(void* base, int64_t batch, int num_layer, int64_t row_stride) {
     const size_t E = 2 * (size_t)batch;
@@ -197,6 +218,11 @@ Workspace carve(void* base, int64_t batch, int num_layer, int64_t row_stride) {
     ws.ctr = reinterpret_cast<uint32_t*>(take(4 * kCtrSlots));
     ws.small_heads = reinterpret_cast<uint32_t*>(take(4 * E));
     ws.svst = reinterpret_cast<int*>(take(4 * (E + 4) * (size_t)(num_layer > 1 ? num_layer - 1 : 1) + 16));
+    ws.gflag = reinterpret_cast<uint32_t*>(take(4 * stream_flag_words(E)));
+    ws.gblk = reinterpret_cast<uint32_t*>(take(4 * (kGiantSortMaxC + 1)));
+    ws.has_stream = ws.has_snap && stream_prod_bytes(E, num_layer, row_stride) <= kStreamMaxBytes &&
+                    E / kGiantMin + 2 <= (size_t)kGiantSortMaxC;
+    ws.gprod = reinterpret_cast<float*>(take(ws.has_stream ? stream_prod_bytes(E, num_layer, row_stride) : 16));
     ws.bytes = off;
     return ws;
 }
@@ -715,14 +741,26 @@ __global__ void __launch_bounds__(256) payload_kernel(PayloadArgs a) {
 
 // Longest giant segments first: their add chains are the critical path of the hub walker.
 // (Scheduling order only — results do not depend on it.)
-constexpr int kGiantSortMax = 2048;
+constexpr int kGiantSortMax = kGiantSortMaxC;
 struct GiantSmem {
-    uint32_t head_s[kGiantSortMax], len_s[kGiantSortMax];
+    uint32_t head_s[kGiantSortMax], len_s[kGiantSortMax], sorted_s[kGiantSortMax];
 };
+// Also decides which giants are STREAMED (walk_hub2_kernel): the first n_stream entries of the sorted list;
+// gblk[i] = first production block of the i-th of them.  stream_mode 0: none; 2: every giant (tests); 1: those whose
+// add chain would otherwise be the critical path of the whole update.  Measured on B200 (profiles/r02_stream_giants.txt):
+// the gathering hub walker adds a giant at ~10 cycles per message, the update as a whole costs ~3 cycles per message
+// of the batch (throughput), a streamed chain ~4.5 cycles per message plus ~2.6 cycles per streamed message of extra
+// traffic spread over all SMs — so streaming pays when 10 len > 3 E + 2.6 len, i.e. len > 3/8 of the batch's messages
+// (the hub-owning rank of a sharded power-law state), and costs time below that (many mid-size giants: throughput-bound).
 __device__ __forceinline__ void sort_giants_body(GiantSmem& sm, uint32_t* __restrict__ hub_giant,
-                                                 const uint32_t* __restrict__ slen, const uint32_t* __restrict__ ctr) {
+                                                 const uint32_t* __restrict__ slen, uint32_t* __restrict__ ctr,
+                                                 uint32_t* __restrict__ gblk, uint32_t* __restrict__ gflag, Count count,
+                                                 int stream_mode) {
+    const uint32_t stream_min = stream_mode == 0 ? 0u
+                                : (stream_mode == 2 ? (uint32_t)kGiantMin
+                                                    : max((uint32_t)kGiantMin, (uint32_t)(((long long)count.get() * 3) >> 3)));
     const int n = (int)ctr[kCtrGiant];
-    if (n < 2 || n > kGiantSortMax) return;
+    if (n < 1 || n > kGiantSortMax) return;          // ctr[kCtrStream] stays 0: the hub walker takes every giant
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         sm.head_s[i] = hub_giant[i];
         sm.len_s[i] = slen[sm.head_s[i]];
@@ -733,12 +771,32 @@ __device__ __forceinline__ void sort_giants_body(GiantSmem& sm, uint32_t* __rest
         int rank = 0;
         for (int j = 0; j < n; ++j) rank += (sm.len_s[j] > li || (sm.len_s[j] == li && j < i)) ? 1 : 0;
         hub_giant[rank] = sm.head_s[i];
+        sm.sorted_s[rank] = li;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && stream_min > 0) {
+        uint32_t blocks = 0;
+        int ns = 0;
+        for (; ns < n && sm.sorted_s[ns] >= stream_min; ++ns) {
+            gblk[ns] = blocks;
+            blocks += (sm.sorted_s[ns] + (uint32_t)kStreamBlock - 1u) / (uint32_t)kStreamBlock;
+        }
+        gblk[ns] = blocks;
+        ctr[kCtrStream] = (uint32_t)ns;
+        ctr[kCtrStreamBlocks] = blocks;
+        sm.head_s[0] = blocks;
+    }
+    __syncthreads();
+    if (stream_min > 0) {                      // "produced" flags of this call's blocks (uniform branch)
+        const uint32_t blocks = sm.head_s[0];
+        for (uint32_t i = threadIdx.x; i < blocks; i += blockDim.x) gflag[i] = 0;
     }
 }
 __global__ void __launch_bounds__(1024)
-sort_giants_kernel(uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ slen, const uint32_t* __restrict__ ctr) {
+sort_giants_kernel(uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ slen, uint32_t* __restrict__ ctr,
+                   uint32_t* __restrict__ gblk, uint32_t* __restrict__ gflag, Count count, int stream_mode) {
     __shared__ GiantSmem sm;
-    sort_giants_body(sm, hub_giant, slen, ctr);
+    sort_giants_body(sm, hub_giant, slen, ctr, gblk, gflag, count, stream_mode);
 }
 
 // ---------------------------------------------------------------- fused front end (large path)
@@ -1416,6 +1474,190 @@ __device__ unsigned long long g_hub2_timeline[8 * 256 * 8];
 #define HUB2_STAMP(pass, ev) do { } while (0)
 #endif
 
+// Streamed giants.  A giant's messages must be added one at a time, and in the walker above the chain's own SM also has
+// to GATHER them (64-byte pieces of random rows): an SM sustains only ~6-10 B/clk of such gathers (outstanding-miss
+// capacity), 10 cycles per message where the add chain alone needs 4.  For the first ctr[kCtrStream] giants of the sorted
+// list the two halves are therefore split over the CTAs of the hub walker:
+//   produce : a work item = block q of 128 consecutive messages of one giant.  The CTA's 8 warps read WHOLE source rows
+//       (rows 0..L-1 are contiguous: full cache lines, the HBM-efficient access), form the reference's rounded products
+//       fmul_rn(x, w) (TPNet.py:91-96; plus the pending decay of received rows of a sharded state) and write them
+//       slice-major — [slice][message][16 floats], the layout of a ring stage — then publish the block's flag (release).
+//   chain   : the (giant, slice) work item as before, but its ring is filled by ONE loader thread: flag (acquire) -> one
+//       8 KB bulk copy per stage (sequential lines, 11 stages = 88 KB in flight, no per-message gather).  The consumer warp
+//       is unchanged: acc = fadd_rn(acc, product) in sorted-message order, bit-identical to every other path.
+// No co-residency assumption: giant items are only taken by the CTA that claimed its SM, the other CTAs register as
+// producers when they start and take every production block before anything else; a claiming CTA that sees no
+// registered producer after a short wait registers itself and produces first.  A registered producer never waits, so
+// every flag is eventually set (also inside CUDA graphs and under a serialising profiler); the flag wait is bounded anyway.
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+template <bool LAZY, bool DIRECT>
+__device__ __noinline__ void hub2_produce_block(const StateView& st, uint32_t q, uint32_t n_stream,
+                                                   const uint32_t* __restrict__ ssrc, const float* __restrict__ sw,
+                                                   const uint32_t* __restrict__ sslot, const uint32_t* __restrict__ slen,
+                                                   const float* __restrict__ snap, const uint32_t* __restrict__ hub_giant,
+                                                   const uint32_t* __restrict__ gblk, float* __restrict__ gprod,
+                                                   uint32_t* __restrict__ gflag, int srow0, int spr_g, int slice_w_g) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kWarps = kHub2Threads / 32;
+    const int L = st.num_layer;
+    const int rs = (int)st.row_stride;
+    const int ds4 = rs >> 2;
+    const int span4 = L * ds4;
+    const int first_snap4 = srow0 * ds4;          // float4 index where the rows read from the snapshot start
+    const size_t mstride = (size_t)(L * spr_g) * kStreamSlice;     // floats of product space per message
+    uint32_t lo = 0, hi = n_stream - 1;            // giant of block q: last i with gblk[i] <= q
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (gblk[mid] <= q) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t b = q - gblk[lo];
+    const uint32_t head = hub_giant[lo];
+    const int len = (int)slen[head];
+    const int first = (int)(b * kStreamBlock);
+    const int nm = min(kStreamBlock, len - first);
+    float* const out = gprod + (size_t)(head + first) * mstride;
+    const size_t sstride = (size_t)nm * kStreamSlice;              // floats between slices of this block
+    // two messages per warp and pass: 8 row requests of 512 bytes in flight per warp
+    for (int m0 = warp; m0 < nm; m0 += 2 * kWarps) {
+        const float* bs[2];                        // rows read from the state (P_0; every row of a received row)
+        const float* bn[2];                        // rows >= srow0: pre-batch snapshot of the source's own segment
+        float w[2], f[2][TPN_MAX_LAYERS];
+        bool have[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int m = m0 + u * kWarps;
+            have[u] = m < nm;
+            const uint32_t j = head + first + (have[u] ? m : m0);
+            const uint32_t v = ssrc[j];
+            const uint32_t x = sslot[j];
+            w[u] = sw[j];
+            const bool direct = DIRECT && (x & kDirect) != 0;
+            float fmine = 1.0f;                     // received row of another rank: its own stamp -> this call's epoch
+            if (DIRECT) {
+                if (LAZY && direct && lane >= 1 && lane < L) {
+                    const int sst = st.stamps[(long long)v * L + (lane - 1)];
+                    if (sst >= 0) fmine = decay_factor(st, lane - 1, sst);
+                }
+                w[u] = fabsf(w[u]);
+            }
+#pragma unroll
+            for (int l = 0; l < TPN_MAX_LAYERS; ++l) f[u][l] = DIRECT ? __shfl_sync(0xffffffffu, fmine, l) : 1.0f;
+            bs[u] = st.data + (long long)v * st.node_stride;
+            bn[u] = direct ? bs[u] : snap + (long long)x * (long long)(L - srow0) * rs - (long long)srow0 * rs;
+        }
+        for (int i0 = lane; i0 < span4; i0 += 128) {
+            float4 xv[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = i0 + 32 * k;
+                    if (have[u] && i < span4) xv[u][k] = ld4((i < first_snap4 ? bs[u] : bn[u]) + 4 * (long long)i);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + 32 * k;
+                if (i < span4) {
+                    // float4 i of the run = row r, column col -> slice r * spr_g + col / slice_w_g (the hub walker's slices)
+                    const int r = (i >= ds4 ? 1 : 0) + (i >= 2 * ds4 ? 1 : 0) + (i >= 3 * ds4 ? 1 : 0);
+                    const int col = 4 * (i - r * ds4);
+                    const int ks = slice_w_g == 16 ? (col >> 4) : col / slice_w_g;
+                    float* const o = out + (size_t)(r * spr_g + ks) * sstride + (col - ks * slice_w_g);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (have[u]) {
+                            if (DIRECT) scale4(xv[u][k], r == 0 ? f[u][0] : (r == 1 ? f[u][1] : (r == 2 ? f[u][2] : f[u][3])));
+                            scale4(xv[u][k], w[u]);
+                            st4(o + (size_t)(m0 + u * kWarps) * kStreamSlice, xv[u][k]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    fence_proxy_async_global();                   // these generic-proxy writes are read by bulk copies (async proxy)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gflag + q), "r"(1u) : "memory");
+    }
+}
+
+
+// Feeds the ring of a streamed giant item: warp 2 polls the producers' flags, warp 1 issues the bulk copies (one lane
+// each), so a flag round trip never delays a copy.  Kept out of line: the gathering path keeps its register allocation.
+__device__ __noinline__ void hub2_stream_feed(int warp, int lane, volatile int* ready_s, uint32_t q0,
+                                              const uint32_t* __restrict__ gflag, const float* __restrict__ gprod,
+                                              int* __restrict__ err, int nblk, uint32_t blk_base, int len, uint32_t head,
+                                              int slice, int slices_g, float* ring, uint64_t* full, uint64_t* empty) {
+    if (warp == 2 && lane == 0) {
+        int ready = 0;                  // leading blocks known to be produced (ready_s was reset by thread 0)
+        while (ready < nblk) {
+            uint32_t seen = 0;
+            long long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(gflag + q0 + ready) : "memory");
+                if (seen != 0) break;
+                if (++spins > (1ll << 21)) {       // seconds: cannot happen (see above); never hang the GPU
+                    if (err != nullptr) *err = 8;
+                    ready = nblk - 1;
+                    break;
+                }
+                __nanosleep(32);
+            }
+            ++ready;
+            // the producers usually run far ahead: one round trip looks at the next 12 flags
+            uint32_t fl[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                fl[k] = 0;
+                if (ready + k < nblk)
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(fl[k]) : "l"(gflag + q0 + ready + k) : "memory");
+            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            int more = 0;
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                if (fl[k] != 0 && more == k) ++more;
+            ready += more;
+            __threadfence_block();
+            *ready_s = ready;
+        }
+    } else if (warp == 1) {
+        const size_t mstride = (size_t)slices_g * kStreamSlice;
+        int fenced = 0;             // blocks [0, fenced) are ordered for this thread's async-proxy reads
+        for (int b = 0; b < nblk; ++b) {
+            const uint32_t g = blk_base + (uint32_t)b;
+            const uint32_t use = g / (uint32_t)kHub2Stages;
+            const int stage = (int)(g - use * (uint32_t)kHub2Stages);
+            if (lane == 0) {
+                if (use > 0) mbar_wait(&empty[stage], (use - 1u) & 1u);
+                if (b >= fenced) {
+                    // one proxy fence per batch of newly produced blocks, not per copy
+                    int r;
+                    while ((r = *ready_s) <= b) { }
+                    __threadfence_block();
+                    fence_proxy_async_global();
+                    fenced = r;
+                }
+                const int first = b * kStreamBlock;
+                const int nmb = min(kStreamBlock, len - first);
+                const uint32_t bytes = (uint32_t)nmb * kStreamSlice * 4u;
+                const float* src = gprod + (size_t)(head + first) * mstride + (size_t)slice * (size_t)(nmb * kStreamSlice);
+                mbar_expect_tx(&full[stage], bytes);          // one of the stage's 32 arrivals, plus the bytes
+                bulk_g2s(ring + (size_t)stage * (32 * kHub2SlotFloats), src, bytes, &full[stage]);
+            }
+            __syncwarp();
+            if (lane != 0) mbar_arrive(&full[stage]);
+        }
+    }
+}
+
+
 __host__ __device__ inline size_t hub2_smem_bytes() {
     return (size_t)kHub2Stages * (32 * kHub2SlotFloats * 4 + 16) + 16;
 }
@@ -1428,12 +1670,15 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                  const uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ hub_reg,
                  uint32_t* __restrict__ ctr, int spr_g, int slice_w_g, int spr_r, int slice_w_r, DecayArgs dnow,
                  const uint32_t* __restrict__ hub_len, const uint32_t* __restrict__ hub_part,
-                 float* __restrict__ partial, int chunked, int srow0) {
+                 float* __restrict__ partial, int chunked, int srow0, const uint32_t* __restrict__ gblk,
+                 float* __restrict__ gprod, uint32_t* __restrict__ gflag, int* __restrict__ err) {
+    static_assert(kStreamSlice == kHub2GiantFloats && kStreamBlock == 32 * kGiantSpm,
+                  "a production block of one slice is exactly one ring stage of a giant item");
     extern __shared__ __align__(128) unsigned char hub2_raw[];
     float* const ring = reinterpret_cast<float*>(hub2_raw);                       // [stages][32][kHub2SlotFloats]
     uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)kHub2Stages * 32 * kHub2SlotFloats);
     uint64_t* const empty = full + kHub2Stages;
-    int* const item = reinterpret_cast<int*>(empty + kHub2Stages);
+    int* const item = reinterpret_cast<int*>(empty + kHub2Stages);          // [0]: work item, [1]: its kind
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int L = st.num_layer;
@@ -1455,24 +1700,64 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
     const uint32_t slices_g = (uint32_t)(L * spr_g), slices_r = (uint32_t)(L * spr_r);
     // chunked accumulation: giants were expanded into chunk entries of the regular list (payload_kernel)
     const uint32_t total_g = chunked ? 0u : n_giant * slices_g, total_r = n_reg * slices_r;
+    // streamed giants: [0, n_stream) of the sorted giant list; their products come in stream_blocks production blocks
+    const uint32_t n_stream = chunked ? 0u : ctr[kCtrStream];
+    const uint32_t stream_blocks = n_stream > 0 ? ctr[kCtrStreamBlocks] : 0u;
+    // scheduling state, meaningful in thread 0 only
+    bool prod_first = false, prod_done = n_stream == 0, giants_done = !(prefer_giant && total_g > 0);
+    if (threadIdx.x == 0 && n_stream > 0) {
+        if (!prefer_giant) {
+            atomicAdd(&ctr[kCtrStreamActive], 1u);       // registered: takes every production block before anything else
+        } else {
+            // a chain is only started once some CTA is registered as a producer (normally the other CTA of this SM,
+            // microseconds at most); otherwise this CTA registers itself and produces first
+            uint32_t active = 0;
+            for (int spins = 0; spins < 16; ++spins) {               // ~15 us at most
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(active) : "l"(ctr + kCtrStreamActive) : "memory");
+                if (active != 0) break;
+                __nanosleep(200);
+            }
+            if (active == 0) {
+                atomicAdd(&ctr[kCtrStreamActive], 1u);
+                prod_first = true;
+            }
+        }
+    }
     uint32_t blk_base = 0;      // ring blocks produced / consumed so far by this CTA (same count in every warp)
     for (;;) {
         if (threadIdx.x == 0) {
             int w = -1;          // >= 0: giant item, <= -2: regular item -(w + 2), -1: nothing left
-            if (prefer_giant && total_g > 0) {
+            int kind = 0;        // 1: w is a production block of the streamed giants
+            if (prod_first && !prod_done) {
+                const uint32_t q = atomicAdd(&ctr[kCtrStreamProd], 1u);
+                if (q < stream_blocks) { w = (int)q; kind = 1; } else prod_done = true;
+            }
+            if (kind == 0 && !giants_done) {
                 const uint32_t g = atomicAdd(&ctr[kCtrHub2Giant], 1u);
-                if (g < total_g) w = (int)g;
+                if (g < total_g) w = (int)g; else giants_done = true;
+            }
+            if (w == -1 && !prod_done) {
+                const uint32_t q = atomicAdd(&ctr[kCtrStreamProd], 1u);
+                if (q < stream_blocks) { w = (int)q; kind = 1; } else prod_done = true;
             }
             if (w == -1 && total_r > 0) {
                 const uint32_t q = atomicAdd(&ctr[kCtrHub2Work], 1u);
                 if (q < total_r) w = -(int)q - 2;
             }
-            *item = w;
+            item[0] = w;
+            item[1] = kind;
+            item[2] = 0;
         }
         __syncthreads();
-        const int work = *item;
+        const int work = item[0];
+        const int kind = item[1];
         __syncthreads();
         if (work == -1) break;
+        if (kind == 1) {
+            hub2_produce_block<LAZY, DIRECT>(st, (uint32_t)work, n_stream, ssrc, sw, sslot, slen, snap, hub_giant, gblk, gprod,
+                                             gflag, srow0, spr_g, slice_w_g);
+            continue;
+        }
         const bool giant = work >= 0;
         const uint32_t idx = giant ? (uint32_t)work : (uint32_t)(-(work + 2));
         const int spr = giant ? spr_g : spr_r;
@@ -1480,6 +1765,7 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
         const uint32_t slices = giant ? slices_g : slices_r;
         const uint32_t hub = idx / slices;
         const int slice = (int)(idx - hub * slices);
+        const bool streamed = giant && hub < n_stream;      // products come from the producers' stream, not from a gather
         const int r = slice / spr;                      // source row 0..L-1 -> target layer r+1
         const int c0 = (slice - r * spr) * slice_w;     // first column of the slice inside the row
         const int width = min(rs, c0 + slice_w) - c0;   // floats, multiple of 4
@@ -1494,7 +1780,11 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
         const int mps = 32 * spm;                       // messages per stage
         const int nblk = (len + mps - 1) / mps;
         if (width > 0) {
-            if (warp >= 1) {
+            if (warp >= 1 && streamed) {
+                // ------------------------------------------------ streamed giant: the ring is fed from the producers' stream
+                hub2_stream_feed(warp, lane, item + 2, gblk[hub], gflag, gprod, err, nblk, blk_base, len, (uint32_t)head, slice,
+                                 (int)slices_g, ring, full, empty);
+            } else if (warp >= 1) {
                 // ------------------------------------------------ producers
                 const int pw = warp - 1;
                 const int nvec = width >> 2;            // 16-byte pieces per message (<= 4 giant, <= 16 otherwise)
@@ -1681,9 +1971,10 @@ combine_giants_kernel(StateView st, const uint32_t* __restrict__ skey, const uin
     }
 }
 
+
 template <bool DIRECT>
 int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const DecayArgs& dnow, int chunk, int srow0,
-                     cudaStream_t stream) {
+                     int* err_flag_dev, cudaStream_t stream) {
     static bool configured_tab[kMaxDevices];          // per device: the shared-memory opt-in is a device attribute
     bool& configured = configured_tab[g_dev_slot];
     const int smem = (int)hub2_smem_bytes();
@@ -1711,13 +2002,13 @@ int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const D
                                                                              ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
                                                                              spr_g, slice_w_g, spr_r, slice_w_r, dnow,
                                                                              ws.hub_len, ws.hub_part, ws.partial, chunked,
-                                                                             srow0);
+                                                                             srow0, ws.gblk, ws.gprod, ws.gflag, err_flag_dev);
     else
         walk_hub2_kernel<false, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                               ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
                                                                               spr_g, slice_w_g, spr_r, slice_w_r, dnow,
                                                                               ws.hub_len, ws.hub_part, ws.partial, chunked,
-                                                                              srow0);
+                                                                              srow0, ws.gblk, ws.gprod, ws.gflag, err_flag_dev);
     if (chunked) {
         const unsigned cgrid = (unsigned)device_sm_count();
         if (lazy)
@@ -1911,6 +2202,9 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
     if (chunk > kGiantMin) chunk = kGiantMin;
     chunk &= ~31;
     const long long sweep_total4 = st->num_nodes * (long long)L * ds4;
+    // streamed giants (snapshot path, reference order): decided here so that both halves of a split call agree
+    const int stream_mode = (ws.has_stream && chunk == 0 && (g_debug_flags & TPN_DEBUG_NO_STREAM) == 0)
+                                ? ((g_debug_flags & TPN_DEBUG_STREAM_ALL) ? 2 : 1) : 0;
 
     // the kernels read the NEW epoch; the caller's struct is only advanced once every launch went through
     StateView view = make_view(st);
@@ -1999,7 +2293,9 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
             fa.pay.order = odd ? ws.val_b : ws.val_a;
             fa.pay.skey = odd ? ws.key_b : ws.key_a;     // odd number of passes: sorted keys in key_b; payload copies them
             payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(fa.pay);
-            if (snapshot_path && chunk == 0) sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr);
+            if (snapshot_path && chunk == 0) {
+                sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr, ws.gblk, ws.gflag, cnt, stream_mode);
+            }
         } else
         {
             // >= 2 blocks: the first kCtrSlots threads also zero the per-call counters
@@ -2018,7 +2314,9 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
             fa.pay.order = vin;
             fa.pay.skey = kin;          // odd number of passes: sorted keys live in key_b; payload copies them to key_a
             payload_kernel<<<(E + 255) / 256, 256, 0, stream>>>(fa.pay);
-            if (snapshot_path && chunk == 0) sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr);
+            if (snapshot_path && chunk == 0) {
+                sort_giants_kernel<<<1, 1024, 0, stream>>>(ws.hub_giant, ws.slen, ws.ctr, ws.gblk, ws.gflag, cnt, stream_mode);
+            }
         }
     }
     if (!small_path && do_rest && eager_sweep) {
@@ -2052,8 +2350,8 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
                 else
                     (void)cudaGetLastError();
             }
-            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, chunk, srow0, hub_stream)
-                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, chunk, srow0, hub_stream);
+            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, chunk, srow0, err_flag_dev, hub_stream)
+                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, chunk, srow0, err_flag_dev, hub_stream);
             if (hrc != TPN_OK) return hrc;
             if (direct) launch_walk_small<true>(view, ws, E, ds4, lazy, dargs, srow0, stream);
             else launch_walk_small<false>(view, ws, E, ds4, lazy, dargs, srow0, stream);

@@ -90,10 +90,17 @@ def tpnet_step(module, batch: Batch, out: Dict[str, torch.Tensor]) -> None:
     features of the positive and the negative pairs, then the update.  ``batch.extra['neg']`` holds the pre-drawn
     negative destinations (the evaluation samplers are seeded, utils/utils.py:339-359: the same negatives every epoch).
     The half of the update that does not write the state (sort by target, work lists, pre-batch snapshot) is started
-    first, on the module's side stream, and overlaps the feature kernels; ``update`` then only runs the rest."""
+    first, on the module's side stream, and overlaps the feature kernels; ``update`` then only runs the rest.
+    The two feature calls are independent: the second runs on the module's feature stream, so the tensor-core head of
+    one overlaps the HBM-bound row gather of the other (same results; forked and joined on the current stream)."""
     module.update_prepare(batch.src, batch.dst, batch.t, next_time=batch.t_last)
+    cur = torch.cuda.current_stream(batch.src.device)
+    fs = module.feature_stream()
+    fs.wait_stream(cur)
+    with torch.cuda.stream(fs):
+        module.get_pair_wise_feature(batch.src, batch.extra['neg'], out=out['neg'][:len(batch)])
     module.get_pair_wise_feature(batch.src, batch.dst, out=out['pos'][:len(batch)])
-    module.get_pair_wise_feature(batch.src, batch.extra['neg'], out=out['neg'][:len(batch)])
+    cur.wait_stream(fs)
     module.update(batch.src, batch.dst, batch.t, next_time=batch.t_last)
 
 

@@ -185,6 +185,7 @@ class RandomProjectionModule(nn.Module):
         self._pending = None            # update_prepare: (array ids, n, next_time, C arguments) of the half in flight
         self._prep_stream: Optional[torch.cuda.Stream] = None
         self._prep_done: Optional[torch.cuda.Event] = None
+        self._feature_stream: Optional[torch.cuda.Stream] = None
         self.validate_ids = True
         self.fused_head = True          # no-grad calls: fused fp32 head kernel when the head has the default shape
         self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module.materialize())
@@ -465,6 +466,16 @@ class RandomProjectionModule(nn.Module):
             raise ValueError(f'out must be a contiguous float32 tensor of shape {tuple(shape)} on {dev}')
         return out
 
+    def feature_stream(self) -> torch.cuda.Stream:
+        """A second stream for feature calls that are independent of each other (no reference counterpart): the two
+        decoder calls of a batch — (src, dst) and (src, neg) — only read the state, so one can run here while the other
+        runs on the current stream; the tensor-core head of one call then overlaps the HBM-bound gather of the other.
+        The caller forks and joins: ``fs.wait_stream(cur)`` ... ``cur.wait_stream(fs)`` (``pipeline.tpnet_step``)."""
+        dev = self._require_cuda()
+        if self._feature_stream is None:
+            self._feature_stream = torch.cuda.Stream(dev)
+        return self._feature_stream
+
     def pair_wise_gram(self, src_node_ids: IdArray, dst_node_ids: IdArray, out: Optional[torch.Tensor] = None
                        ) -> torch.Tensor:
         """The input of ``self.mlp``: TPNet.py:119-128 (everything before the head)."""
@@ -625,6 +636,7 @@ class RandomProjectionModule(nn.Module):
         if self._prep_stream is None:
             self._prep_stream = torch.cuda.Stream(dev, priority=-1)      # its CTAs go first when SM slots free up
             self._prep_done = torch.cuda.Event()
+        self.feature_stream()
         ids = torch.zeros(max(int(batch), 1), dtype=torch.int64, device=dev)
         with torch.no_grad():
             self.get_pair_wise_feature(ids, ids)
