@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from tpnet_b200 import RandomProjectionModule, _lib  # noqa: E402
 
 dev = 'cuda:0'
-N, B = 1_000_001, 100_000
+N, B = 1_000_001, int(os.environ.get('PROBE_HUB', 100_000))
 m = RandomProjectionModule(node_num=N, edge_num=10**9, dim_factor=10, num_layer=3, time_decay_weight=1e-7, device=dev,
                            use_matrix=False, beginning_time=np.float64(0.0), not_scale=False, enforce_dim=-1,
                            decay_mode='lazy', init_p0=False, state_device=dev).to(dev)
@@ -35,9 +35,11 @@ assert lib.tpn_debug_hub_timeline(buf, n) == 0
 a = np.array(buf[:], dtype=np.int64).reshape(8, 256, 8)
 t0 = a[0, 0, 0]
 print('consumer (warp 0) per stage: [before wait, after wait, after chain, after release]')
-for b in range(60, 70):
+for b in range(200, 206):
     print('  stage', b, (a[0, b, :4] - t0).tolist())
-d = a[0, 40:200]
+d = a[0, 40:250]
+print('consumer, stages 40-120 :', 'period', np.diff(a[0, 40:120, 0]).mean(), 'wait', (a[0, 40:120, 1] - a[0, 40:120, 0]).mean())
+print('consumer, stages 170-250:', 'period', np.diff(a[0, 170:250, 0]).mean(), 'wait', (a[0, 170:250, 1] - a[0, 170:250, 0]).mean())
 print('consumer: period', np.diff(d[:, 0]).mean(), 'wait', (d[:, 1] - d[:, 0]).mean(), 'chain', (d[:, 2] - d[:, 1]).mean(),
       'release', (d[:, 3] - d[:, 2]).mean())
 print('producer warp 1 per pass: [start, meta issued, rows issued, after wait-empty, rows arrived, stored, published]')

@@ -103,6 +103,42 @@ __global__ void chain_lds32_db(const float* __restrict__ in, float* out, long lo
     if (lane == 0) cyc[0] = t1 - t0;
 }
 
+// (e) transposed layout [col][128 messages], 16-byte slots swizzled by the column (slot ^ (col & 7)): one LDS.128 per
+// 4 messages, conflict-free for every quarter-warp; 8 loads (32 messages) ahead
+__global__ void chain_lds128_t(const float* __restrict__ in, float* out, long long* cyc) {
+    __shared__ __align__(16) float buf[16 * kMsgs];
+    for (int i = threadIdx.x; i < 16 * kMsgs; i += 32) buf[i] = in[i];
+    __syncwarp();
+    const int lane = threadIdx.x;
+    const int c = lane & 15;
+    float acc = 0.f;
+    const float4* col = reinterpret_cast<const float4*>(buf + c * kMsgs);
+    const long long t0 = clock64();
+    float4 a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = col[j ^ (c & 7)];
+    for (int s = 0; s < kStages; ++s) {
+#pragma unroll
+        for (int blk = 0; blk < 4; blk += 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = col[((blk + 1) * 8 + j) ^ (c & 7)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc = __fadd_rn(acc, a[j].x); acc = __fadd_rn(acc, a[j].y); acc = __fadd_rn(acc, a[j].z); acc = __fadd_rn(acc, a[j].w);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = col[(((blk + 2) & 3) * 8 + j) ^ (c & 7)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc = __fadd_rn(acc, b[j].x); acc = __fadd_rn(acc, b[j].y); acc = __fadd_rn(acc, b[j].z); acc = __fadd_rn(acc, b[j].w);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    out[lane] = acc;
+    if (lane == 0) cyc[0] = t1 - t0;
+}
+
 int main() {
     float *in, *out;
     long long* cyc;
@@ -122,6 +158,9 @@ int main() {
         chain_lds64_db<<<1, 32>>>(in, out, cyc);
         cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         printf("lds64 transposed, dbuf : %.2f cycles/message\n", h / n);
+        chain_lds128_t<<<1, 32>>>(in, out, cyc);
+        cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("lds128 transposed+swz  : %.2f cycles/message\n", h / n);
         chain_regs<<<1, 32>>>(in, out, cyc);
         cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         printf("register chain (floor) : %.2f cycles/message\n", h / n);

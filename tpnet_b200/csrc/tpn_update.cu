@@ -79,7 +79,7 @@ constexpr int kCtrGiant = 0, kCtrHub = 1, kCtrWork0 = 2, kCtrSmall = 6, kCtrHub2
 constexpr int kCtrChunks = 9;            // chunked accumulation: partial-sum rows handed out so far
 // streamed giants (walk_hub2_kernel): the first ctr[kCtrStream] entries of the (sorted) giant list have their message
 // products materialised by producer CTAs and their add chains fed from that stream by bulk copies
-constexpr int kCtrStream = 10, kCtrStreamBlocks = 11, kCtrStreamProd = 12, kCtrStreamActive = 13;
+constexpr int kCtrStream = 10, kCtrStreamBlocks = 11, kCtrStreamProd = 12, kCtrStreamActive = 13, kCtrStreamChain = 14, kCtrStreamTicket = 15;
 constexpr int kStreamSlice = kHub2GiantFloats;      // floats between messages of a slice chunk: a giant's ring-stage layout
 constexpr int kStreamBlock = 32 * kGiantSpm;        // messages per production block (one flag; one 8 KB bulk copy per slice)
 constexpr uint32_t kNoPart = 0xffffffffu;   // hub_part[e]: the entry accumulates straight into its target row
@@ -1470,14 +1470,70 @@ walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_
 __device__ unsigned long long g_hub2_timeline[8 * 256 * 8];
 #define HUB2_STAMP(pass, ev) \
     do { if (work == 0 && lane == 0 && (pass) < 256) g_hub2_timeline[(warp * 256 + (pass)) * 8 + (ev)] = clock64(); } while (0)
+#define HUB2_STAMP_W0(pass, ev) \
+    do { if (stamp_me && lane == 0 && (pass) < 256) g_hub2_timeline[(0 * 256 + (pass)) * 8 + (ev)] = clock64(); } while (0)
 #else
 #define HUB2_STAMP(pass, ev) do { } while (0)
+#define HUB2_STAMP_W0(pass, ev) do { } while (0)
 #endif
+
+// The add chain of one giant work item (consumer warp): one column per lane, stages of 128 messages x 16 floats.
+// Out of line on purpose: inside the walker's 128-register allocation ptxas sinks the loads to ~10 messages ahead of
+// their adds, and a shared-memory load that queues behind the other warps' global loads and stores on this SM then
+// arrives late — measured 6.9 cycles per message for the chain alone where the same loop runs at 4.1 on an idle SM
+// (scripts/micro/chain_bench.cu).  Here the 32 values of the NEXT group are loaded before the 32 dependent adds of the
+// current one, and the next stage's barrier is tested under the adds of a stage's last group.
+__device__ __noinline__ float hub2_giant_chain(float acc, const float* ring, uint64_t* full, uint64_t* empty,
+                                               uint32_t blk_base, int nblk, int len, int col, int lane, bool stamp_me) {
+    constexpr int mps = 32 * kGiantSpm;
+    (void)stamp_me;                     // only the timeline build reads it
+    bool next_full = false;             // the next stage's `full` phase was already seen complete
+    for (int b = 0; b < nblk; ++b) {
+        const uint32_t g = blk_base + (uint32_t)b;
+        const uint32_t use = g / (uint32_t)kHub2Stages;
+        const int stage = (int)(g - use * (uint32_t)kHub2Stages);
+        HUB2_STAMP_W0(b, 0);
+        if (!next_full) mbar_wait(&full[stage], use & 1u);
+        next_full = false;
+        HUB2_STAMP_W0(b, 1);
+        const int nm = min(mps, len - b * mps);
+        const float* xs = ring + (size_t)stage * (32 * kHub2SlotFloats) + col;
+        int j0 = 0;
+        if (nm == mps) {
+            float va[32], vb[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) va[j] = xs[j * kHub2GiantFloats];
+#pragma unroll
+            for (int q = 0; q < kGiantSpm; ++q) {
+                float* cur = (q & 1) ? vb : va;
+                float* nxt = (q & 1) ? va : vb;
+                if (q + 1 < kGiantSpm) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) nxt[j] = xs[(32 * (q + 1) + j) * kHub2GiantFloats];
+                } else if (b + 1 < nblk) {
+                    const uint32_t g1 = g + 1u;
+                    const uint32_t use1 = g1 / (uint32_t)kHub2Stages;
+                    next_full = mbar_test(&full[g1 - use1 * (uint32_t)kHub2Stages], use1 & 1u);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, cur[j]);
+            }
+            j0 = nm;
+        }
+        for (; j0 < nm; ++j0) acc = __fadd_rn(acc, xs[j0 * kHub2GiantFloats]);
+        HUB2_STAMP_W0(b, 2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        HUB2_STAMP_W0(b, 3);
+    }
+    return acc;
+}
+
 
 // Streamed giants.  A giant's messages must be added one at a time, and in the walker above the chain's own SM also has
 // to GATHER them (64-byte pieces of random rows): an SM sustains only ~6-10 B/clk of such gathers (outstanding-miss
 // capacity), 10 cycles per message where the add chain alone needs 4.  For the first ctr[kCtrStream] giants of the sorted
-// list the two halves are therefore split over the CTAs of the hub walker:
+// list the two halves are therefore split over the CTAs of walk_stream_kernel:
 //   produce : a work item = block q of 128 consecutive messages of one giant.  The CTA's 8 warps read WHOLE source rows
 //       (rows 0..L-1 are contiguous: full cache lines, the HBM-efficient access), form the reference's rounded products
 //       fmul_rn(x, w) (TPNet.py:91-96; plus the pending decay of received rows of a sharded state) and write them
@@ -1485,16 +1541,13 @@ __device__ unsigned long long g_hub2_timeline[8 * 256 * 8];
 //   chain   : the (giant, slice) work item as before, but its ring is filled by ONE loader thread: flag (acquire) -> one
 //       8 KB bulk copy per stage (sequential lines, 11 stages = 88 KB in flight, no per-message gather).  The consumer warp
 //       is unchanged: acc = fadd_rn(acc, product) in sorted-message order, bit-identical to every other path.
-// No co-residency assumption: giant items are only taken by the CTA that claimed its SM, the other CTAs register as
-// producers when they start and take every production block before anything else; a claiming CTA that sees no
-// registered producer after a short wait registers itself and produces first.  A registered producer never waits, so
-// every flag is eventually set (also inside CUDA graphs and under a serialising profiler); the flag wait is bounded anyway.
+// The roles and why no deadlock is possible: see walk_stream_kernel.  The flag wait is bounded anyway.
 __device__ __forceinline__ void fence_proxy_async_global() {
     asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
 template <bool LAZY, bool DIRECT>
-__device__ __noinline__ void hub2_produce_block(const StateView& st, uint32_t q, uint32_t n_stream,
+__device__ __forceinline__ void hub2_produce_block(const StateView& st, uint32_t q, uint32_t n_stream,
                                                    const uint32_t* __restrict__ ssrc, const float* __restrict__ sw,
                                                    const uint32_t* __restrict__ sslot, const uint32_t* __restrict__ slen,
                                                    const float* __restrict__ snap, const uint32_t* __restrict__ hub_giant,
@@ -1590,7 +1643,7 @@ __device__ __noinline__ void hub2_produce_block(const StateView& st, uint32_t q,
 
 // Feeds the ring of a streamed giant item: warp 2 polls the producers' flags, warp 1 issues the bulk copies (one lane
 // each), so a flag round trip never delays a copy.  Kept out of line: the gathering path keeps its register allocation.
-__device__ __noinline__ void hub2_stream_feed(int warp, int lane, volatile int* ready_s, uint32_t q0,
+__device__ __forceinline__ void hub2_stream_feed(int warp, int lane, volatile int* ready_s, uint32_t q0,
                                               const uint32_t* __restrict__ gflag, const float* __restrict__ gprod,
                                               int* __restrict__ err, int nblk, uint32_t blk_base, int len, uint32_t head,
                                               int slice, int slices_g, float* ring, uint64_t* full, uint64_t* empty) {
@@ -1658,6 +1711,135 @@ __device__ __noinline__ void hub2_stream_feed(int warp, int lane, volatile int* 
 }
 
 
+// The streamed giants of one update: ONE launch beside walk_hub2_kernel (which skips them), same CTA shape and ring.
+//   * CTAs take a ticket when they start.  Tickets 1..C chain: they pull (giant, slice) items — the longest giant's
+//     slices first — warp 0 adds, warp 1 issues the bulk copies, warp 2 polls the flags;
+//   * every other CTA (ticket 0 included) registers as a producer when it starts and takes production blocks until none
+//     are left, then exits;
+//   * a chaining CTA only starts once a producer is registered; if none shows up within microseconds it registers
+//     itself and produces first.  A registered producer never waits for anything, so every flag a chain waits for is
+//     eventually set whatever else is (or is not) resident: no co-residency assumption between CTAs or launches — valid
+//     inside CUDA graphs, on aliased hardware queues and under a serialising profiler.  (The first design had producers
+//     and chains as two launches on two streams: it passed the tests and then hung in the bench, where the process owns
+//     more streams than hardware queues and the chain kernel was queued in front of its own producers.)
+template <bool LAZY, bool DIRECT>
+__global__ void __launch_bounds__(kHub2Threads, 2)
+walk_stream_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ssrc,
+                   const float* __restrict__ sw, const uint32_t* __restrict__ sslot, const uint32_t* __restrict__ slen,
+                   const float* __restrict__ snap, const uint32_t* __restrict__ hub_giant, uint32_t* __restrict__ ctr,
+                   int spr_g, int slice_w_g, int srow0, const uint32_t* __restrict__ gblk, float* __restrict__ gprod,
+                   uint32_t* __restrict__ gflag, int* __restrict__ err) {
+    static_assert(kStreamSlice == kHub2GiantFloats && kStreamBlock == 32 * kGiantSpm,
+                  "a production block of one slice is exactly one ring stage of a giant item");
+    const uint32_t n_stream = ctr[kCtrStream];
+    if (n_stream == 0) return;                       // the usual case: nothing is streamed
+    extern __shared__ __align__(128) unsigned char stream_raw[];
+    float* const ring = reinterpret_cast<float*>(stream_raw);                     // [stages][128 messages][16 floats]
+    uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)kHub2Stages * 32 * kHub2SlotFloats);
+    uint64_t* const empty = full + kHub2Stages;
+    int* const item = reinterpret_cast<int*>(empty + kHub2Stages);          // [0]: work item, [1]: its kind, [2]: ready blocks
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int L = st.num_layer;
+    const int rs = (int)st.row_stride;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kHub2Stages; ++i) {
+            mbar_init(&full[i], 32);                   // the loader warp: lane 0 with the bytes, 31 plain arrivals
+            mbar_init(&empty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *item = (int)atomicAdd(&ctr[kCtrStreamTicket], 1u);
+    }
+    __syncthreads();
+    const uint32_t ticket = (uint32_t)*item;
+    __syncthreads();
+    const uint32_t slices_g = (uint32_t)(L * spr_g);
+    const uint32_t total_c = n_stream * slices_g;
+    const uint32_t stream_blocks = ctr[kCtrStreamBlocks];
+    // one CTA per SM (the grid): tickets 1..C chain, C = one per chain item but at most half of the grid; ticket 0 and
+    // the rest produce.  The producers only have to stay ahead of the chains (a chain consumes ~0.3 messages per ns,
+    // a producer CTA delivers ~8 per us), so they leave the other half of every SM to the walkers of the other segments.
+    const bool chains = ticket >= 1u && ticket <= min(total_c, gridDim.x / 2u);
+    // scheduling state, meaningful in thread 0 only
+    bool prod_first = !chains, prod_done = false, chains_done = !chains;
+    if (threadIdx.x == 0) {
+        if (!chains) {
+            atomicAdd(&ctr[kCtrStreamActive], 1u);
+        } else {
+            uint32_t active = 0;
+            for (int spins = 0; spins < 16; ++spins) {               // ~15 us at most
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(active) : "l"(ctr + kCtrStreamActive) : "memory");
+                if (active != 0) break;
+                __nanosleep(200);
+            }
+            if (active == 0) {
+                atomicAdd(&ctr[kCtrStreamActive], 1u);
+                prod_first = true;
+            }
+        }
+    }
+    uint32_t blk_base = 0;      // ring stages used so far by this CTA (same count in every warp)
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int w = -1, kind = 0;        // kind 1: production block w; kind 0: chain item w; w == -1: nothing left
+            if (prod_first && !prod_done) {
+                const uint32_t q = atomicAdd(&ctr[kCtrStreamProd], 1u);
+                if (q < stream_blocks) { w = (int)q; kind = 1; } else prod_done = true;
+            }
+            if (w == -1 && !chains_done) {
+                const uint32_t c = atomicAdd(&ctr[kCtrStreamChain], 1u);
+                if (c < total_c) w = (int)c; else chains_done = true;
+            }
+            if (w == -1 && !prod_done) {               // a chaining CTA that ran out of chains helps the producers
+                const uint32_t q = atomicAdd(&ctr[kCtrStreamProd], 1u);
+                if (q < stream_blocks) { w = (int)q; kind = 1; } else prod_done = true;
+            }
+            item[0] = w;
+            item[1] = kind;
+            item[2] = 0;
+        }
+        __syncthreads();
+        const int work = item[0];
+        const int kind = item[1];
+        __syncthreads();
+        if (work == -1) break;
+        if (kind == 1) {
+            hub2_produce_block<LAZY, DIRECT>(st, (uint32_t)work, n_stream, ssrc, sw, sslot, slen, snap, hub_giant, gblk, gprod,
+                                             gflag, srow0, spr_g, slice_w_g);
+            continue;
+        }
+        const uint32_t hub = (uint32_t)work / slices_g;              // giant-major: the longest giant's slices first
+        const int slice = (int)((uint32_t)work - hub * slices_g);
+        const int r = slice / spr_g;                     // source row 0..L-1 -> target layer r+1
+        const int c0 = (slice - r * spr_g) * slice_w_g;  // first column of the slice inside the row
+        const int width = min(rs, c0 + slice_w_g) - c0;
+        const int head = (int)hub_giant[hub];
+        const int len = (int)slen[head];
+        const int nblk = (len + kStreamBlock - 1) / kStreamBlock;
+        if (width > 0) {
+            if (warp >= 1) {
+                hub2_stream_feed(warp, lane, item + 2, gblk[hub], gflag, gprod, err, nblk, blk_base, len, (uint32_t)head, slice,
+                                 (int)slices_g, ring, full, empty);
+            } else {
+                const uint32_t key = skey[head];
+                const bool active = lane < width;
+                float* const tptr = st.data + (long long)key * st.node_stride + (long long)(r + 1) * rs + c0 + lane;
+                float acc = 0.f;
+                if (active) {
+                    acc = *tptr;                               // zeros if never written
+                    if (LAZY) {
+                        const int ts = st.stamps[(long long)key * L + r];
+                        if (ts >= 0) acc = __fmul_rn(acc, decay_factor(st, r, ts));
+                    }
+                }
+                acc = hub2_giant_chain(acc, ring, full, empty, blk_base, nblk, len, lane, lane, work == 0);
+                if (active) *tptr = acc;
+            }
+            blk_base += (uint32_t)nblk;
+        }
+    }
+}
+
 __host__ __device__ inline size_t hub2_smem_bytes() {
     return (size_t)kHub2Stages * (32 * kHub2SlotFloats * 4 + 16) + 16;
 }
@@ -1670,15 +1852,12 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
                  const uint32_t* __restrict__ hub_giant, const uint32_t* __restrict__ hub_reg,
                  uint32_t* __restrict__ ctr, int spr_g, int slice_w_g, int spr_r, int slice_w_r, DecayArgs dnow,
                  const uint32_t* __restrict__ hub_len, const uint32_t* __restrict__ hub_part,
-                 float* __restrict__ partial, int chunked, int srow0, const uint32_t* __restrict__ gblk,
-                 float* __restrict__ gprod, uint32_t* __restrict__ gflag, int* __restrict__ err) {
-    static_assert(kStreamSlice == kHub2GiantFloats && kStreamBlock == 32 * kGiantSpm,
-                  "a production block of one slice is exactly one ring stage of a giant item");
+                 float* __restrict__ partial, int chunked, int srow0) {
     extern __shared__ __align__(128) unsigned char hub2_raw[];
     float* const ring = reinterpret_cast<float*>(hub2_raw);                       // [stages][32][kHub2SlotFloats]
     uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)kHub2Stages * 32 * kHub2SlotFloats);
     uint64_t* const empty = full + kHub2Stages;
-    int* const item = reinterpret_cast<int*>(empty + kHub2Stages);          // [0]: work item, [1]: its kind
+    int* const item = reinterpret_cast<int*>(empty + kHub2Stages);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int L = st.num_layer;
@@ -1696,76 +1875,38 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
     __syncthreads();
     const bool prefer_giant = *item != 0;          // this CTA holds its SM's giant-segment slot
     __syncthreads();
-    const uint32_t n_giant = ctr[kCtrGiant], n_reg = ctr[kCtrHub];
+    // giants [0, n_stream) of the sorted list belong to walk_stream_kernel (0 in chunked mode: no giant ordering)
+    const uint32_t n_stream = ctr[kCtrStream];
+    const uint32_t n_giant = ctr[kCtrGiant] - n_stream, n_reg = ctr[kCtrHub];
     const uint32_t slices_g = (uint32_t)(L * spr_g), slices_r = (uint32_t)(L * spr_r);
     // chunked accumulation: giants were expanded into chunk entries of the regular list (payload_kernel)
     const uint32_t total_g = chunked ? 0u : n_giant * slices_g, total_r = n_reg * slices_r;
-    // streamed giants: [0, n_stream) of the sorted giant list; their products come in stream_blocks production blocks
-    const uint32_t n_stream = chunked ? 0u : ctr[kCtrStream];
-    const uint32_t stream_blocks = n_stream > 0 ? ctr[kCtrStreamBlocks] : 0u;
-    // scheduling state, meaningful in thread 0 only
-    bool prod_first = false, prod_done = n_stream == 0, giants_done = !(prefer_giant && total_g > 0);
-    if (threadIdx.x == 0 && n_stream > 0) {
-        if (!prefer_giant) {
-            atomicAdd(&ctr[kCtrStreamActive], 1u);       // registered: takes every production block before anything else
-        } else {
-            // a chain is only started once some CTA is registered as a producer (normally the other CTA of this SM,
-            // microseconds at most); otherwise this CTA registers itself and produces first
-            uint32_t active = 0;
-            for (int spins = 0; spins < 16; ++spins) {               // ~15 us at most
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(active) : "l"(ctr + kCtrStreamActive) : "memory");
-                if (active != 0) break;
-                __nanosleep(200);
-            }
-            if (active == 0) {
-                atomicAdd(&ctr[kCtrStreamActive], 1u);
-                prod_first = true;
-            }
-        }
-    }
     uint32_t blk_base = 0;      // ring blocks produced / consumed so far by this CTA (same count in every warp)
     for (;;) {
         if (threadIdx.x == 0) {
             int w = -1;          // >= 0: giant item, <= -2: regular item -(w + 2), -1: nothing left
-            int kind = 0;        // 1: w is a production block of the streamed giants
-            if (prod_first && !prod_done) {
-                const uint32_t q = atomicAdd(&ctr[kCtrStreamProd], 1u);
-                if (q < stream_blocks) { w = (int)q; kind = 1; } else prod_done = true;
-            }
-            if (kind == 0 && !giants_done) {
+            if (prefer_giant && total_g > 0) {
                 const uint32_t g = atomicAdd(&ctr[kCtrHub2Giant], 1u);
-                if (g < total_g) w = (int)g; else giants_done = true;
-            }
-            if (w == -1 && !prod_done) {
-                const uint32_t q = atomicAdd(&ctr[kCtrStreamProd], 1u);
-                if (q < stream_blocks) { w = (int)q; kind = 1; } else prod_done = true;
+                if (g < total_g) w = (int)g;
             }
             if (w == -1 && total_r > 0) {
                 const uint32_t q = atomicAdd(&ctr[kCtrHub2Work], 1u);
                 if (q < total_r) w = -(int)q - 2;
             }
-            item[0] = w;
-            item[1] = kind;
-            item[2] = 0;
+            *item = w;
         }
         __syncthreads();
-        const int work = item[0];
-        const int kind = item[1];
+        const int work = *item;
         __syncthreads();
         if (work == -1) break;
-        if (kind == 1) {
-            hub2_produce_block<LAZY, DIRECT>(st, (uint32_t)work, n_stream, ssrc, sw, sslot, slen, snap, hub_giant, gblk, gprod,
-                                             gflag, srow0, spr_g, slice_w_g);
-            continue;
-        }
         const bool giant = work >= 0;
         const uint32_t idx = giant ? (uint32_t)work : (uint32_t)(-(work + 2));
         const int spr = giant ? spr_g : spr_r;
         const int slice_w = giant ? slice_w_g : slice_w_r;
         const uint32_t slices = giant ? slices_g : slices_r;
-        const uint32_t hub = idx / slices;
-        const int slice = (int)(idx - hub * slices);
-        const bool streamed = giant && hub < n_stream;      // products come from the producers' stream, not from a gather
+        const uint32_t hub_i = idx / slices;
+        const int slice = (int)(idx - hub_i * slices);
+        const uint32_t hub = giant ? hub_i + n_stream : hub_i;
         const int r = slice / spr;                      // source row 0..L-1 -> target layer r+1
         const int c0 = (slice - r * spr) * slice_w;     // first column of the slice inside the row
         const int width = min(rs, c0 + slice_w) - c0;   // floats, multiple of 4
@@ -1780,11 +1921,7 @@ walk_hub2_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_t
         const int mps = 32 * spm;                       // messages per stage
         const int nblk = (len + mps - 1) / mps;
         if (width > 0) {
-            if (warp >= 1 && streamed) {
-                // ------------------------------------------------ streamed giant: the ring is fed from the producers' stream
-                hub2_stream_feed(warp, lane, item + 2, gblk[hub], gflag, gprod, err, nblk, blk_base, len, (uint32_t)head, slice,
-                                 (int)slices_g, ring, full, empty);
-            } else if (warp >= 1) {
+            if (warp >= 1) {
                 // ------------------------------------------------ producers
                 const int pw = warp - 1;
                 const int nvec = width >> 2;            // 16-byte pieces per message (<= 4 giant, <= 16 otherwise)
@@ -1974,7 +2111,7 @@ combine_giants_kernel(StateView st, const uint32_t* __restrict__ skey, const uin
 
 template <bool DIRECT>
 int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const DecayArgs& dnow, int chunk, int srow0,
-                     int* err_flag_dev, cudaStream_t stream) {
+                     cudaStream_t stream) {
     static bool configured_tab[kMaxDevices];          // per device: the shared-memory opt-in is a device attribute
     bool& configured = configured_tab[g_dev_slot];
     const int smem = (int)hub2_smem_bytes();
@@ -2002,13 +2139,13 @@ int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const D
                                                                              ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
                                                                              spr_g, slice_w_g, spr_r, slice_w_r, dnow,
                                                                              ws.hub_len, ws.hub_part, ws.partial, chunked,
-                                                                             srow0, ws.gblk, ws.gprod, ws.gflag, err_flag_dev);
+                                                                             srow0);
     else
         walk_hub2_kernel<false, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                               ws.snap, ws.hub_giant, ws.hub_reg, ws.ctr,
                                                                               spr_g, slice_w_g, spr_r, slice_w_r, dnow,
                                                                               ws.hub_len, ws.hub_part, ws.partial, chunked,
-                                                                              srow0, ws.gblk, ws.gprod, ws.gflag, err_flag_dev);
+                                                                              srow0);
     if (chunked) {
         const unsigned cgrid = (unsigned)device_sm_count();
         if (lazy)
@@ -2018,6 +2155,37 @@ int launch_walk_hub2(const StateView& v, const Workspace& ws, bool lazy, const D
             combine_giants_kernel<false><<<cgrid, 256, 0, stream>>>(v, ws.key_a, ws.slen, ws.hub_giant, ws.giant_cbase,
                                                                     ws.ctr, ws.partial, chunk);
     }
+    return TPN_OK;
+}
+
+// Streamed giants: one launch; exits at once when the front end streamed nothing (ctr[kCtrStream] == 0).
+template <bool DIRECT>
+int launch_walk_stream(const StateView& v, const Workspace& ws, bool lazy, int srow0, int* err_flag_dev, cudaStream_t stream) {
+    static bool configured_tab[kMaxDevices];
+    bool& configured = configured_tab[g_dev_slot];
+    const int smem = (int)hub2_smem_bytes();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(walk_stream_kernel<false, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(walk_stream_kernel<true, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_cuda_error(e);
+            return TPN_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int rs = (int)v.row_stride;
+    const int spr_g = (rs + kHub2GiantFloats - 1) / kHub2GiantFloats;
+    const int slice_w_g = (((rs + spr_g - 1) / spr_g) + 3) & ~3;
+    const unsigned grid = (unsigned)device_sm_count();
+    if (lazy)
+        walk_stream_kernel<true, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
+                                                                               ws.snap, ws.hub_giant, ws.ctr, spr_g, slice_w_g,
+                                                                               srow0, ws.gblk, ws.gprod, ws.gflag, err_flag_dev);
+    else
+        walk_stream_kernel<false, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
+                                                                                ws.snap, ws.hub_giant, ws.ctr, spr_g, slice_w_g,
+                                                                                srow0, ws.gblk, ws.gprod, ws.gflag, err_flag_dev);
     return TPN_OK;
 }
 
@@ -2061,8 +2229,9 @@ void launch_walk_small(const StateView& v, const Workspace& ws, int E, int ds4, 
 // short-segment walker (disjoint target rows), forked from / joined back into the caller's stream
 // with events, so the caller still sees one stream-ordered call (also valid under graph capture).
 struct SideStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t stream = nullptr;          // hub walker
+    cudaStream_t stream2 = nullptr;         // streamed giants
+    cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
     int state = 0;          // 0: not created, 1: ready, -1: creation failed (run serially)
 };
 SideStream* side_stream() {
@@ -2072,8 +2241,10 @@ SideStream* side_stream() {
     SideStream& s = table[dev];
     if (s.state == 0) {
         bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&s.join2, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) (void)cudaGetLastError();
         s.state = ok ? 1 : -1;
     }
@@ -2342,22 +2513,35 @@ int update_impl(tpn_state_t* st, const MsgSource& msgs, int E, const int32_t* co
             // persistent warp walker (disjoint target rows; both read only pre-batch values)
             const bool direct = msgs.B == 0;
             SideStream* side = (g_debug_flags & TPN_DEBUG_SERIAL_WALK) ? nullptr : side_stream();
-            cudaStream_t hub_stream = stream;
+            cudaStream_t hub_stream = stream, giant_stream = stream;
             if (side != nullptr) {
                 if (cudaEventRecord(side->fork, stream) == cudaSuccess &&
-                    cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess)
+                    cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
                     hub_stream = side->stream;
-                else
+                    if (stream_mode > 0 && cudaStreamWaitEvent(side->stream2, side->fork, 0) == cudaSuccess)
+                        giant_stream = side->stream2;
+                } else {
                     (void)cudaGetLastError();
+                }
             }
-            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, chunk, srow0, err_flag_dev, hub_stream)
-                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, chunk, srow0, err_flag_dev, hub_stream);
+            if (stream_mode > 0) {
+                // first: its chains are the critical path when anything is streamed; otherwise it exits at once
+                const int src = direct ? launch_walk_stream<true>(view, ws, lazy, srow0, err_flag_dev, giant_stream)
+                                       : launch_walk_stream<false>(view, ws, lazy, srow0, err_flag_dev, giant_stream);
+                if (src != TPN_OK) return src;
+            }
+            const int hrc = direct ? launch_walk_hub2<true>(view, ws, lazy, dargs, chunk, srow0, hub_stream)
+                                   : launch_walk_hub2<false>(view, ws, lazy, dargs, chunk, srow0, hub_stream);
             if (hrc != TPN_OK) return hrc;
             if (direct) launch_walk_small<true>(view, ws, E, ds4, lazy, dargs, srow0, stream);
             else launch_walk_small<false>(view, ws, E, ds4, lazy, dargs, srow0, stream);
             if (hub_stream != stream) {
-                if (cudaEventRecord(side->join, hub_stream) != cudaSuccess ||
-                    cudaStreamWaitEvent(stream, side->join, 0) != cudaSuccess) {
+                bool ok = cudaEventRecord(side->join, hub_stream) == cudaSuccess &&
+                          cudaStreamWaitEvent(stream, side->join, 0) == cudaSuccess;
+                if (giant_stream != stream)
+                    ok = ok && cudaEventRecord(side->join2, giant_stream) == cudaSuccess &&
+                         cudaStreamWaitEvent(stream, side->join2, 0) == cudaSuccess;
+                if (!ok) {
                     set_cuda_error(cudaGetLastError());
                     return TPN_ERR_CUDA;
                 }
