@@ -886,32 +886,39 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
     n_pairs_rank, n_msgs_rank = B // world, 2 * B // world
     pair_gbs = n_pairs_rank * per_pair_B / (pair_ms * 1e-3) / 1e9
     upd_gbs = n_msgs_rank * (per_edge_B / 2) / (upd_ms * 1e-3) / 1e9
-    dominant_is_update = upd_ms >= 2 * pair_ms            # two pair-wise calls per step vs one update
+    # the dominant launch group of a step is the longest single call: the update (one per step) unless one pair-wise
+    # call alone takes longer
+    dominant_is_update = upd_ms >= pair_ms
     step_bytes = B * per_edge_B + 2 * B * per_pair_B
     block_bytes = (shape.num_layer + 1) * row_stride * 4
     state_gb = shape.node_num * block_bytes / 1e9
     front = 'routing + NVLink pull + barriers + ' if world > 1 else ''
+    step_gbs = (step_bytes / world) * K / (dev_ms * 1e-3) / 1e9          # per GPU
     roof = {'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
-            'phases': {'pairwise': {'what': front + 'tpn::pairwise_tma_kernel + tpn::head_forward_kernel, ~%d pairs per rank'
+            'phases': {'pairwise': {'what': front + 'tpn::pairwise_tma_kernel + tpn::head_tc_kernel (self.mlp on tcgen05), ~%d '
+                                            'pairs per rank; the gather kernel alone: profiles/r02m_ncu_full_step_kernels.txt'
                                             % n_pairs_rank, 'ms': pair_ms, 'achieved': pair_gbs, 'frac': pair_gbs / peak},
-                       'update': {'what': front + 'radix sort + snapshot + tpn::walk_small_kernel || tpn::walk_hub2_kernel'
-                                          ' (+ combine_giants), ~%d messages per rank' % n_msgs_rank,
-                                  'ms': upd_ms, 'achieved': upd_gbs, 'frac': upd_gbs / peak}}}
+                       'update': {'what': front + 'sort front end + snapshot + tpn::walk_small_kernel || tpn::walk_hub2_kernel || '
+                                          'tpn::walk_stream_kernel (+ combine_giants), ~%d messages per rank' % n_msgs_rank,
+                                  'ms': upd_ms, 'achieved': upd_gbs, 'frac': upd_gbs / peak},
+                       'step': {'what': 'whole step (two pair-wise calls incl. head + one update, overlapped as in `value`), '
+                                        'algorithmic bytes per GPU / step time', 'ms': dev_ms / K, 'achieved': step_gbs,
+                                'frac': step_gbs / peak}}}
     tkey = 'powerlaw_update_dram_bytes_per_call' if dominant_is_update else 'powerlaw_pairwise_dram_bytes_per_launch'
     if accumulation == 'chunked' and dominant_is_update:
         tkey = 'powerlaw_update_chunked_dram_bytes_per_call'
     if dominant_is_update:
-        roof.update(kernel='update path (radix sort + snapshot + walk_small || walk_hub2)', achieved=upd_gbs,
+        roof.update(kernel='update path (sort front end + snapshot + walk_small || walk_hub2 || walk_stream)', achieved=upd_gbs,
                     frac=upd_gbs / peak)
     else:
         roof.update(kernel='tpn::pairwise_tma_kernel (+ head)', achieved=pair_gbs, frac=pair_gbs / peak)
     # ncu DRAM bytes are a property of the N=1 launch: not carried over to the sharded runs
     roof['traffic'] = traffic_note(tkey) if world == 1 else None
     h2d = 3 * B * 8 + 2 * (2 * B * 8)
-    upd_launches = 1 + 1 + 1 + 1 + 1                            # fused front end (prep + radix passes + payload + giant
-    #                                                             ordering, one cooperative launch), snapshot, hub2, small, stamps
+    upd_launches = 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1                # fused front end (prep + radix passes), payload, giant ordering,
+    #                                                             snapshot, walk_stream, hub2, small, stamps
     if accumulation == 'chunked':
-        upd_launches += 1                                       # combine_giants
+        upd_launches -= 1                                       # no giant ordering, no walk_stream; + combine_giants
     per_step = 2 * 2 + upd_launches if world == 1 else (2 * (4 + 1 + 2) + 1 + 4 + 1 + 1 + upd_launches)
     line = {
         'metric': METRIC, 'value': B * K / (dev_ms * 1e-3), 'unit': 'edges/s', 'n_gpus': world, 'steps': K,
