@@ -183,7 +183,7 @@ int tpn_update_phase(tpn_state_t* st,
 /*   TPN_DEBUG_NO_STREAM      : no giant segment is streamed: the hub walker gathers and adds every one on the same SM.
  *   TPN_DEBUG_STREAM_ALL     : every giant segment (>= 2,048 messages of one target) is streamed — products
  *                              materialised by producer CTAs on every SM, add chains fed by bulk copies — instead of
- *                              only those above 3/8 of the call's messages; results are identical either way. */
+ *                              only those above 1/4 of the call's messages; results are identical either way. */
 #define TPN_DEBUG_NO_STREAM 32
 #define TPN_DEBUG_STREAM_ALL 64
 int tpn_set_debug_flags(int flags);

@@ -286,7 +286,7 @@ def test_update_bit_exact_with_equal_timestamps(B, N, dim, L, mode):
 def test_hub_walker_bit_exact(B, N, dim, L, skew, mode, flags):
     """Long segments (>= 64 messages on one target) leave the warp walker for the CTA-pipelined
     hub walkers (cp.async / TMA rings + mbarriers): giant (>= 2048) and regular hubs — giants STREAMED by default
-    when one of them holds more than 3/8 of the batch's messages (products materialised by producer CTAs, chains fed by
+    when one of them holds more than 1/4 of the batch's messages (products materialised by producer CTAs, chains fed by
     bulk copies; 'no-stream': never, 'stream-all': every giant) — 64-float column slices (d=210 -> 216-float rows -> 4 slices of 56/56/56/48 per row; d=1000 -> 16),
     the snapshot + all-layer launches (hub walker on the side stream concurrently with the
     short-segment walker, or serially) and the per-layer launches, eager and lazy decay.

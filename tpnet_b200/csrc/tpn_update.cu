@@ -750,15 +750,16 @@ struct GiantSmem {
 // add chain would otherwise be the critical path of the whole update.  Measured on B200 (profiles/r02_stream_giants.txt):
 // the gathering hub walker adds a giant at ~10 cycles per message, the update as a whole costs ~3 cycles per message
 // of the batch (throughput), a streamed chain ~4.5 cycles per message plus ~2.6 cycles per streamed message of extra
-// traffic spread over all SMs — so streaming pays when 10 len > 3 E + 2.6 len, i.e. len > 3/8 of the batch's messages
-// (the hub-owning rank of a sharded power-law state), and costs time below that (many mid-size giants: throughput-bound).
+// traffic spread over all SMs — so streaming pays when the giant's chain, not the batch's throughput, bounds the call.
+// Measured crossover: a giant holding 18 % of the messages (the N=1 bench batch): streaming it costs 10 % of the update;
+// 30 % (the hub-owning rank at N=2): it gains 11 %; 47 % / 63 % (N=4 / N=8): much more.  Threshold: 1/4 of the messages.
 __device__ __forceinline__ void sort_giants_body(GiantSmem& sm, uint32_t* __restrict__ hub_giant,
                                                  const uint32_t* __restrict__ slen, uint32_t* __restrict__ ctr,
                                                  uint32_t* __restrict__ gblk, uint32_t* __restrict__ gflag, Count count,
                                                  int stream_mode) {
     const uint32_t stream_min = stream_mode == 0 ? 0u
                                 : (stream_mode == 2 ? (uint32_t)kGiantMin
-                                                    : max((uint32_t)kGiantMin, (uint32_t)(((long long)count.get() * 3) >> 3)));
+                                                    : max((uint32_t)kGiantMin, (uint32_t)(count.get() >> 2)));
     const int n = (int)ctr[kCtrGiant];
     if (n < 1 || n > kGiantSortMax) return;          // ctr[kCtrStream] stays 0: the hub walker takes every giant
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
