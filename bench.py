@@ -838,6 +838,15 @@ def run_powerlaw(args, rank, world, device, K, W, sampler, accumulation=None, wi
                 if peer:
                     pos = m.routed_pair_wise_feature(s, d).feat          # zero rows past the count
                     ng = m.routed_pair_wise_feature(s, neg).feat
+                elif world == 1 and not args.no_feature_overlap:
+                    # the two decoder calls are independent: the second one (own staging ring) on the feature stream
+                    cur, fs = torch.cuda.current_stream(device), m.feature_stream()
+                    fs.wait_stream(cur)
+                    with torch.cuda.stream(fs):
+                        _, ng = m.get_pair_wise_feature(s, neg)
+                    _, pos = m.get_pair_wise_feature(s, d)
+                    cur.wait_stream(fs)
+                    ng.record_stream(cur)
                 else:
                     _, pos = m.get_pair_wise_feature(s, d)
                     _, ng = m.get_pair_wise_feature(s, neg)

@@ -998,3 +998,51 @@ def test_update_prepare_overlaps_reads_and_changes_nothing(mode):
     assert not a.update_prepare(ds[:100], dd[:100], dt[:100], next_time=t)      # single-CTA sort path: nothing to split
     a.check_errors()
     b.check_errors()
+
+
+def test_feature_stream_calls_equal_sequential_calls():
+    """The two decoder calls of a batch on two streams (module.feature_stream(): pipeline.tpnet_step, bench e2e): the
+    (src, neg) call runs on the feature stream with its own staging ring while the (src, dst) call and update_prepare
+    run on the current / prepare streams.  Same features, same state as a module that does everything in sequence —
+    through more calls than a staging ring has slots, with numpy and with device-resident ids."""
+    rng = np.random.default_rng(21)
+    N, dim, L, B = 4000, 40, 3, 5000
+    kw = dict(node_num=N, edge_num=10 * N, dim_factor=1, num_layer=L, time_decay_weight=1e-6, use_matrix=False,
+              beginning_time=0.0, not_scale=False, enforce_dim=dim)
+    torch.manual_seed(5)
+    a = RandomProjectionModule(device=DEV, decay_mode='lazy', **kw).to(DEV)
+    b = RandomProjectionModule(device=DEV, decay_mode='lazy', **kw).to(DEV)
+    b.random_projections[0].data.copy_(a.random_projections[0].data)
+    b.mlp.load_state_dict(a.mlp.state_dict())
+    t = 0.0
+    cur = torch.cuda.current_stream(DEV)
+    fs = a.feature_stream()
+    for it in range(12):
+        s = (1 + (rng.zipf(1.3, B) - 1) % (N - 1)).astype(np.int64)
+        d = rng.integers(1, N, B).astype(np.int64)
+        neg = rng.integers(1, N, B).astype(np.int64)
+        ts = np.sort(t + rng.random(B) * 5000.0)
+        t = float(ts[-1])
+        if it % 3 == 2:                                      # device-resident ids
+            s, d, neg, ts = (torch.from_numpy(x).to(DEV) for x in (s, d, neg, ts))
+        with torch.no_grad():
+            want_pos = b.get_pair_wise_feature(s, d)
+            want_neg = b.get_pair_wise_feature(s, neg)
+            a.update_prepare(s, d, ts, next_time=t)
+            fs.wait_stream(cur)
+            with torch.cuda.stream(fs):
+                got_neg = a.get_pair_wise_feature(s, neg)
+            got_pos = a.get_pair_wise_feature(s, d)
+            cur.wait_stream(fs)
+            got_neg.record_stream(cur)
+        a.update(s, d, ts, next_time=t)
+        b.update(s, d, ts, next_time=t)
+        assert torch.equal(got_pos, want_pos), it
+        assert torch.equal(got_neg, want_neg), it
+    a.materialize()
+    b.materialize()
+    for i in range(1, L + 1):
+        assert torch.equal(a.random_projections[i].data, b.random_projections[i].data), i
+    assert a._h.stager2 is not None                          # the feature stream staged through its own ring
+    a.check_errors()
+    b.check_errors()

@@ -86,7 +86,7 @@ class _Stager:
 
 class _Host:
     """Mutable host-side bookkeeping kept off the nn.Module (its __setattr__ is slow)."""
-    __slots__ = ('now', 'begin', 'epoch', 'launches', 'stager', 'st', 'st_ref', 'dev_index', 'keepalive',
+    __slots__ = ('now', 'begin', 'epoch', 'launches', 'stager', 'stager2', 'st', 'st_ref', 'dev_index', 'keepalive',
                  'device_ids_seen')
 
     def __init__(self, t0: float):
@@ -95,6 +95,7 @@ class _Host:
         self.epoch = 0
         self.launches = 0
         self.stager: Optional[_Stager] = None
+        self.stager2: Optional[_Stager] = None       # ring of the calls issued on the feature stream
         self.st: Optional[TpnState] = None
         self.st_ref = None
         self.dev_index = -1
@@ -337,10 +338,16 @@ class RandomProjectionModule(nn.Module):
             host.append(a)
             ck.append(id_kind if kind == 'id' else _lib.STAGE_RAW)
         h = self._h
+        raw = self._stream()                            # also resolves dev_index
+        if self._feature_stream is not None and raw == self._feature_stream.cuda_stream:
+            # a staging ring orders the reuse of its slots against ONE caller stream: calls on the feature stream
+            # (pipeline.tpnet_step) get their own
+            if h.stager2 is None:
+                h.stager2 = _Stager(h.dev_index)
+            return h.stager2.upload(host, ck, self.node_num, raw)
         if h.stager is None:
-            self._stream()                              # resolves dev_index
             h.stager = _Stager(h.dev_index)
-        return h.stager.upload(host, ck, self.node_num, self._stream())
+        return h.stager.upload(host, ck, self.node_num, raw)
 
     # ------------------------------------------------------------------ reference API
     def _cancel_prepare(self) -> None:
