@@ -34,19 +34,12 @@ lib.tpn_debug_hub_timeline.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
 assert lib.tpn_debug_hub_timeline(buf, n) == 0
 a = np.array(buf[:], dtype=np.int64).reshape(8, 256, 8)
 t0 = a[0, 0, 0]
-print('consumer (warp 0) per stage: [before wait, after wait, after chain, after release]')
-for b in range(200, 206):
-    print('  stage', b, (a[0, b, :4] - t0).tolist())
-d = a[0, 40:250]
-print('consumer, stages 40-120 :', 'period', np.diff(a[0, 40:120, 0]).mean(), 'wait', (a[0, 40:120, 1] - a[0, 40:120, 0]).mean())
-print('consumer, stages 170-250:', 'period', np.diff(a[0, 170:250, 0]).mean(), 'wait', (a[0, 170:250, 1] - a[0, 170:250, 0]).mean())
-print('consumer: period', np.diff(d[:, 0]).mean(), 'wait', (d[:, 1] - d[:, 0]).mean(), 'chain', (d[:, 2] - d[:, 1]).mean(),
-      'release', (d[:, 3] - d[:, 2]).mean())
-print('producer warp 1 per pass: [start, meta issued, rows issued, after wait-empty, rows arrived, stored, published]')
-for p in range(8, 14):
-    print('  pass', p, (a[1, p, :7] - t0).tolist())
-for w in range(1, 8):
-    x = a[w, 6:28]
-    print(f'producer w{w}: period', np.diff(x[:, 0]).mean(), '| meta issue', (x[:, 1] - x[:, 0]).mean(), '| shuffles+row issue',
-          (x[:, 2] - x[:, 1]).mean(), '| wait empty', (x[:, 3] - x[:, 2]).mean(), '| rows arrive', (x[:, 4] - x[:, 3]).mean(),
-          '| scale+store', (x[:, 5] - x[:, 4]).mean(), '| publish', (x[:, 6] - x[:, 5]).mean())
+print('consumer (warp 0), every 8th stage of the first chain item: [before wait, after wait, after chain, after release]')
+nst = min(256, (B + 127) // 128 // 8)
+for lo in range(0, nst, 32):
+    d = a[0, lo:min(lo + 32, nst)]
+    if len(d) < 2:
+        break
+    print('consumer, stages %4d-%4d: period per stage %.0f  wait %.0f  chain %.0f  release %.0f' % (
+        8 * lo, 8 * (lo + len(d)), np.diff(d[:, 0]).mean() / 8, (d[:, 1] - d[:, 0]).mean(), (d[:, 2] - d[:, 1]).mean(),
+        (d[:, 3] - d[:, 2]).mean()))

@@ -45,7 +45,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // MODE 2: consumer only: no loader, no barriers, the ring is filled once (the floor inside a CTA of this shape)
 // MODE 3: as 0, but the consumer also loads the first 16 values of the NEXT stage before the arrive (pipeline never drains)
 template <int MODE>
-__global__ void __launch_bounds__(256) chain_cta(const float* __restrict__ prod, int nstage, float* out, long long* cyc) {
+__global__ void __launch_bounds__(256) chain_cta(const float* __restrict__ prod0, int nstage, float* out, long long* cyc,
+                                                  size_t region_stages) {
+    const float* prod = prod0 + (size_t)blockIdx.x * region_stages * kStageFloats;
     extern __shared__ __align__(128) unsigned char raw[];
     float* ring = reinterpret_cast<float*>(raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + kStages * kStageFloats);
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(256) chain_cta(const float* __restrict__ prod,
                 const int use = b / kStages, stage = b - use * kStages;
                 if (use > 0) mbar_wait<MODE == 1 ? 100 : 0>(&empty[stage], (use - 1) & 1);
                 mbar_expect_tx(&full[stage], kStageFloats * 4);
-                bulk_g2s(ring + stage * kStageFloats, prod + (size_t)(b % 4096) * kStageFloats, kStageFloats * 4, &full[stage]);
+                bulk_g2s(ring + stage * kStageFloats, prod + (size_t)((size_t)b % region_stages) * kStageFloats, kStageFloats * 4, &full[stage]);
             }
         }
     } else if (warp == 0) {
@@ -101,32 +103,39 @@ __global__ void __launch_bounds__(256) chain_cta(const float* __restrict__ prod,
         }
         const long long t1 = clock64();
         out[lane] = acc;
-        if (lane == 0) cyc[0] = t1 - t0;
+        if (lane == 0) cyc[blockIdx.x] = t1 - t0;
     }
 }
 
 template <int MODE>
-void run(const char* name, const float* prod, float* out, long long* cyc, int nstage) {
+void run(const char* name, const float* prod, float* out, long long* cyc, int nstage, int grid, size_t region_stages) {
     const int smem = kStages * (kStageFloats * 4 + 16) + 16;
     cudaFuncSetAttribute(chain_cta<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    long long h = 0;
+    long long h[256];
     for (int rep = 0; rep < 2; ++rep) {
-        chain_cta<MODE><<<1, 256, smem>>>(prod, nstage, out, cyc);
-        cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        chain_cta<MODE><<<grid, 256, smem>>>(prod, nstage, out, cyc, region_stages);
+        cudaMemcpy(h, cyc, 8 * grid, cudaMemcpyDeviceToHost);
     }
-    printf("%-58s: %.2f cycles/message (%s)\n", name, (double)h / ((double)nstage * kMsgs), cudaGetErrorString(cudaGetLastError()));
+    long long worst = 0;
+    for (int i = 0; i < grid; ++i) worst = h[i] > worst ? h[i] : worst;
+    printf("%-58s grid %3d, %5zu stages per CTA region: %.2f cycles/message (%s)\n", name, grid, region_stages,
+           (double)worst / ((double)nstage * kMsgs), cudaGetErrorString(cudaGetLastError()));
 }
 
 int main() {
     float *prod, *out;
     long long* cyc;
-    cudaMalloc(&prod, (size_t)4096 * kStageFloats * 4);      // 32 MB: L2-resident after the first pass
-    cudaMemset(prod, 0, (size_t)4096 * kStageFloats * 4);
+    const size_t total_stages = 262144;                       // 2 GB of products
+    cudaMalloc(&prod, total_stages * kStageFloats * 4);
+    cudaMemset(prod, 0, total_stages * kStageFloats * 4);
     cudaMalloc(&out, 4096);
-    cudaMalloc(&cyc, 64);
+    cudaMalloc(&cyc, 8 * 256);
     const int nstage = 2200;
-    run<2>("consumer alone, ring filled once, no barriers", prod, out, cyc, nstage);
-    run<0>("loader spinning on try_wait + consumer as shipped", prod, out, cyc, nstage);
-    run<1>("loader backing off 100 ns between polls", prod, out, cyc, nstage);
+    run<2>("consumer alone, ring filled once, no barriers", prod, out, cyc, nstage, 1, 4096);
+    run<0>("loader + consumer as shipped, L2-resident products", prod, out, cyc, nstage, 1, 4096);
+    run<1>("... loader backing off 100 ns between polls", prod, out, cyc, nstage, 1, 4096);
+    run<0>("loader + consumer, every stage from HBM", prod, out, cyc, nstage, 1, 2200);
+    run<0>("42 chain CTAs, every stage from HBM", prod, out, cyc, nstage, 42, 2200);
+    run<0>("148 chain CTAs (one per SM), every stage from HBM", prod, out, cyc, 1700, 148, 1700);
     return 0;
 }

@@ -1471,8 +1471,10 @@ walk_small_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32_
 __device__ unsigned long long g_hub2_timeline[8 * 256 * 8];
 #define HUB2_STAMP(pass, ev) \
     do { if (work == 0 && lane == 0 && (pass) < 256) g_hub2_timeline[(warp * 256 + (pass)) * 8 + (ev)] = clock64(); } while (0)
+// every 8th stage of the first chain item, so that 256 slots cover a 2,048-stage (262,144-message) chain
 #define HUB2_STAMP_W0(pass, ev) \
-    do { if (stamp_me && lane == 0 && (pass) < 256) g_hub2_timeline[(0 * 256 + (pass)) * 8 + (ev)] = clock64(); } while (0)
+    do { if (stamp_me && lane == 0 && ((pass) & 7) == 0 && ((pass) >> 3) < 256) \
+             g_hub2_timeline[(0 * 256 + ((pass) >> 3)) * 8 + (ev)] = clock64(); } while (0)
 #else
 #define HUB2_STAMP(pass, ev) do { } while (0)
 #define HUB2_STAMP_W0(pass, ev) do { } while (0)
@@ -1702,11 +1704,10 @@ __device__ __forceinline__ void hub2_stream_feed(int warp, int lane, volatile in
                 const int nmb = min(kStreamBlock, len - first);
                 const uint32_t bytes = (uint32_t)nmb * kStreamSlice * 4u;
                 const float* src = gprod + (size_t)(head + first) * mstride + (size_t)slice * (size_t)(nmb * kStreamSlice);
-                mbar_expect_tx(&full[stage], bytes);          // one of the stage's 32 arrivals, plus the bytes
+                mbar_expect_tx(&full[stage], bytes);          // the stage's one arrival, plus the bytes
                 bulk_g2s(ring + (size_t)stage * (32 * kHub2SlotFloats), src, bytes, &full[stage]);
             }
             __syncwarp();
-            if (lane != 0) mbar_arrive(&full[stage]);
         }
     }
 }
@@ -1745,7 +1746,7 @@ walk_stream_kernel(StateView st, const uint32_t* __restrict__ skey, const uint32
     const int rs = (int)st.row_stride;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kHub2Stages; ++i) {
-            mbar_init(&full[i], 32);                   // the loader warp: lane 0 with the bytes, 31 plain arrivals
+            mbar_init(&full[i], 1);                    // the loader's expect_tx arrival; the bulk copy completes the bytes
             mbar_init(&empty[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
