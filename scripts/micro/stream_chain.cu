@@ -29,6 +29,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (SLEEP > 0) __nanosleep(SLEEP);
     }
 }
+__device__ __forceinline__ void mbar_wait_ptx(uint64_t* bar, uint32_t parity) {      // the product's wait loop
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
@@ -63,7 +74,7 @@ __global__ void __launch_bounds__(256) chain_cta(const float* __restrict__ prod0
         if (lane == 0) {
             for (int b = 0; b < nstage; ++b) {
                 const int use = b / kStages, stage = b - use * kStages;
-                if (use > 0) mbar_wait<MODE == 1 ? 100 : 0>(&empty[stage], (use - 1) & 1);
+                if (use > 0) { if (MODE == 4) mbar_wait_ptx(&empty[stage], (use - 1) & 1); else mbar_wait<MODE == 1 ? 100 : 0>(&empty[stage], (use - 1) & 1); }
                 mbar_expect_tx(&full[stage], kStageFloats * 4);
                 bulk_g2s(ring + stage * kStageFloats, prod + (size_t)((size_t)b % region_stages) * kStageFloats, kStageFloats * 4, &full[stage]);
             }
@@ -75,7 +86,7 @@ __global__ void __launch_bounds__(256) chain_cta(const float* __restrict__ prod0
         for (int b = 0; b < nstage; ++b) {
             const int use = b / kStages, stage = b - use * kStages;
             if (MODE != 2) {
-                if (!next_full) mbar_wait<0>(&full[stage], use & 1);
+                if (!next_full) { if (MODE == 4) mbar_wait_ptx(&full[stage], use & 1); else mbar_wait<0>(&full[stage], use & 1); }
                 next_full = false;
             }
             const float* xs = ring + stage * kStageFloats + lane;
@@ -105,6 +116,7 @@ __global__ void __launch_bounds__(256) chain_cta(const float* __restrict__ prod0
         out[lane] = acc;
         if (lane == 0) cyc[blockIdx.x] = t1 - t0;
     }
+    if (MODE == 4) __syncthreads();          // warps 2..7 are parked here while warps 0 and 1 work (as in the product)
 }
 
 template <int MODE>
@@ -135,6 +147,7 @@ int main() {
     run<0>("loader + consumer as shipped, L2-resident products", prod, out, cyc, nstage, 1, 4096);
     run<1>("... loader backing off 100 ns between polls", prod, out, cyc, nstage, 1, 4096);
     run<0>("loader + consumer, every stage from HBM", prod, out, cyc, nstage, 1, 2200);
+    run<4>("... other warps parked at the CTA barrier, PTX wait loops", prod, out, cyc, nstage, 1, 2200);
     run<0>("42 chain CTAs, every stage from HBM", prod, out, cyc, nstage, 42, 2200);
     run<0>("148 chain CTAs (one per SM), every stage from HBM", prod, out, cyc, 1700, 148, 1700);
     return 0;
