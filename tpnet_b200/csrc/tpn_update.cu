@@ -2179,7 +2179,7 @@ int launch_walk_stream(const StateView& v, const Workspace& ws, bool lazy, int s
     const int rs = (int)v.row_stride;
     const int spr_g = (rs + kHub2GiantFloats - 1) / kHub2GiantFloats;
     const int slice_w_g = (((rs + spr_g - 1) / spr_g) + 3) & ~3;
-    const unsigned grid = (unsigned)device_sm_count();
+    const unsigned grid = (unsigned)(device_sm_count() < 2 ? 2 : device_sm_count());      // >= 1 chaining CTA + ticket 0
     if (lazy)
         walk_stream_kernel<true, DIRECT><<<grid, kHub2Threads, smem, stream>>>(v, ws.key_a, ws.ssrc, ws.sw, ws.sslot, ws.slen,
                                                                                ws.snap, ws.hub_giant, ws.ctr, spr_g, slice_w_g,
